@@ -1,0 +1,171 @@
+/*
+ * worm_b200.h -- C ABI of libworm_b200.so: the B200 (sm_100a) replacement for the worm-algorithm
+ * hot path of saforem2/worm_algorithm.
+ *
+ * The reference has no FFI: its boundary is `subprocess.Popen` of one single-chain executable per
+ * temperature plus text files (worm_simulation.py:107-129; input line worm_simulation.py:53-55 parsed
+ * at worm_ising_2d.cpp:44; result line worm_ising_2d.cpp:189-191).  These entry points are what a
+ * binding would call instead; INTEGRATION.md shows the ctypes stub for worm_simulation.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `d_` = device pointer, `h_` = host pointer, `stream` = a
+ *     cudaStream_t passed as void* (NULL = default stream).
+ *   - the caller allocates every buffer and keeps ownership; the library never frees caller memory.
+ *   - every function returns WORM_OK (0) or a negative WORM_E_* code; worm_last_error() gives the
+ *     text for the calling thread.  No entry point has global mutable state besides that
+ *     thread-local message, so calls on different streams/threads are independent.
+ *   - device entry points are stream-ordered and do not synchronise, EXCEPT that host parameter
+ *     arrays (h_T, h_seed) are consumed before the call returns.
+ *   - `*_host` entry points take host buffers only, allocate and free their own device memory, and
+ *     synchronise before returning: they are the complete drop-in for a caller without CUDA code.
+ *
+ * Lattice conventions (worm_ising_2d.cpp:81-95,214-244): N = L*L sites, site = y*L + x, 2N bonds,
+ * bond 2*site = +x bond, bond 2*site+1 = +y bond; directions 0:+x 1:+y 2:-x 3:-y.
+ */
+#ifndef WORM_B200_H
+#define WORM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WORM_B200_ABI_VERSION 1
+
+enum {
+    WORM_OK = 0,
+    WORM_E_ARG = -1,       /* invalid argument (message says which)                              */
+    WORM_E_CUDA = -2,      /* CUDA runtime error (message carries cudaGetErrorString)            */
+    WORM_E_NOGPU = -3,     /* no sm_100 device / no device at all: there is NO CPU fallback      */
+    WORM_E_WORKSPACE = -4  /* workspace too small (see worm_*_workspace_bytes)                   */
+};
+
+enum { WORM_ALGO_TAYLOR = 0,   /* integer bond occupations, the reference's chain (worm_ising_2d.cpp:139-155) */
+       WORM_ALGO_BINARY = 1 }; /* binary bonds, tanh(K) acceptance (north star; same parity-projected law)   */
+
+/* per-chain accumulator record written by worm_philox_run: int64 acc[n_chains][WORM_ACC_STRIDE] */
+enum { WORM_ACC_Z = 0,      /* closed iterations measured          (Z of worm_ising_2d.cpp:130)   */
+       WORM_ACC_NB = 1,     /* sum of Nb over them                 (-Nb_tot of :132)               */
+       WORM_ACC_NB2 = 2,    /* sum of Nb^2                                                           */
+       WORM_ACC_N = 3,      /* sum of n = number of odd-parity bonds (count_bonds.py:110-117)        */
+       WORM_ACC_N2 = 4,     /* sum of n^2                                                            */
+       WORM_ACC_ITERS = 5,  /* measured loop iterations (steps with step >= therm)                   */
+       WORM_ACC_STRIDE = 8 };
+
+/* per-chain result record written by worm_mt_run: int64 out[n_chains][WORM_MT_STRIDE] */
+enum { WORM_MT_Z = 0, WORM_MT_NB_TOT = 1 /* negative running sum, like the reference's Nb_tot */,
+       WORM_MT_STEPS = 2, WORM_MT_NB_FINAL = 3, WORM_MT_STATUS = 4 /* 0 ok, 1 occupation overflow (>254) */,
+       WORM_MT_STRIDE = 8 };
+
+int worm_abi_version(void);
+/* copies the calling thread's last error text into buf (NUL-terminated); returns its length */
+int worm_last_error(char *buf, size_t buflen);
+/* number of visible sm_100 devices (0 if none); never fails */
+int worm_device_count(void);
+/* SM count and max opt-in shared memory per block of `device` */
+int worm_device_info(int device, int *sm_count, int *smem_optin_bytes, int *clock_khz);
+
+/* ---------------------------------------------------------------------------------------------
+ * Deterministic mode: n_chains independent copies of the reference loop (worm_ising_2d.cpp:47-57,
+ * 111-157), one thread per chain, each consuming its own MT19937 stream seeded like the reference
+ * (init_genrand((unsigned long)seed), worm_ising_2d.cpp:47 / mt19937ar.c:68-81).  Bit-exact: bond
+ * dumps, Z, Nb_tot, step_num and Nb equal the reference executable's for the same (L, T, steps, seed).
+ *
+ *   h_T[n], h_seed[n]        temperature and (double) seed per chain -- the input.txt fields
+ *   num_steps, bond_flag     as in input.txt; a chain stops at its first closed iteration with
+ *                            step >= num_steps (worm_ising_2d.cpp:133-134)
+ *   d_bonds  u8 [n][2N]      out: final occupations (what the trailing dump :160-167 writes)
+ *   d_out    i64 [n][8]      out: WORM_MT_* record
+ *   events:  at every point the reference appends an observables row (:113-119) the kernel stores
+ *            d_events[c][e] = {step_num, Z, Nb_tot} (values before that iteration's kick) for
+ *            e < max_events and, if bond_flag != 0 and d_dumps != NULL, the occupations in
+ *            d_dumps[c][e][2N].  d_n_events[c] counts all events, stored or not.
+ *   trace:   optional N_b trace: d_trace[c][k] = {step_num, Nb} at the k-th closed iteration,
+ *            k < max_trace; d_n_trace[c] counts them all.  NULL / 0 to skip.
+ *   d_workspace              worm_mt_workspace_bytes(n) bytes
+ * ------------------------------------------------------------------------------------------- */
+size_t worm_mt_workspace_bytes(int64_t n_chains);
+int worm_mt_run(int L, int64_t n_chains, const double *h_T, const double *h_seed,
+                uint64_t num_steps, int bond_flag,
+                uint8_t *d_bonds, int64_t *d_out,
+                int32_t max_events, int32_t *d_n_events, int64_t *d_events, uint8_t *d_dumps,
+                int32_t max_trace, int32_t *d_n_trace, int64_t *d_trace,
+                void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Production mode: counter-based Philox4x32-10, one call per worm step, counter = {step, chain id},
+ * key = seed, so a chain's trajectory does not depend on launch geometry, chunking or the number
+ * of GPUs.  Words: 0 kick site, 1 direction, 2 +/- coin, 3 acceptance draw -- the draw order of
+ * worm_ising_2d.cpp:128,137,141,151.
+ *
+ * Runs steps [step_begin, step_begin + n_steps) of every chain, resuming from (d_bonds, d_head,
+ * d_tail) and leaving the new state there.  Iterations with step >= therm_steps are measured into
+ * d_acc (added to what is there; see WORM_ACC_*).  Unlike the reference thermalisation
+ * really excludes the warm-up from the sums, and a run is exactly n_steps long.
+ *
+ *   algo                     WORM_ALGO_TAYLOR or WORM_ALGO_BINARY
+ *   chain_id0                global id of chain 0 of this call (chain c uses id chain_id0 + c)
+ *   h_T[n], h_seed[n]        per-chain temperature and 64-bit seed
+ *   d_hist_index i32 [n], d_hist i64 [n_hist][N]   optional G(r): every measured iteration adds 1 to
+ *                            d_hist[d_hist_index[c]][dy*L + dx], (dx,dy) = head - tail mod L, taken
+ *                            before the kick, so bin 0 collects Z.  NULL to skip.
+ *   dump_every, max_dumps    a measured closed iteration with step % dump_every == 0 stores
+ *                            d_events[c][e] = {step, Z so far, sum Nb so far} and (d_dumps != NULL)
+ *                            the occupations d_dumps[c][e][2N]; d_n_dumps[c] (in/out) counts them.
+ *                            dump_every = 0 disables.
+ *   lanes_per_chain          0 = choose; 1 = one thread per chain; 4 = quad per chain (latency mode);
+ *                            -1 = one thread per chain with bonds left in global memory (the path
+ *                            taken automatically when a lattice does not fit shared memory)
+ *   d_workspace              worm_philox_workspace_bytes(n) bytes
+ * ------------------------------------------------------------------------------------------- */
+size_t worm_philox_workspace_bytes(int64_t n_chains);
+int worm_philox_run(int L, int algo, int64_t n_chains, uint64_t chain_id0,
+                    const double *h_T, const uint64_t *h_seed,
+                    uint64_t step_begin, uint64_t n_steps, uint64_t therm_steps,
+                    uint8_t *d_bonds, int32_t *d_head, int32_t *d_tail, int64_t *d_acc,
+                    const int32_t *d_hist_index, int64_t *d_hist, int32_t n_hist,
+                    uint64_t dump_every, int32_t max_dumps, int32_t *d_n_dumps,
+                    int64_t *d_events, uint8_t *d_dumps,
+                    int lanes_per_chain, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* fixed-point acceptance constants used by the production kernels for temperature T:
+ * kfix = ceil(2^32/T), tfix = ceil(2^32 * (1/(1/T))), hfix = ceil(2^32 * tanh(1/T)) */
+int worm_thresholds(double T, uint64_t *kfix, uint64_t *tfix, uint64_t *hfix);
+
+/* ---------------------------------------------------------------------------------------------
+ * Post-processing of dumped configurations.
+ *
+ * worm_image   u8 occupations [n][2N] -> int32 image [n][2L][2L], first index = x pixel:
+ *              odd-parity bonds and both their end sites set to 1 (bonds.py:199-239,241-319).
+ * worm_block   one RG blocking step, int32 [n][W][W] -> [n][W/2][W/2] (W = 2L, even):
+ *              variant 0 = block_configs._block_config / iterated_blocking._block_config
+ *                          (block_configs.py:6-71; double_bonds_value 0 = "1+1=0" xor scheme)
+ *              variant 1 = Bonds._block_config_T (bonds.py:333-410; double_bonds_value = block_val)
+ * worm_count   n[c] = sum of pixels with (i + j) odd of int32 [n][W][W] (count_bonds.py:110-117).
+ * ------------------------------------------------------------------------------------------- */
+int worm_image(int L, int64_t n, const uint8_t *d_bonds, int32_t *d_img, void *stream);
+int worm_block(int W, int64_t n, const int32_t *d_in, int32_t *d_out,
+               int double_bonds_value, int variant, void *stream);
+int worm_count(int W, int64_t n, const int32_t *d_img, int64_t *d_count, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer drop-ins (allocate, copy in, run, copy out, free, synchronise).
+ * worm_sim_host replaces the per-temperature Popen loop of worm_simulation.py:107-129:
+ *   rng_mode 0 = deterministic MT19937 (h_seed read as double bits via h_seed_f64),
+ *   rng_mode 1 = Philox (h_seed_u64).  h_out is i64 [n][8]: WORM_MT_* or WORM_ACC_* records.
+ *   h_bonds (u8 [n][2N], may be NULL) receives the final occupations.
+ * ------------------------------------------------------------------------------------------- */
+int worm_sim_host(int L, int64_t n_chains, const double *h_T, const double *h_seed_f64,
+                  const uint64_t *h_seed_u64, uint64_t num_steps, uint64_t therm_steps,
+                  int rng_mode, int algo, int64_t *h_out, uint8_t *h_bonds);
+int worm_image_host(int L, int64_t n, const uint8_t *h_bonds, int32_t *h_img);
+int worm_block_host(int W, int64_t n, const int32_t *h_in, int32_t *h_out,
+                    int double_bonds_value, int variant);
+int worm_count_host(int W, int64_t n, const int32_t *h_img, int64_t *h_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WORM_B200_H */

@@ -1,0 +1,266 @@
+"""GPU parity tests (run on a B200: `pytest -m gpu`).  Every check goes through the C ABI
+(libworm_b200.so via worm_algorithm_b200.engine) and compares with the oracle / golden vectors.
+Bar: bit-exact (integer state, accumulators, images)."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    from worm_algorithm_b200 import engine
+    engine.lib()                      # fails loudly if the extension was not built
+    return engine
+
+
+# ------------------------------------------------------------------------------------------------
+# deterministic mode
+# ------------------------------------------------------------------------------------------------
+def test_mt_mode_matches_reference_golden(eng, ref_runs):
+    """All golden (L, T, steps, seed) cases in ONE batched launch: dumps, Z, Nb_tot, step_num, Nb."""
+    recs = [r for r in ref_runs if r["num_steps"] <= 400000]
+    by_L = {}
+    for r in recs:
+        by_L.setdefault(r["L"], []).append(r)
+    for L, group in by_L.items():
+        res = eng.run_mt(L, [r["T"] for r in group], [r["seed"] for r in group],
+                         group[0]["num_steps"], bond_flag=1, max_events=1024) \
+            if len({r["num_steps"] for r in group}) == 1 else None
+        for i, r in enumerate(group):
+            one = res if res is not None else eng.run_mt(L, [r["T"]], [r["seed"]], r["num_steps"], bond_flag=1, max_events=1024)
+            k = i if res is not None else 0
+            out = one.out[k].cpu().numpy()
+            N = L * L
+            T = r["T"]
+            fields = r["output_line"].split()
+            assert out[4] == 0
+            assert int(out[2]) == r["step_num"]
+            assert "%.12f" % (int(out[0]) / (int(out[2]) * 1.0)) == fields[3]
+            assert "%.12f" % (int(out[1]) * T / (int(out[0]) * N)) == fields[4]
+            assert int(out[3]) == r["Nb_final"]
+            ne = int(one.n_events[k])
+            assert ne == r["n_observables"]
+            if r["bond_flag"]:
+                dumps = one.dumps[k, :ne].cpu().numpy().astype(np.int32)
+                alld = np.concatenate([dumps, one.bonds[k].cpu().numpy().astype(np.int32)[None, :]], axis=0)
+                assert _sha(alld) == r["dumps_sha"]
+
+
+def test_mt_mode_long_run_survey_vector(eng):
+    # L=32, T=2.269, 1e7 steps, seed 12345
+    res = eng.run_mt(32, [2.269], [12345.0], 10000000, bond_flag=0, max_events=0)
+    out = res.out[0].cpu().numpy()
+    assert int(out[2]) == 10023006
+    assert "%.12f" % (int(out[0]) / int(out[2])) == "0.002276263229"
+    assert "%.12f" % (int(out[1]) * 2.269 / (int(out[0]) * 1024)) == "-1.407139231916"
+
+
+def test_mt_mode_batch_matches_oracle_with_trace(eng):
+    from oracle import worm_oracle as wo
+    rng = np.random.default_rng(11)
+    for L in (2, 3, 8, 13):
+        n = 40
+        T = rng.uniform(0.7, 4.0, n)
+        seeds = rng.integers(0, 2 ** 32, n).astype(np.float64) + 0.25
+        steps = 3000
+        res = eng.run_mt(L, T, seeds, steps, bond_flag=1, max_events=64, max_trace=128)
+        out = res.out.cpu().numpy()
+        for c in range(n):
+            o = wo.run_mt(L, float(T[c]), steps, float(seeds[c]), 1, max_events=64, max_trace=128)
+            assert [int(v) for v in out[c, :4]] == [o["Z"], o["Nb_tot"], o["step_num"], o["Nb_final"]]
+            assert (res.bonds[c].cpu().numpy() == o["final_bonds"]).all()
+            ne = min(o["n_events"], 64)
+            assert int(res.n_events[c]) == o["n_events"]
+            assert (res.events[c, :ne].cpu().numpy() == o["events"]).all()
+            assert (res.dumps[c, :ne].cpu().numpy() == o["dumps"]).all()
+            nt = min(o["n_trace"], 128)
+            assert int(res.n_trace[c]) == o["n_trace"]
+            assert (res.trace[c, :nt].cpu().numpy() == o["trace"]).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# production mode: every kernel variant reproduces the CPU restatement bit for bit
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("lanes", [1, 4, -1])
+@pytest.mark.parametrize("L", [3, 8, 32])
+def test_philox_matches_oracle(eng, algo, lanes, L):
+    from oracle import worm_oracle as wo
+    rng = np.random.default_rng(100 * L + 10 * algo + lanes + 1)
+    n = 37                      # not a multiple of the chains per warp: exercises dead lanes
+    T = rng.uniform(0.8, 3.5, n)
+    T[:8] = 2.269
+    seeds = rng.integers(0, 2 ** 63, n, dtype=np.uint64)
+    hidx = np.arange(n) % 3
+    steps, therm, cid0 = 2500, 400, 1000
+    st = eng.PhiloxState(L, T, seeds, algo=algo, chain_id0=cid0, hist_index=hidx, n_hist=3, max_dumps=16)
+    st.run(1000, therm_steps=therm, dump_every=50, lanes_per_chain=lanes)      # resumable: two launches
+    st.run(steps - 1000, therm_steps=therm, dump_every=50, lanes_per_chain=lanes)
+    acc = st.acc.cpu().numpy()
+    bonds = st.bonds.cpu().numpy()
+    head, tail = st.head.cpu().numpy(), st.tail.cpu().numpy()
+    nd = st.n_dumps.cpu().numpy()
+    ev = st.events.cpu().numpy()
+    dm = st.dumps.cpu().numpy()
+    hist = np.zeros((3, L * L), dtype=np.int64)
+    for c in range(n):
+        o = wo.run_philox(L, algo, cid0 + c, int(seeds[c]), float(T[c]), 0, steps, therm, hist=True,
+                          dump_every=50, max_dumps=16)
+        assert (acc[c, :6] == o["acc"][:6]).all(), (c, acc[c], o["acc"])
+        assert (bonds[c] == o["bonds"]).all()
+        assert head[c] == o["head"] and tail[c] == o["tail"]
+        assert nd[c] == o["n_dumps"]
+        k = min(o["n_dumps"], 16)
+        assert (ev[c, :k] == o["events"]).all()
+        assert (dm[c, :k] == o["dumps"]).all()
+        hist[hidx[c]] += o["hist"]
+    assert (st.hist.cpu().numpy() == hist).all()
+
+
+def test_philox_thresholds_match_oracle(eng):
+    from oracle import worm_oracle as wo
+    from worm_algorithm_b200 import _lib
+    for T in (0.5, 1.0, 1.5, 2.269185314213022, 3.5, 10.0):
+        assert _lib.thresholds(T) == wo.thresholds(T)
+
+
+def test_philox_geometry_independence(eng):
+    """Same chains, different launch geometry / chunking / chain offset -> identical results
+    (what makes 1/2/4/8-GPU runs reproduce each other)."""
+    L, n = 16, 64
+    T = np.repeat(np.linspace(1.5, 3.5, 8), 8)
+    seeds = np.arange(n, dtype=np.uint64) + 7
+    a = eng.PhiloxState(L, T, seeds, algo=0).run(5000, therm_steps=500, lanes_per_chain=1)
+    b = eng.PhiloxState(L, T, seeds, algo=0).run(1234, therm_steps=500, lanes_per_chain=4).run(3766, therm_steps=500, lanes_per_chain=-1)
+    assert (a.acc == b.acc).all() and (a.bonds == b.bonds).all()
+    # second half of the chains run as their own batch with chain_id0 = 32
+    c = eng.PhiloxState(L, T[32:], seeds[32:], algo=0, chain_id0=32).run(5000, therm_steps=500)
+    assert (a.acc[32:] == c.acc).all() and (a.bonds[32:] == c.bonds).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# post-processing
+# ------------------------------------------------------------------------------------------------
+def test_image_block_count_match_reference_golden(eng, post_golden):
+    import torch
+    g = post_golden
+    for L in (4, 8, 16):
+        tag = "img_L%d" % L
+        dumps = torch.from_numpy(g[tag + "_dumps"]).cuda()
+        imgs = eng.image(dumps, L)
+        assert (imgs.cpu().numpy() == g[tag + "_images"]).all()
+        assert (eng.block(imgs, 0, variant=1).cpu().numpy() == g[tag + "_blockT0"]).all()
+        assert (eng.block(imgs, 2, variant=1).cpu().numpy() == g[tag + "_blockT2"]).all()
+        cnt = eng.count(imgs).cpu().numpy()
+        assert (cnt == (g[tag + "_dumps"] & 1).sum(axis=1)).all()
+        assert np.mean(cnt) == g[tag + "_count"][0]
+    tags = sorted({k[:-3] for k in g.files if k.startswith("blk_") and k.endswith("_in")})
+    for tag in tags:
+        img = torch.from_numpy(g[tag + "_in"].astype(np.int32)).cuda()
+        Wo = img.shape[0] // 2
+        assert (eng.block(img, 0).cpu().numpy().reshape(-1) == g[tag + "_bc0"]).all()
+        if tag + "_bc1" in g.files:
+            assert (eng.block(img, 1).cpu().numpy().reshape(-1) == g[tag + "_bc1"]).all()
+        assert (eng.block(img, 2).cpu().numpy().reshape(-1) == g[tag + "_bc2"]).all()
+        cur, s = eng.block(img, 0), 2
+        while tag + "_ib_s%d" % s in g.files:
+            cur = eng.block(cur, 0)
+            assert (cur.cpu().numpy().reshape(-1) == g[tag + "_ib_s%d" % s]).all()
+            s += 1
+        assert Wo >= 1
+
+
+@pytest.mark.parametrize("L", [3, 5, 6, 16, 64, 128])
+def test_postproc_matches_oracle_random(eng, L):
+    import torch
+    from oracle import postproc_oracle as po
+    rng = np.random.default_rng(L)
+    n = 5 if L <= 16 else 2
+    bonds = rng.integers(0, 4, (n, 2 * L * L)).astype(np.uint8)
+    imgs = eng.image(torch.from_numpy(bonds).cuda(), L)
+    ref = np.array([po.image_from_bonds(b, L) for b in bonds])
+    assert (imgs.cpu().numpy() == ref).all()
+    # blocking on random (non-loop) 0/1/2 images, every variant
+    a = rng.integers(0, 2, (n, 2 * L, 2 * L)).astype(np.int32)
+    at = torch.from_numpy(a).cuda()
+    for v in (0, 1, 2):
+        got = eng.block(at, v, variant=0).cpu().numpy()
+        assert (got.reshape(n, -1) == np.array([po.block_config(x, 1, v) for x in a])).all()
+        got = eng.block(at, v, variant=1).cpu().numpy()
+        assert (got == np.array([po.block_config_T(x, v) for x in a])).all()
+    cnt = eng.count(at).cpu().numpy()
+    assert (cnt == po.bond_counts(a, 2 * L)).all()
+
+
+def test_full_size_pipeline_properties(eng):
+    """BASELINE config 3 sizes (L = 64, 128): size-independent properties at full size."""
+    import torch
+    for L in (64, 128):
+        T = [2.21, 2.22, 2.23, 2.24, 2.26, 2.27, 2.28, 2.269]
+        st = eng.PhiloxState(L, T, np.arange(8, dtype=np.uint64), algo=0, max_dumps=32)
+        st.run(400000, therm_steps=40000, dump_every=50)
+        nd = st.n_dumps.cpu().numpy()
+        assert (nd > 0).all()
+        k = int(min(nd.min(), 32))
+        dumps = st.dumps[:, :k]
+        imgs = eng.image(dumps, L)
+        par = (dumps & 1).to(torch.int64)
+        # (1) bond pixels == odd bonds; (2) closed configs: every site has even degree
+        assert (eng.count(imgs) == par.sum(-1)).all()
+        p4 = par.reshape(8, k, L, L, 2)
+        deg = p4[..., 0] + p4[..., 1] + torch.roll(p4[..., 0], 1, dims=3) + torch.roll(p4[..., 1], 1, dims=2)
+        assert (deg % 2 == 0).all()
+        # (3) "1+1=0" blocking keeps closed loops closed at every level down to 2x2 (even degree)
+        cur, W = imgs, 2 * L
+        while W > 4:
+            cur = eng.block(cur, 0)
+            W //= 2
+            Lc = W // 2
+            xb = cur[..., 0::2, 1::2]
+            yb = cur[..., 1::2, 0::2]
+            deg = xb + yb + torch.roll(xb, 1, dims=-1) + torch.roll(yb, 1, dims=-2)
+            assert (deg % 2 == 0).all(), (L, W)
+            site = cur[..., 0::2, 0::2]
+            assert (site == (deg > 0).to(site.dtype)).all()
+            assert cur.shape[-1] == 2 * Lc
+
+
+# ------------------------------------------------------------------------------------------------
+# host-buffer C entry points (the drop-in without torch)
+# ------------------------------------------------------------------------------------------------
+def test_host_entry_points(eng, ref_runs):
+    from worm_algorithm_b200 import _lib
+    lib = _lib.lib()
+    rec = ref_runs[2]                                      # L=8, T=2.269, 20000 steps, seed 42
+    L = rec["L"]
+    T = np.array([rec["T"]], dtype=np.float64)
+    sd = np.array([rec["seed"]], dtype=np.float64)
+    out = np.zeros((1, 8), dtype=np.int64)
+    bonds = np.zeros((1, 2 * L * L), dtype=np.uint8)
+    _lib.check(lib.worm_sim_host(L, 1, T.ctypes.data_as(_lib._pd), sd.ctypes.data_as(_lib._pd), None,
+                                 rec["num_steps"], 0, 0, 0, out.ctypes.data_as(C.c_void_p), bonds.ctypes.data_as(C.c_void_p)))
+    assert int(out[0, 2]) == rec["step_num"]
+    assert "".join(str(int(v)) for v in bonds[0]) == rec["final_bonds"]
+    img = np.zeros((1, 2 * L, 2 * L), dtype=np.int32)
+    _lib.check(lib.worm_image_host(L, 1, bonds.ctypes.data_as(C.c_void_p), img.ctypes.data_as(C.c_void_p)))
+    from oracle import postproc_oracle as po
+    assert (img[0] == po.image_from_bonds(bonds[0], L)).all()
+    blk = np.zeros((1, L, L), dtype=np.int32)
+    _lib.check(lib.worm_block_host(2 * L, 1, img.ctypes.data_as(C.c_void_p), blk.ctypes.data_as(C.c_void_p), 0, 0))
+    assert (blk[0].reshape(-1) == po.block_config(img[0], 1, 0)).all()
+    cnt = np.zeros(1, dtype=np.int64)
+    _lib.check(lib.worm_count_host(2 * L, 1, img.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)))
+    assert cnt[0] == (bonds[0] & 1).sum()
+    # error path: bad argument -> status code + message, no exception from C
+    rc = lib.worm_count_host(0, 1, img.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p))
+    assert rc == -1 and "W" in _lib.last_error()

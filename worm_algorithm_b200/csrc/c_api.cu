@@ -1,0 +1,377 @@
+// c_api.cu -- the extern "C" boundary declared in include/worm_b200.h.
+//
+// Host-side work done here and nowhere else: argument checks, the per-chain parameter records
+// (temperature -> the doubles / fixed-point constants the kernels consume, computed exactly as the
+// reference computes K and 1/K at worm_ising_2d.cpp:49-50), upload of those records into the
+// caller's workspace, and kernel launches.  There is no CPU implementation behind these entry
+// points: without an sm_100 device they return WORM_E_NOGPU.
+#include "../../include/worm_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "worm_kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(WORM_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+struct DevInfo {
+    int ok = 0, sm = 0, smem_optin = 0, clock_khz = 0, major = 0, minor = 0;
+};
+
+int current_device_info(DevInfo &d)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(WORM_E_NOGPU, "no CUDA device visible (%s); libworm_b200 has no CPU fallback",
+                    e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    }
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&d.minor, cudaDevAttrComputeCapabilityMinor, dev);
+    cudaDeviceGetAttribute(&d.sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&d.clock_khz, cudaDevAttrClockRate, dev);
+    if (d.major != 10)
+        return fail(WORM_E_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", dev, d.major, d.minor);
+    d.ok = 1;
+    return WORM_OK;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void thresholds(double T, uint64_t &kfix, uint64_t &tfix, uint64_t &hfix)
+{
+    const double K = 1.0 / T;                 // worm_ising_2d.cpp:49
+    const double inv_K = 1.0 / K;             // :50
+    kfix = (uint64_t)std::ceil(std::ldexp(K, 32));
+    tfix = (uint64_t)std::ceil(std::ldexp(inv_K, 32));
+    hfix = (uint64_t)std::ceil(std::ldexp(std::tanh(K), 32));
+}
+
+bool bad_T(double T) { return !(T > 0.0) || !std::isfinite(T) || T < 1e-3 || T > 1e6; }
+
+}  // namespace
+
+extern "C" {
+
+int worm_abi_version(void) { return WORM_B200_ABI_VERSION; }
+
+int worm_last_error(char *buf, size_t buflen)
+{
+    const size_t n = strlen(g_err);
+    if (buf && buflen) {
+        const size_t k = n < buflen - 1 ? n : buflen - 1;
+        memcpy(buf, g_err, k);
+        buf[k] = 0;
+    }
+    return (int)n;
+}
+
+int worm_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < count; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+int worm_device_info(int device, int *sm_count, int *smem_optin_bytes, int *clock_khz)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return fail(WORM_E_NOGPU, "device %d not available", device);
+    }
+    if (sm_count) cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (smem_optin_bytes) cudaDeviceGetAttribute(smem_optin_bytes, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (clock_khz) cudaDeviceGetAttribute(clock_khz, cudaDevAttrClockRate, device);
+    return WORM_OK;
+}
+
+int worm_thresholds(double T, uint64_t *kfix, uint64_t *tfix, uint64_t *hfix)
+{
+    if (bad_T(T)) return fail(WORM_E_ARG, "temperature %g out of range", T);
+    uint64_t k, t, h;
+    thresholds(T, k, t, h);
+    if (kfix) *kfix = k;
+    if (tfix) *tfix = t;
+    if (hfix) *hfix = h;
+    return WORM_OK;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+size_t worm_mt_workspace_bytes(int64_t n_chains)
+{
+    if (n_chains <= 0) return 0;
+    const size_t n_pad = align_up((size_t)n_chains, 32);
+    return align_up(n_pad * sizeof(worm::MtChain), 256) + 624 * n_pad * sizeof(uint32_t) + 256;
+}
+
+int worm_mt_run(int L, int64_t n_chains, const double *h_T, const double *h_seed,
+                uint64_t num_steps, int bond_flag,
+                uint8_t *d_bonds, int64_t *d_out,
+                int32_t max_events, int32_t *d_n_events, int64_t *d_events, uint8_t *d_dumps,
+                int32_t max_trace, int32_t *d_n_trace, int64_t *d_trace,
+                void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (L < 2 || L > 1024) return fail(WORM_E_ARG, "L = %d out of range [2, 1024]", L);
+    if (n_chains <= 0) return fail(WORM_E_ARG, "n_chains = %lld must be positive", (long long)n_chains);
+    if (!h_T || !h_seed || !d_bonds || !d_out) return fail(WORM_E_ARG, "null required pointer");
+    if (max_events < 0 || max_trace < 0) return fail(WORM_E_ARG, "negative buffer capacity");
+    if (max_events > 0 && !d_n_events) return fail(WORM_E_ARG, "d_n_events required when max_events > 0");
+    if (workspace_bytes < worm_mt_workspace_bytes(n_chains) || !d_workspace)
+        return fail(WORM_E_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, worm_mt_workspace_bytes(n_chains));
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    const size_t n_pad = align_up((size_t)n_chains, 32);
+    std::vector<worm::MtChain> prm((size_t)n_chains);
+    for (int64_t c = 0; c < n_chains; ++c) {
+        const double T = h_T[c];
+        if (bad_T(T)) return fail(WORM_E_ARG, "temperature[%lld] = %g out of range", (long long)c, T);
+        if (!(h_seed[c] >= 0.0) || h_seed[c] >= 18446744073709551616.0)
+            return fail(WORM_E_ARG, "seed[%lld] = %g must be in [0, 2^64)", (long long)c, h_seed[c]);
+        worm::MtChain &p = prm[(size_t)c];
+        p.T = T;
+        p.K = 1.0 / T;                                         // worm_ising_2d.cpp:49
+        p.inv_K = 1.0 / p.K;                                   // :50
+        p.seed = (uint32_t)(unsigned long)h_seed[c];           // :47 -> mt19937ar.c:70 (low 32 bits)
+        p.pad = 0;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)d_workspace;
+    worm::MtChain *d_prm = (worm::MtChain *)ws;
+    uint32_t *d_state = (uint32_t *)(ws + align_up(n_pad * sizeof(worm::MtChain), 256));
+    cudaError_t e = cudaMemcpyAsync(d_prm, prm.data(), prm.size() * sizeof(worm::MtChain), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "upload chain parameters");
+    const uint64_t therm = (uint64_t)(0.1 * (double)num_steps);   // worm_ising_2d.cpp:55
+    e = worm::launch_mt(L, n_chains, (int64_t)n_pad, d_prm, num_steps, therm, bond_flag, d_bonds, d_out,
+                        max_events, d_n_events, d_events, d_dumps, max_trace, d_n_trace, d_trace, d_state, st);
+    if (e != cudaSuccess) return cuda_fail(e, "worm_mt_kernel launch");
+    // cudaMemcpyAsync from pageable memory has already staged `prm`; nothing else to wait for
+    return WORM_OK;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+size_t worm_philox_workspace_bytes(int64_t n_chains)
+{
+    if (n_chains <= 0) return 0;
+    return align_up((size_t)n_chains * sizeof(worm::PhiloxChain), 256) + 256;
+}
+
+int worm_philox_run(int L, int algo, int64_t n_chains, uint64_t chain_id0,
+                    const double *h_T, const uint64_t *h_seed,
+                    uint64_t step_begin, uint64_t n_steps, uint64_t therm_steps,
+                    uint8_t *d_bonds, int32_t *d_head, int32_t *d_tail, int64_t *d_acc,
+                    const int32_t *d_hist_index, int64_t *d_hist, int32_t n_hist,
+                    uint64_t dump_every, int32_t max_dumps, int32_t *d_n_dumps,
+                    int64_t *d_events, uint8_t *d_dumps,
+                    int lanes_per_chain, void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (L < 3 || L > 1024) return fail(WORM_E_ARG, "L = %d out of range [3, 1024] (production mode)", L);
+    if (algo != WORM_ALGO_TAYLOR && algo != WORM_ALGO_BINARY) return fail(WORM_E_ARG, "algo = %d", algo);
+    if (n_chains <= 0) return fail(WORM_E_ARG, "n_chains = %lld must be positive", (long long)n_chains);
+    if (!h_T || !h_seed || !d_bonds || !d_head || !d_tail || !d_acc) return fail(WORM_E_ARG, "null required pointer");
+    if ((d_hist == nullptr) != (d_hist_index == nullptr)) return fail(WORM_E_ARG, "d_hist and d_hist_index go together");
+    if (d_hist && n_hist <= 0) return fail(WORM_E_ARG, "n_hist must be positive with d_hist");
+    if (dump_every && (max_dumps <= 0 || !d_n_dumps)) return fail(WORM_E_ARG, "dump_every needs max_dumps > 0 and d_n_dumps");
+    if (lanes_per_chain != 0 && lanes_per_chain != 1 && lanes_per_chain != 4 && lanes_per_chain != -1)
+        return fail(WORM_E_ARG, "lanes_per_chain = %d (0, 1, 4 or -1)", lanes_per_chain);
+    if (step_begin + n_steps < step_begin) return fail(WORM_E_ARG, "step range overflows");
+    if (workspace_bytes < worm_philox_workspace_bytes(n_chains) || !d_workspace)
+        return fail(WORM_E_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, worm_philox_workspace_bytes(n_chains));
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    std::vector<worm::PhiloxChain> prm((size_t)n_chains);
+    double lastT = -1.0;
+    uint64_t k = 0, t = 0, h = 0;
+    for (int64_t c = 0; c < n_chains; ++c) {
+        const double T = h_T[c];
+        if (T != lastT) {
+            if (bad_T(T)) return fail(WORM_E_ARG, "temperature[%lld] = %g out of range", (long long)c, T);
+            thresholds(T, k, t, h);
+            lastT = T;
+        }
+        prm[(size_t)c] = worm::PhiloxChain{k, t, h, h_seed[c]};
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    worm::PhiloxChain *d_prm = (worm::PhiloxChain *)d_workspace;
+    cudaError_t e = cudaMemcpyAsync(d_prm, prm.data(), prm.size() * sizeof(worm::PhiloxChain), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "upload chain parameters");
+    worm::PhiloxArgs a;
+    a.L = L; a.algo = algo; a.n_chains = n_chains; a.chain_id0 = chain_id0; a.prm = d_prm;
+    a.step_begin = step_begin; a.step_end = step_begin + n_steps; a.therm = therm_steps;
+    a.bonds = d_bonds; a.head = d_head; a.tail = d_tail; a.acc = d_acc;
+    a.hist_index = d_hist_index; a.hist = d_hist;
+    a.dump_every = dump_every; a.max_dumps = max_dumps; a.n_dumps = d_n_dumps; a.events = d_events; a.dumps = d_dumps;
+    const char *why = "";
+    e = worm::launch_philox(a, lanes_per_chain, dev.smem_optin, dev.sm, st, &why);
+    if (e != cudaSuccess) return cuda_fail(e, why[0] ? why : "worm_philox_kernel launch");
+    // cudaMemcpyAsync from pageable memory has already staged `prm`; nothing else to wait for
+    return WORM_OK;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+int worm_image(int L, int64_t n, const uint8_t *d_bonds, int32_t *d_img, void *stream)
+{
+    if (L < 3 || L > 256) return fail(WORM_E_ARG, "L = %d out of range [3, 256] for imaging", L);
+    if (n < 0 || (n > 0 && (!d_bonds || !d_img))) return fail(WORM_E_ARG, "bad n / null pointer");
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    cudaError_t e = worm::launch_image(L, n, d_bonds, d_img, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "image_kernel launch");
+    return WORM_OK;
+}
+
+int worm_block(int W, int64_t n, const int32_t *d_in, int32_t *d_out, int double_bonds_value, int variant, void *stream)
+{
+    if (W < 2 || (W & 1) || W > 65536) return fail(WORM_E_ARG, "W = %d must be even and in [2, 65536]", W);
+    if (variant != 0 && variant != 1) return fail(WORM_E_ARG, "variant = %d (0 or 1)", variant);
+    if (n < 0 || (n > 0 && (!d_in || !d_out))) return fail(WORM_E_ARG, "bad n / null pointer");
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    cudaError_t e = worm::launch_block(W, n, d_in, d_out, double_bonds_value, variant, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "block_kernel launch");
+    return WORM_OK;
+}
+
+int worm_count(int W, int64_t n, const int32_t *d_img, int64_t *d_count, void *stream)
+{
+    if (W < 1 || W > 65536) return fail(WORM_E_ARG, "W = %d out of range", W);
+    if (n < 0 || (n > 0 && (!d_img || !d_count))) return fail(WORM_E_ARG, "bad n / null pointer");
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    cudaError_t e = worm::launch_count(W, n, d_img, d_count, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "count_kernel launch");
+    return WORM_OK;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+}  // namespace
+
+int worm_sim_host(int L, int64_t n_chains, const double *h_T, const double *h_seed_f64,
+                  const uint64_t *h_seed_u64, uint64_t num_steps, uint64_t therm_steps,
+                  int rng_mode, int algo, int64_t *h_out, uint8_t *h_bonds)
+{
+    if (n_chains <= 0 || !h_T || !h_out) return fail(WORM_E_ARG, "bad n_chains / null pointer");
+    if (L < 2 || L > 1024) return fail(WORM_E_ARG, "L = %d out of range", L);
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    const size_t nb2 = 2 * (size_t)L * L;
+    DevBuf bonds, out, ws, head, tail;
+    cudaError_t e;
+    if ((e = bonds.alloc((size_t)n_chains * nb2)) != cudaSuccess) return cuda_fail(e, "cudaMalloc bonds");
+    if ((e = out.alloc((size_t)n_chains * 8 * sizeof(int64_t))) != cudaSuccess) return cuda_fail(e, "cudaMalloc out");
+    int rc;
+    if (rng_mode == 0) {
+        if (!h_seed_f64) return fail(WORM_E_ARG, "h_seed_f64 required for rng_mode 0");
+        const size_t wsb = worm_mt_workspace_bytes(n_chains);
+        if ((e = ws.alloc(wsb)) != cudaSuccess) return cuda_fail(e, "cudaMalloc workspace");
+        rc = worm_mt_run(L, n_chains, h_T, h_seed_f64, num_steps, 0, (uint8_t *)bonds.p, (int64_t *)out.p,
+                         0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, ws.p, wsb, nullptr);
+    } else if (rng_mode == 1) {
+        if (!h_seed_u64) return fail(WORM_E_ARG, "h_seed_u64 required for rng_mode 1");
+        const size_t wsb = worm_philox_workspace_bytes(n_chains);
+        if ((e = ws.alloc(wsb)) != cudaSuccess) return cuda_fail(e, "cudaMalloc workspace");
+        if ((e = head.alloc((size_t)n_chains * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc head");
+        if ((e = tail.alloc((size_t)n_chains * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc tail");
+        cudaMemsetAsync(bonds.p, 0, (size_t)n_chains * nb2, nullptr);
+        cudaMemsetAsync(out.p, 0, (size_t)n_chains * 8 * sizeof(int64_t), nullptr);
+        cudaMemsetAsync(head.p, 0, (size_t)n_chains * 4, nullptr);
+        cudaMemsetAsync(tail.p, 0, (size_t)n_chains * 4, nullptr);
+        rc = worm_philox_run(L, algo, n_chains, 0, h_T, h_seed_u64, 0, num_steps, therm_steps,
+                             (uint8_t *)bonds.p, (int32_t *)head.p, (int32_t *)tail.p, (int64_t *)out.p,
+                             nullptr, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, 0, ws.p, wsb, nullptr);
+    } else {
+        return fail(WORM_E_ARG, "rng_mode = %d (0 = MT19937, 1 = Philox)", rng_mode);
+    }
+    if (rc != WORM_OK) return rc;
+    if ((e = cudaMemcpy(h_out, out.p, (size_t)n_chains * 8 * sizeof(int64_t), cudaMemcpyDeviceToHost)) != cudaSuccess)
+        return cuda_fail(e, "copy results");
+    if (h_bonds && (e = cudaMemcpy(h_bonds, bonds.p, (size_t)n_chains * nb2, cudaMemcpyDeviceToHost)) != cudaSuccess)
+        return cuda_fail(e, "copy bonds");
+    return WORM_OK;
+}
+
+int worm_image_host(int L, int64_t n, const uint8_t *h_bonds, int32_t *h_img)
+{
+    if (n <= 0 || !h_bonds || !h_img) return fail(WORM_E_ARG, "bad n / null pointer");
+    if (L < 3 || L > 256) return fail(WORM_E_ARG, "L = %d out of range [3, 256] for imaging", L);
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    const size_t nb2 = 2 * (size_t)L * L, px = 4 * (size_t)L * L;
+    DevBuf in, out;
+    cudaError_t e;
+    if ((e = in.alloc((size_t)n * nb2)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = out.alloc((size_t)n * px * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMemcpy(in.p, h_bonds, (size_t)n * nb2, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "copy in");
+    if (int rc = worm_image(L, n, (const uint8_t *)in.p, (int32_t *)out.p, nullptr)) return rc;
+    if ((e = cudaMemcpy(h_img, out.p, (size_t)n * px * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "copy out");
+    return WORM_OK;
+}
+
+int worm_block_host(int W, int64_t n, const int32_t *h_in, int32_t *h_out, int double_bonds_value, int variant)
+{
+    if (n <= 0 || !h_in || !h_out) return fail(WORM_E_ARG, "bad n / null pointer");
+    if (W < 2 || (W & 1) || W > 65536) return fail(WORM_E_ARG, "W = %d must be even and in [2, 65536]", W);
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    const size_t pin = (size_t)W * W, pout = (size_t)(W / 2) * (W / 2);
+    DevBuf in, out;
+    cudaError_t e;
+    if ((e = in.alloc((size_t)n * pin * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = out.alloc((size_t)n * pout * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMemcpy(in.p, h_in, (size_t)n * pin * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "copy in");
+    if (int rc = worm_block(W, n, (const int32_t *)in.p, (int32_t *)out.p, double_bonds_value, variant, nullptr)) return rc;
+    if ((e = cudaMemcpy(h_out, out.p, (size_t)n * pout * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "copy out");
+    return WORM_OK;
+}
+
+int worm_count_host(int W, int64_t n, const int32_t *h_img, int64_t *h_count)
+{
+    if (n <= 0 || !h_img || !h_count) return fail(WORM_E_ARG, "bad n / null pointer");
+    if (W < 1 || W > 65536) return fail(WORM_E_ARG, "W = %d out of range", W);
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    DevBuf in, out;
+    cudaError_t e;
+    if ((e = in.alloc((size_t)n * W * W * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = out.alloc((size_t)n * 8)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMemcpy(in.p, h_img, (size_t)n * W * W * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "copy in");
+    if (int rc = worm_count(W, n, (const int32_t *)in.p, (int64_t *)out.p, nullptr)) return rc;
+    if ((e = cudaMemcpy(h_count, out.p, (size_t)n * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "copy out");
+    return WORM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,308 @@
+// postproc.cu -- imaging, RG blocking and bond counting of dumped worm configurations (sm_100a).
+//
+// All three are streaming integer kernels bounded by HBM bandwidth (no reuse beyond a 2-row
+// halo), so the design rules are: 16-byte vector loads/stores along the contiguous (second)
+// pixel index, every input sector read once from DRAM (neighbour reuse through L1/L2), grids of
+// a few waves of 148 SMs.  No tensor cores: there is no contraction here.
+//
+//   image : bonds.py:199-239 (odd-parity filter) + bonds.py:241-319 (rasterise to [2L][2L])
+//   block : block_configs.py:6-71 == iterated_blocking.py:6-59 (variant 0), bonds.py:333-410 (variant 1)
+//   count : count_bonds.py:110-117
+#include "worm_common.cuh"
+#include "worm_kernels.h"
+
+namespace worm {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// imaging.  Image pixel (px, py), first index = x pixel, flat index px*2L + py:
+//   px even, py even : site (x = px/2, y = py/2): 1 if any of its four bonds is odd
+//   px odd,  py even : +x bond of site ((px-1)/2, py/2)   (the wrap bond of x = L-1 lands on px = 2L-1)
+//   px even, py odd  : +y bond of site (px/2, (py-1)/2)
+//   px odd,  py odd  : 0
+// One block per configuration: the 2N occupation bytes are read once (coalesced) into shared
+// memory as parity bytes with a padded row pitch, then each thread writes 4 pixels (int4) of a
+// pixel row; consecutive threads -> consecutive py, so stores are fully coalesced.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int par_at(const uint8_t *sp, int pitch, int x, int y, int dir)
+{
+    return sp[y * pitch + 2 * x + dir];
+}
+
+__global__ void __launch_bounds__(256)
+image_kernel(int L, int64_t n, const uint8_t *__restrict__ bonds, int32_t *__restrict__ img, int vec_out)
+{
+    extern __shared__ __align__(16) uint8_t sp[];
+    const int pitch = 2 * L + 2;                 // bytes per lattice row y (x-major inside), padded
+    const int N = L * L, nb2 = 2 * N, W = 2 * L;
+    for (int64_t cfg = blockIdx.x; cfg < n; cfg += gridDim.x) {
+        const uint8_t *src = bonds + cfg * (int64_t)nb2;
+        __syncthreads();
+        if ((nb2 & 15) == 0 && ((uintptr_t)src & 15) == 0) {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+            for (int i = threadIdx.x; i < nb2 / 16; i += blockDim.x) {
+                const uint4 v = s4[i];
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int b = 16 * i + k;
+                    const int site = b >> 1, y = site / L, x = site - y * L;
+                    sp[y * pitch + 2 * x + (b & 1)] = (uint8_t)((w[k >> 2] >> (8 * (k & 3))) & 1u);
+                }
+            }
+        } else {
+            for (int b = threadIdx.x; b < nb2; b += blockDim.x) {
+                const int site = b >> 1, y = site / L, x = site - y * L;
+                sp[y * pitch + 2 * x + (b & 1)] = src[b] & 1u;
+            }
+        }
+        __syncthreads();
+        int32_t *dst = img + cfg * (int64_t)W * W;
+        if (vec_out) {
+            const int qn = W / 4;                // int4 per pixel row
+            for (int t = threadIdx.x; t < W * qn; t += blockDim.x) {
+                const int px = t / qn, qq = t - px * qn;
+                const int x = px >> 1, y0 = 2 * qq;        // py = 4*qq .. 4*qq+3  -> y0, y0+1
+                int4 o;
+                if (px & 1) {
+                    o.x = par_at(sp, pitch, x, y0, 0);
+                    o.y = 0;
+                    o.z = par_at(sp, pitch, x, y0 + 1, 0);
+                    o.w = 0;
+                } else {
+                    const int xm = (x == 0) ? L - 1 : x - 1;
+                    const int ym = (y0 == 0) ? L - 1 : y0 - 1;
+                    const int yb0 = par_at(sp, pitch, x, y0, 1);
+                    const int yb1 = par_at(sp, pitch, x, y0 + 1, 1);
+                    o.x = par_at(sp, pitch, x, y0, 0) | yb0 | par_at(sp, pitch, xm, y0, 0) | par_at(sp, pitch, x, ym, 1);
+                    o.y = yb0;
+                    o.z = par_at(sp, pitch, x, y0 + 1, 0) | yb1 | par_at(sp, pitch, xm, y0 + 1, 0) | yb0;
+                    o.w = yb1;
+                }
+                reinterpret_cast<int4 *>(dst)[t] = o;
+            }
+        } else {
+            for (int t = threadIdx.x; t < W * W; t += blockDim.x) {
+                const int px = t / W, py = t - px * W;
+                const int x = px >> 1, y = py >> 1;
+                int v;
+                if ((px & 1) && (py & 1)) v = 0;
+                else if (px & 1) v = par_at(sp, pitch, x, y, 0);
+                else if (py & 1) v = par_at(sp, pitch, x, y, 1);
+                else {
+                    const int xm = (x == 0) ? L - 1 : x - 1;
+                    const int ym = (y == 0) ? L - 1 : y - 1;
+                    v = par_at(sp, pitch, x, y, 0) | par_at(sp, pitch, x, y, 1) | par_at(sp, pitch, xm, y, 0) |
+                        par_at(sp, pitch, x, ym, 1);
+                }
+                dst[t] = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// blocking.  A [W][W] -> B [Wo][Wo], Wo = W/2, blocks (p, q), p, q < h = Wo/2:
+//   xb(p,q) = f(A[4p][4q+3], A[4p+2][4q+3])  -> B[2p][2q+1]        (block_configs.py:35,38,58)
+//   yb(p,q) = f(A[4p+3][4q], A[4p+3][4q+2])  -> B[2p+1][2q]        (:36,39,59)
+//   B[2p][2q] = site(xb, yb) then forced to 1 if B[2p][2q-1] or B[2p-1][2q] is non-zero, indices
+//   taken mod Wo like Python's negative indexing (:56-57,61-65); B[odd][odd] = 0.
+//   f = xor for double_bonds_value 0; otherwise (a+b == 2 ? v : a+b == 1 ? 1 : 0)  (:41-55).
+// For odd Wo the wrapped neighbour is a pixel no block ever writes, i.e. 0.
+// variant 1 (bonds.py:381-409): xor first, then pairs equal to [1,1] overwrite with block_val;
+// the fix-up sets 1 if a neighbour == 1 and then block_val if a neighbour == block_val.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int comb(int a, int b, int v, int variant)
+{
+    if (variant == 0) {
+        if (v == 0) return a ^ b;
+        const int s = a + b;
+        return s == 2 ? v : (s == 1 ? 1 : 0);
+    }
+    int r = a ^ b;
+    if (v != 0 && a == 1 && b == 1) r = v;
+    return r;
+}
+
+__device__ __forceinline__ int site_of(int xb, int yb, int ex0, int ex1, int ey0, int ey1, int v, int variant)
+{
+    if (variant == 0) return xb ? xb : yb;                 // Python `xb or yb`
+    int s = (ex0 ^ ex1) ? (ex0 ^ ex1) : (ey0 ^ ey1);       // bonds.py:388
+    if (v != 0) {
+        if (ex0 == 1 && ex1 == 1) s = v;                   // :393-395
+        if (ey0 == 1 && ey1 == 1) s = v;                   // :396-398
+    }
+    return s;
+}
+
+__device__ __forceinline__ int fixup(int s, int left, int down, int v, int variant)
+{
+    if (variant == 0) return (left || down) ? 1 : s;       // block_configs.py:64-65
+    if (left == 1 || down == 1) s = 1;                     // bonds.py:405-406
+    if (v != 0 && (left == v || down == v)) s = v;         // :407-409
+    return s;
+}
+
+// generic scalar kernel: one thread per block (p, q); any W
+__global__ void __launch_bounds__(256)
+block_kernel_scalar(int W, int64_t n, const int32_t *__restrict__ in, int32_t *__restrict__ out, int v, int variant)
+{
+    const int Wo = W / 2, h = Wo / 2;
+    const int64_t per = (int64_t)Wo * Wo;
+    const int64_t total = n * per;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t cfg = t / per;
+        const int rem = (int)(t - cfg * per);
+        const int i = rem / Wo, j = rem - i * Wo;
+        const int32_t *A = in + cfg * (int64_t)W * W;
+        int val = 0;
+        const int p = i >> 1, q = j >> 1;
+        if (p < h && q < h) {
+            auto XB = [&](int pp, int qq, int &e0, int &e1) {
+                e0 = A[(4 * pp) * W + 4 * qq + 3]; e1 = A[(4 * pp + 2) * W + 4 * qq + 3];
+                return comb(e0, e1, v, variant);
+            };
+            auto YB = [&](int pp, int qq, int &e0, int &e1) {
+                e0 = A[(4 * pp + 3) * W + 4 * qq]; e1 = A[(4 * pp + 3) * W + 4 * qq + 2];
+                return comb(e0, e1, v, variant);
+            };
+            int a0, a1, b0, b1;
+            if ((i & 1) == 0 && (j & 1) == 1) val = XB(p, q, a0, a1);
+            else if ((i & 1) == 1 && (j & 1) == 0) val = YB(p, q, b0, b1);
+            else if ((i & 1) == 0 && (j & 1) == 0) {
+                const int xb = XB(p, q, a0, a1), yb = YB(p, q, b0, b1);
+                int s = site_of(xb, yb, a0, a1, b0, b1, v, variant);
+                int left = 0, down = 0, t0, t1;
+                // B[2p][2q-1]: q > 0 -> xb(p, q-1); q == 0 -> column Wo-1: a bond column iff Wo even
+                if (q > 0) left = XB(p, q - 1, t0, t1);
+                else if ((Wo & 1) == 0) left = XB(p, h - 1, t0, t1);
+                if (p > 0) down = YB(p - 1, q, t0, t1);
+                else if ((Wo & 1) == 0) down = YB(h - 1, q, t0, t1);
+                val = fixup(s, left, down, v, variant);
+            }
+        }
+        out[t] = val;
+    }
+}
+
+// vector kernel (Wo % 4 == 0, hence W % 8 == 0): one thread per (config, block row p, 4 output
+// columns) produces B rows 2p and 2p+1 with two int4 stores from ten int4 loads; consecutive
+// threads -> consecutive columns (coalesced); the halo loads hit L1.
+__global__ void __launch_bounds__(256)
+block_kernel_vec(int W, int64_t n, const int32_t *__restrict__ in, int32_t *__restrict__ out, int v, int variant)
+{
+    const int Wo = W / 2, h = Wo / 2;
+    const int tq = Wo / 4;                        // threads per block row
+    const int64_t per = (int64_t)h * tq;
+    const int64_t total = n * per;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t cfg = t / per;
+        const int rem = (int)(t - cfg * per);
+        const int p = rem / tq, tt = rem - p * tq;           // output columns 4tt..4tt+3 = blocks q0 = 2tt, 2tt+1
+        const int32_t *A = in + cfg * (int64_t)W * W;
+        const int4 *r0 = reinterpret_cast<const int4 *>(A + (int64_t)(4 * p) * W);
+        const int4 *r2 = reinterpret_cast<const int4 *>(A + (int64_t)(4 * p + 2) * W);
+        const int4 *r3 = reinterpret_cast<const int4 *>(A + (int64_t)(4 * p + 3) * W);
+        const int pm = (p == 0) ? h - 1 : p - 1;
+        const int4 *rm = reinterpret_cast<const int4 *>(A + (int64_t)(4 * pm + 3) * W);
+        const int c0 = 2 * tt, c1 = 2 * tt + 1;               // int4 index of columns 8tt.. and 8tt+4..
+        const int cm = (tt == 0) ? 2 * tq - 1 : c0 - 1;       // int4 holding column 8tt-1 (wraps to W-1)
+        const int4 a0 = r0[c0], a1 = r0[c1], am = r0[cm];
+        const int4 b0 = r2[c0], b1 = r2[c1], bm = r2[cm];
+        const int4 y0 = r3[c0], y1 = r3[c1];
+        const int4 d0 = rm[c0], d1 = rm[c1];
+        const int xb0 = comb(a0.w, b0.w, v, variant), xb1 = comb(a1.w, b1.w, v, variant);
+        const int xbm = comb(am.w, bm.w, v, variant);
+        const int yb0 = comb(y0.x, y0.z, v, variant), yb1 = comb(y1.x, y1.z, v, variant);
+        const int dn0 = comb(d0.x, d0.z, v, variant), dn1 = comb(d1.x, d1.z, v, variant);
+        int s0 = site_of(xb0, yb0, a0.w, b0.w, y0.x, y0.z, v, variant);
+        int s1 = site_of(xb1, yb1, a1.w, b1.w, y1.x, y1.z, v, variant);
+        s0 = fixup(s0, xbm, dn0, v, variant);
+        s1 = fixup(s1, xb0, dn1, v, variant);
+        int32_t *B = out + cfg * (int64_t)Wo * Wo;
+        reinterpret_cast<int4 *>(B + (int64_t)(2 * p) * Wo)[tt] = make_int4(s0, xb0, s1, xb1);
+        reinterpret_cast<int4 *>(B + (int64_t)(2 * p + 1) * Wo)[tt] = make_int4(yb0, 0, yb1, 0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// counting: n = sum over (i + j) odd.  One warp per configuration (grid-stride), int4 loads when
+// W % 4 == 0: in an even row the odd columns are .y/.w, in an odd row .x/.z.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+count_kernel(int W, int64_t n, const int32_t *__restrict__ img, int64_t *__restrict__ cnt, int vec)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int per = W * W;
+    for (int64_t cfg = warp; cfg < n; cfg += nwarps) {
+        const int32_t *A = img + cfg * (int64_t)per;
+        long long s = 0;
+        if (vec) {
+            const int4 *A4 = reinterpret_cast<const int4 *>(A);
+            const int qn = W / 4, tot = per / 4;
+            for (int t = lane; t < tot; t += 32) {
+                const int4 vv = A4[t];
+                const int i = t / qn;
+                s += (i & 1) ? ((long long)vv.x + vv.z) : ((long long)vv.y + vv.w);
+            }
+        } else {
+            for (int t = lane; t < per; t += 32) {
+                const int i = t / W, j = t - i * W;
+                if ((i + j) & 1) s += A[t];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) cnt[cfg] = s;
+    }
+}
+
+int grid_for(int64_t work_items, int threads, int waves_cap = 148 * 16)
+{
+    int64_t b = (work_items + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > waves_cap) b = waves_cap;
+    return (int)b;
+}
+
+}  // namespace
+
+cudaError_t launch_image(int L, int64_t n, const uint8_t *d_bonds, int32_t *d_img, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    const size_t smem = (size_t)L * (2 * L + 2) + 16;
+    cudaError_t e = cudaFuncSetAttribute(image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = (int)(n < 148 * 8 ? n : 148 * 8);
+    const int vec_out = ((2 * L) % 4 == 0) && (((uintptr_t)d_img & 15) == 0);
+    image_kernel<<<grid, 256, smem, st>>>(L, n, d_bonds, d_img, vec_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_block(int W, int64_t n, const int32_t *d_in, int32_t *d_out, int dbv, int variant, cudaStream_t st)
+{
+    if (n == 0 || W < 2) return cudaSuccess;
+    const int Wo = W / 2;
+    if ((Wo & 3) == 0 && ((uintptr_t)d_in & 15) == 0 && ((uintptr_t)d_out & 15) == 0) {
+        const int64_t items = n * (int64_t)(Wo / 2) * (Wo / 4);
+        block_kernel_vec<<<grid_for(items, 256), 256, 0, st>>>(W, n, d_in, d_out, dbv, variant);
+    } else {
+        const int64_t items = n * (int64_t)Wo * Wo;
+        block_kernel_scalar<<<grid_for(items, 256), 256, 0, st>>>(W, n, d_in, d_out, dbv, variant);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count(int W, int64_t n, const int32_t *d_img, int64_t *d_count, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    const int64_t threads_needed = n * 32;
+    const int vec = (W % 4 == 0) && (((uintptr_t)d_img & 15) == 0);
+    count_kernel<<<grid_for(threads_needed, 256), 256, 0, st>>>(W, n, d_img, d_count, vec);
+    return cudaGetLastError();
+}
+
+}  // namespace worm

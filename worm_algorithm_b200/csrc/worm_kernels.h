@@ -1,0 +1,48 @@
+// worm_kernels.h -- launch prototypes between the C-ABI layer (c_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "worm_common.cuh"
+
+namespace worm {
+
+constexpr int MT_STRIDE = 8;    // int64 words per chain in the deterministic result record
+constexpr int ACC_STRIDE = 8;   // int64 words per chain in the production accumulator record
+
+struct PhiloxArgs {
+    int L;
+    int algo;                 // 0 Taylor, 1 binary
+    int64_t n_chains;
+    uint64_t chain_id0;
+    const PhiloxChain *prm;   // [n]
+    uint64_t step_begin, step_end, therm;
+    uint8_t *bonds;           // [n][2N] in/out
+    int32_t *head, *tail;     // [n] in/out
+    int64_t *acc;             // [n][ACC_STRIDE] in/out
+    const int32_t *hist_index;
+    int64_t *hist;            // [n_hist][N]
+    uint64_t dump_every;
+    int32_t max_dumps;
+    int32_t *n_dumps;
+    int64_t *events;
+    uint8_t *dumps;
+};
+
+cudaError_t launch_mt(int L, int64_t n_chains, int64_t n_pad, const MtChain *d_prm,
+                      uint64_t num_steps, uint64_t therm, int bond_flag,
+                      uint8_t *d_bonds, int64_t *d_out,
+                      int32_t max_events, int32_t *d_n_events, int64_t *d_events, uint8_t *d_dumps,
+                      int32_t max_trace, int32_t *d_n_trace, int64_t *d_trace,
+                      uint32_t *d_mt_state, cudaStream_t st);
+
+// lanes_per_chain: 1 or 4 (0 = choose).  smem_optin = max opt-in dynamic shared memory per block.
+cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, int smem_optin, int sm_count,
+                          cudaStream_t st, const char **why);
+
+cudaError_t launch_image(int L, int64_t n, const uint8_t *d_bonds, int32_t *d_img, cudaStream_t st);
+cudaError_t launch_block(int W, int64_t n, const int32_t *d_in, int32_t *d_out, int dbv, int variant,
+                         cudaStream_t st);
+cudaError_t launch_count(int W, int64_t n, const int32_t *d_img, int64_t *d_count, cudaStream_t st);
+
+}  // namespace worm

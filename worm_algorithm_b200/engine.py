@@ -1,0 +1,197 @@
+"""Torch-tensor front end of the C ABI: allocation, streams and result tensors only.
+
+PyTorch is plumbing here (device memory, the current CUDA stream, `torch.distributed`); all
+compute is in libworm_b200.so.  Every function raises if the library or a B200 is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACC_STRIDE, ALGO_BINARY, ALGO_TAYLOR, MT_STRIDE, check, lib  # noqa: F401
+
+
+def _dev(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.WormError(-3, "no CUDA device visible; worm_algorithm_b200 has no CPU fallback")
+    d = torch.device("cuda" if device is None else device)
+    if d.type != "cuda":
+        raise _lib.WormError(-3, "device %s: worm_algorithm_b200 runs on a B200 (cuda) only" % d)
+    return d
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+
+
+def _u64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint64).reshape(-1))
+
+
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class MtResult:
+    """Per-chain results of the deterministic mode (device tensors)."""
+    L: int
+    T: np.ndarray
+    out: torch.Tensor          # int64 [n, 8]   WORM_MT_* record
+    bonds: torch.Tensor        # uint8 [n, 2N]  final occupations
+    n_events: torch.Tensor     # int32 [n]
+    events: torch.Tensor       # int64 [n, max_events, 3]  {step, Z, Nb_tot}
+    dumps: torch.Tensor | None  # uint8 [n, max_events, 2N]
+    n_trace: torch.Tensor | None
+    trace: torch.Tensor | None  # int64 [n, max_trace, 2]
+
+
+def run_mt(L: int, T, seeds, num_steps: int, bond_flag: int = 0, max_events: int = 0,
+           max_trace: int = 0, device=None) -> MtResult:
+    """n independent copies of the reference loop on the reference's MT19937 stream
+    (worm_ising_2d.cpp:111-157).  T, seeds: per-chain arrays (seeds are doubles, like input.txt)."""
+    dev = _dev(device)
+    T = _f64(T)
+    seeds = _f64(seeds)
+    n = T.size
+    if seeds.size != n:
+        raise ValueError("T and seeds must have the same length")
+    nb2 = 2 * L * L
+    with torch.cuda.device(dev):
+        out = torch.zeros((n, MT_STRIDE), dtype=torch.int64, device=dev)
+        bonds = torch.zeros((n, nb2), dtype=torch.uint8, device=dev)
+        me = max(int(max_events), 0)
+        n_events = torch.zeros((n,), dtype=torch.int32, device=dev)
+        events = torch.zeros((n, max(me, 1), 3), dtype=torch.int64, device=dev)
+        dumps = torch.zeros((n, max(me, 1), nb2), dtype=torch.uint8, device=dev) if (bond_flag and me) else None
+        mt = max(int(max_trace), 0)
+        n_trace = torch.zeros((n,), dtype=torch.int32, device=dev) if mt else None
+        trace = torch.zeros((n, mt, 2), dtype=torch.int64, device=dev) if mt else None
+        wsb = lib().worm_mt_workspace_bytes(n)
+        ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+        check(lib().worm_mt_run(L, n, T.ctypes.data_as(_lib._pd), seeds.ctypes.data_as(_lib._pd),
+                                int(num_steps), int(bond_flag), _ptr(bonds), _ptr(out),
+                                me, _ptr(n_events), _ptr(events), _ptr(dumps),
+                                mt, _ptr(n_trace), _ptr(trace), _ptr(ws), wsb, _stream_ptr(dev)))
+        # the workspace must stay alive until the kernel has consumed it
+        torch.cuda.current_stream(dev).synchronize()
+    return MtResult(L, T, out, bonds, n_events, events[:, :me], dumps, n_trace, trace)
+
+
+# ---------------------------------------------------------------------------------------------
+class PhiloxState:
+    """Resumable state + accumulators of a batch of production chains (all device tensors)."""
+
+    def __init__(self, L: int, T, seeds, algo: int = ALGO_TAYLOR, chain_id0: int = 0,
+                 hist_index=None, n_hist: int = 0, max_dumps: int = 0, store_dumps: bool = True,
+                 device=None):
+        self.device = _dev(device)
+        self.L = int(L)
+        self.N = self.L * self.L
+        self.algo = int(algo)
+        self.T = _f64(T)
+        self.seeds = _u64(seeds)
+        self.n = self.T.size
+        if self.seeds.size != self.n:
+            raise ValueError("T and seeds must have the same length")
+        self.chain_id0 = int(chain_id0)
+        self.step = 0
+        dev = self.device
+        with torch.cuda.device(dev):
+            self.bonds = torch.zeros((self.n, 2 * self.N), dtype=torch.uint8, device=dev)
+            self.head = torch.zeros((self.n,), dtype=torch.int32, device=dev)
+            self.tail = torch.zeros((self.n,), dtype=torch.int32, device=dev)
+            self.acc = torch.zeros((self.n, ACC_STRIDE), dtype=torch.int64, device=dev)
+            self.hist_index = None
+            self.hist = None
+            self.n_hist = 0
+            if hist_index is not None:
+                hi = np.ascontiguousarray(np.asarray(hist_index, dtype=np.int32).reshape(-1))
+                if hi.size != self.n:
+                    raise ValueError("hist_index must have one entry per chain")
+                self.n_hist = int(n_hist) if n_hist else int(hi.max()) + 1
+                if hi.min() < 0 or hi.max() >= self.n_hist:
+                    raise ValueError("hist_index out of range")
+                self.hist_index = torch.from_numpy(hi).to(dev)
+                self.hist = torch.zeros((self.n_hist, self.N), dtype=torch.int64, device=dev)
+            self.max_dumps = int(max_dumps)
+            self.n_dumps = torch.zeros((self.n,), dtype=torch.int32, device=dev)
+            self.events = torch.zeros((self.n, max(self.max_dumps, 1), 3), dtype=torch.int64, device=dev)
+            self.dumps = (torch.zeros((self.n, self.max_dumps, 2 * self.N), dtype=torch.uint8, device=dev)
+                          if (self.max_dumps and store_dumps) else None)
+            self._wsb = lib().worm_philox_workspace_bytes(self.n)
+            self._ws = torch.empty((self._wsb,), dtype=torch.uint8, device=dev)
+
+    def run(self, n_steps: int, therm_steps: int = 0, dump_every: int = 0, lanes_per_chain: int = 0):
+        """Advance every chain by n_steps (stream-ordered, no host synchronisation)."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            check(lib().worm_philox_run(
+                self.L, self.algo, self.n, self.chain_id0,
+                self.T.ctypes.data_as(_lib._pd), self.seeds.ctypes.data_as(_lib._pu64),
+                self.step, int(n_steps), int(therm_steps),
+                _ptr(self.bonds), _ptr(self.head), _ptr(self.tail), _ptr(self.acc),
+                _ptr(self.hist_index), _ptr(self.hist), self.n_hist,
+                int(dump_every) if self.max_dumps else 0, self.max_dumps, _ptr(self.n_dumps),
+                _ptr(self.events), _ptr(self.dumps),
+                int(lanes_per_chain), _ptr(self._ws), self._wsb, _stream_ptr(dev)))
+        self.step += int(n_steps)
+        return self
+
+
+# ---------------------------------------------------------------------------------------------
+def image(bonds: torch.Tensor, L: int) -> torch.Tensor:
+    """uint8 occupations [..., 2N] -> int32 images [..., 2L, 2L]   (bonds.py:199-319)."""
+    dev = _dev(bonds.device)
+    b = bonds.contiguous()
+    if b.dtype != torch.uint8:
+        raise TypeError("bonds must be uint8")
+    lead = b.shape[:-1]
+    n = int(np.prod(lead)) if len(lead) else 1
+    if b.shape[-1] != 2 * L * L:
+        raise ValueError("last dimension must be 2*L*L")
+    with torch.cuda.device(dev):
+        out = torch.empty((n, 2 * L, 2 * L), dtype=torch.int32, device=dev)
+        check(lib().worm_image(L, n, _ptr(b), _ptr(out), _stream_ptr(dev)))
+    return out.reshape(*lead, 2 * L, 2 * L)
+
+
+def block(images: torch.Tensor, double_bonds_value: int = 0, variant: int = 0) -> torch.Tensor:
+    """One RG blocking step int32 [..., W, W] -> [..., W/2, W/2]   (block_configs.py:6-71)."""
+    dev = _dev(images.device)
+    a = images.contiguous()
+    if a.dtype != torch.int32:
+        raise TypeError("images must be int32")
+    W = a.shape[-1]
+    if a.shape[-2] != W:
+        raise ValueError("images must be square")
+    lead = a.shape[:-2]
+    n = int(np.prod(lead)) if len(lead) else 1
+    with torch.cuda.device(dev):
+        out = torch.empty((n, W // 2, W // 2), dtype=torch.int32, device=dev)
+        check(lib().worm_block(W, n, _ptr(a), _ptr(out), int(double_bonds_value), int(variant), _stream_ptr(dev)))
+    return out.reshape(*lead, W // 2, W // 2)
+
+
+def count(images: torch.Tensor) -> torch.Tensor:
+    """n = sum of pixels with (i + j) odd, int32 [..., W, W] -> int64 [...]   (count_bonds.py:110-117)."""
+    dev = _dev(images.device)
+    a = images.contiguous()
+    if a.dtype != torch.int32:
+        raise TypeError("images must be int32")
+    W = a.shape[-1]
+    lead = a.shape[:-2]
+    n = int(np.prod(lead)) if len(lead) else 1
+    with torch.cuda.device(dev):
+        out = torch.empty((n,), dtype=torch.int64, device=dev)
+        check(lib().worm_count(W, n, _ptr(a), _ptr(out), _stream_ptr(dev)))
+    return out.reshape(lead) if len(lead) else out.reshape(())

@@ -1,0 +1,211 @@
+"""`WormSimulation` -- the reference's interface (worm_simulation.py:8-188) on a B200.
+
+Same constructor arguments, same result attributes (`_T`, `_beta`, `_Z`, `_E`, `_Nb`,
+`_sim_steps`, dicts keyed `str(T).rstrip('0')` exactly like worm_simulation.py:119-126).  Where
+the reference compiles a C++ file and `Popen`s it once per temperature, this class makes ONE
+batched call into libworm_b200.so for all temperatures x replicas and gets tensors back.
+
+Two modes:
+  rng="mt19937"  deterministic: the reference's chain on the reference's MT19937 stream, bit-exact
+                 (`seeds` are the doubles the reference writes into input.txt; if omitted they are
+                 drawn like worm_simulation.py:46).  The values stored in the result dicts go
+                 through the same "%.12f" text rounding output.txt imposes (worm_ising_2d.cpp:190).
+  rng="philox"   production: counter-based RNG, fixed-length chains, warm-up excluded from the
+                 averages; `_E` = -T<Nb>/N, `_Z` = closed fraction, `_Nb` = <Nb>/N.
+
+`data_dir` (default None = nothing written) reproduces the reference's `../data` tree
+ so its analysis classes can read the results unchanged.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import compat_io, engine
+from ._lib import ACC_ITERS, ACC_N, ACC_N2, ACC_NB, ACC_NB2, ACC_Z, ALGO_BINARY, ALGO_TAYLOR
+
+
+def temperature_key(T) -> str:
+    """worm_simulation.py:121: `str(T).rstrip('0')`."""
+    return str(float(T)).rstrip('0')
+
+
+class WormSimulation(object):
+    def __init__(self, L=32, run=True, num_steps=1E7, verbose=True,
+                 T_start=1., T_end=3.5, T_step=0.1, T_arr=None, bond_flag=1,
+                 seeds=None, n_replicas=1, rng="mt19937", algo="taylor", therm_frac=0.1,
+                 write_steps=50, max_dumps=None, data_dir=None, device=None,
+                 lanes_per_chain=0, rank=0, world_size=1):
+        self._L = int(L)
+        self._num_steps = int(num_steps)
+        self._verbose = verbose
+        self._bond_flag = int(bond_flag)
+        if T_arr is None:
+            self._T_range = np.arange(T_start, T_end, T_step)        # worm_simulation.py:22
+        else:
+            self._T_range = np.asarray(T_arr, dtype=np.float64)
+        self._run = run
+        if rng not in ("mt19937", "philox"):
+            raise ValueError("rng must be 'mt19937' or 'philox'")
+        if algo not in ("taylor", "binary"):
+            raise ValueError("algo must be 'taylor' or 'binary'")
+        if rng == "mt19937" and algo != "taylor":
+            raise ValueError("the deterministic mode is the reference's Taylor-expansion chain")
+        self._rng = rng
+        self._algo = ALGO_TAYLOR if algo == "taylor" else ALGO_BINARY
+        self._n_replicas = int(n_replicas)
+        self._therm_frac = float(therm_frac)
+        self._write_steps = int(write_steps)
+        self._max_dumps = max_dumps
+        self._device = device
+        self._lanes = int(lanes_per_chain)
+        self._rank, self._world = int(rank), int(world_size)
+        self._seeds = seeds
+        self._tree = compat_io.DataTree(data_dir, self._L) if data_dir is not None else None
+        self.results = None
+        if self._run:
+            self.remove_old_data()
+            self.run()
+
+    # -- reference methods that have no work left to do -----------------------------------------
+    def make(self):
+        """The reference recompiles its C++ here (worm_simulation.py:69-89); the CUDA library is
+        prebuilt, so this only checks that it loads."""
+        engine.lib()
+
+    def prepare_input(self, T, num_steps):
+        """worm_simulation.py:44-57 draws `seed = T + randint(1e4) * rand()`; kept for callers that
+        want the reference's (unseeded) seed law."""
+        return T + np.random.randint(1E4) * np.random.rand()
+
+    def remove_old_data(self):
+        if self._tree is not None:
+            self._tree.remove_old_bonds()
+
+    def clean(self):
+        pass
+
+    # -------------------------------------------------------------------------------------------
+    def _chain_table(self):
+        """(T per chain, replica index per chain, temperature index per chain); temperatures fastest,
+        so a contiguous shard of the chain range holds every temperature."""
+        nT, R = len(self._T_range), self._n_replicas
+        t_idx = np.tile(np.arange(nT), R)          # replica-major: chain c = replica * nT + t
+        r_idx = np.repeat(np.arange(R), nT)
+        return np.asarray(self._T_range, dtype=np.float64)[t_idx], r_idx, t_idx
+
+    def run(self):
+        self._T = []
+        self._beta, self._Z, self._E, self._Nb, self._sim_steps = {}, {}, {}, {}, {}
+        if len(self._T_range) == 0:
+            return
+        if self._rng == "mt19937":
+            self._run_mt()
+        else:
+            self._run_philox()
+        if self._tree is not None:
+            self._tree.write_headers()
+
+    # -- deterministic mode ---------------------------------------------------------------------
+    def _run_mt(self):
+        L = self._L
+        Tc, r_idx, t_idx = self._chain_table()
+        # the executable reads T from "%.12f" text (worm_simulation.py:53, worm_ising_2d.cpp:44)
+        Tc = np.array([float("%.12f" % t) for t in Tc])
+        n = Tc.size
+        if self._seeds is None:
+            seeds = np.array([self.prepare_input(t, self._num_steps) for t in Tc])
+        else:
+            seeds = np.asarray(self._seeds, dtype=np.float64).reshape(-1)
+            if seeds.size == len(self._T_range) and self._n_replicas > 1:
+                seeds = seeds[t_idx] + 10007.0 * r_idx
+            if seeds.size != n:
+                raise ValueError("seeds: one per temperature (x replica)")
+        # "%.32f" text round trip of the seed is exact for doubles of this size (worm_simulation.py:53)
+        want_dumps = bool(self._bond_flag)
+        max_events = self._max_dumps
+        if max_events is None:
+            # every closed iteration at a multiple of 50 after warm-up is an event; Z_av <= ~0.5
+            max_events = min(int(0.9 * self._num_steps / self._write_steps) + 2, 4096)
+        res = engine.run_mt(L, Tc, seeds, self._num_steps, bond_flag=self._bond_flag,
+                            max_events=max_events, device=self._device)
+        out = res.out.cpu().numpy()
+        n_ev = res.n_events.cpu().numpy()
+        self.results = dict(T=Tc, seeds=seeds, replica=r_idx, out=res.out, bonds=res.bonds,
+                            n_events=res.n_events, events=res.events, dumps=res.dumps, mode="mt19937")
+        if (out[:, 4] != 0).any():
+            raise RuntimeError("bond occupation exceeded 254 (uint8 storage)")
+        events = res.events.cpu().numpy() if (self._tree is not None) else None
+        dumps = res.dumps.cpu().numpy() if (self._tree is not None and want_dumps and res.dumps is not None) else None
+        final = res.bonds.cpu().numpy() if (self._tree is not None and want_dumps) else None
+        N = L * L
+        per_T = {}
+        for c in range(n):
+            T = float(Tc[c])
+            Z, nbt, step, nbf = (int(v) for v in out[c, :4])
+            if self._verbose:
+                print("Running L = {}, T = {}, num_steps: {}".format(L, T, self._num_steps))
+            if self._tree is not None:
+                k = min(int(n_ev[c]), max_events)
+                self._tree.write_chain(T, Z, nbt, step, nbf, events[c, :k],
+                                       dumps[c, :k] if dumps is not None else None,
+                                       final[c] if final is not None else None)
+            line = compat_io.output_line(L, T, Z, nbt, step).split()
+            # what np.loadtxt(output.txt) hands to worm_simulation.py:119-125
+            vals = [float(x) for x in line]
+            per_T.setdefault(temperature_key(vals[1]), []).append(vals)
+        for key, rows in per_T.items():
+            a = np.mean(np.array(rows), axis=0) if len(rows) > 1 else np.array(rows[0])
+            self._beta[key], self._Z[key], self._E[key], self._Nb[key], self._sim_steps[key] = a[2], a[3], a[4], a[5], a[6]
+            self._T.append(rows[0][1])
+
+    # -- production mode ------------------------------------------------------------------------
+    def _run_philox(self):
+        import torch
+        from . import dist
+        L = self._L
+        N = L * L
+        Tc, r_idx, t_idx = self._chain_table()
+        n_all = Tc.size
+        nT = len(self._T_range)
+        if self._seeds is None:
+            seeds = r_idx.astype(np.uint64)
+        else:
+            seeds = np.asarray(self._seeds, dtype=np.uint64).reshape(-1)
+            if seeds.size == self._n_replicas and self._n_replicas != n_all:
+                seeds = seeds[r_idx]
+            elif seeds.size == nT and nT != n_all:
+                seeds = seeds[t_idx] + np.uint64(1000003) * r_idx.astype(np.uint64)
+            if seeds.size != n_all:
+                raise ValueError("seeds: one per replica, per temperature, or per chain")
+        # Shard: contiguous block of the global chain range per rank.  Chain ids are global (they are
+        # the Philox counter), so the reduced sums do not depend on the number of ranks.
+        c0, c1 = dist.shard_range(n_all, self._rank, self._world)
+        therm = int(self._therm_frac * self._num_steps)
+        max_dumps = self._max_dumps
+        if max_dumps is None:
+            max_dumps = 64 if self._bond_flag else 0
+        per_T = torch.zeros((nT, 8), dtype=torch.int64)
+        st = None
+        if c1 > c0:
+            st = engine.PhiloxState(L, Tc[c0:c1], seeds[c0:c1], algo=self._algo, chain_id0=c0,
+                                    max_dumps=max_dumps, store_dumps=bool(self._bond_flag), device=self._device)
+            st.run(self._num_steps, therm_steps=therm, dump_every=self._write_steps if max_dumps else 0,
+                   lanes_per_chain=self._lanes)
+            ti = torch.from_numpy(t_idx[c0:c1].astype(np.int64)).to(st.acc.device)
+            per_T = torch.zeros((nT, 8), dtype=torch.int64, device=st.acc.device).index_add_(0, ti, st.acc)
+        per_T = dist.allreduce_sum(per_T, self._world)
+        self.results = dict(T=Tc[c0:c1], seeds=seeds[c0:c1], replica=r_idx[c0:c1], t_index=t_idx[c0:c1],
+                            chain_range=(c0, c1), acc=(st.acc if st is not None else None), state=st,
+                            per_T=per_T, mode="philox", therm=therm)
+        a = per_T.cpu().numpy().astype(np.float64)
+        for ti_, T in enumerate(self._T_range):
+            Z = a[ti_, ACC_Z]
+            key = temperature_key(T)
+            self._T.append(float(T))
+            self._beta[key] = 1.0 / float(T)
+            self._Z[key] = Z / max(a[ti_, ACC_ITERS], 1.0)
+            self._E[key] = -float(T) * (a[ti_, ACC_NB] / max(Z, 1.0)) / N
+            self._Nb[key] = (a[ti_, ACC_NB] / max(Z, 1.0)) / N
+            self._sim_steps[key] = float(self._num_steps)
+            if self._verbose:
+                print("Ran L = {}, T = {}, num_steps: {} x {} replicas".format(L, T, self._num_steps, self._n_replicas))
