@@ -175,7 +175,7 @@ def gen_post():
         # count on the images with the reference's CountBonds._count_bonds
         cb = ref_cb.CountBonds.__new__(ref_cb.CountBonds)
         cb._width = 2 * L
-        flat = imgs.reshape(imgs.shape[0], -1)
+        flat = imgs[keep].reshape(imgs[keep].shape[0], -1)
         g[tag + "_count"] = np.array(cb._count_bonds(flat), dtype=np.float64)
         nblk = 3
         val, err = cb._count_bonds_with_err(flat, nblk)
