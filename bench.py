@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- worm steps/s (whole job) for the L=32 Ising temperature sweep (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path, all host cores
+
+Workload: L = 32, T_i = 1.5 + 2 i / 63 (i = 0..63) x 64 seed replicas = 4096
+independent Markov chains PER GPU, 1e7 worm steps each (the reference's default num_steps,
+worm_simulation.py:14), empty initial bonds, 10 % warm-up excluded from the sums.  One bench
+"step" = one pass of the hot path over that batch (4.096e10 worm steps per GPU).  Chains shard
+over ranks by replica (weak scaling: rank r owns replicas [64 r, 64 r + 64) of every temperature),
+no data-path collective; the per-temperature accumulator block is all-reduced once per pass.
+
+Numbers:
+  value  device-timed (CUDA events on the launching stream, summed over the K passes, max over
+         ranks): state, parameters and accumulators already resident in HBM.
+  e2e    the same pass through the public API `WormSimulation(...)` with host arrays in and the
+         reference's result dicts (host floats) out: allocation, H2D of the per-chain parameter
+         records, the kernel, the per-temperature reduction, the all-reduce and the D2H of the
+         reduced sums are all inside the timed region (wall clock around a synchronised call).
+  roofline        SM integer-issue roofline of the worm kernel (64 thread-instr/step).
+  roofline_blocking  HBM roofline of the RG blocking kernel (20 L^2 bytes per config per level).
+  cpu_baseline    the UNMODIFIED reference executable (oracle/_ref) on all host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "worm steps/sec (whole box) for L=32 Ising T-sweep"
+UNIT = "worm steps/s"
+L_BENCH = 32
+N_T = 64
+N_REP = 64                       # seed replicas per temperature per GPU
+I_ALG = 64                       # algorithmic integer thread-instructions per worm step
+
+
+def sweep_temperatures():
+    return 1.5 + 2.0 * np.arange(N_T) / 63.0
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks: nvidia-smi sampled DURING the timed region
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.p = None
+        self.t = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.p = None
+            return
+        self.t = threading.Thread(target=self._pump, daemon=True)
+        self.t.start()
+
+    def _pump(self):
+        for line in self.p.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(power))}
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference CPU path (the UNMODIFIED executable when oracle/_ref travelled, else our C port)
+# --------------------------------------------------------------------------------------------------
+def _port_worker(args):
+    from oracle import worm_oracle as wo
+    T, seed, steps = args
+    o = wo.run_mt(L_BENCH, float(T), int(steps), float(seed), 0, max_events=0)
+    return o["step_num"]
+
+
+def cpu_reference_pass(num_steps: int, runs_per_core: int, cores: int, seed0: int = 1):
+    """One bounded sample of the workload on all host cores: `cores * runs_per_core` chains of the
+    sweep (temperatures round-robin), `num_steps` steps each, `cores` at a time.
+    Returns (worm steps done, wall seconds, kind)."""
+    from oracle import ref_runner as rr
+    temps = sweep_temperatures()
+    n_runs = cores * runs_per_core
+    tl = [temps[(i * 7) % N_T] for i in range(n_runs)]      # stride through the sweep
+    if rr.have_ref():
+        steps, wall, _ = rr.time_ref_all_cores(L_BENCH, tl, num_steps, cores, seed0=seed0, bond_flag=0)
+        return steps, wall, "reference"
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        done = pool.map(_port_worker, [(T, seed0 + i, num_steps) for i, T in enumerate(tl)], chunksize=1)
+    return int(sum(done)), time.perf_counter() - t0, "port"
+
+
+def run_reference_arm(a) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    # a step = one bounded sample: every core runs `runs_per_core` chains of a.ref_steps steps
+    for _ in range(a.warmup):
+        cpu_reference_pass(a.ref_steps // 10, 1, cores)
+    tot_steps, tot_wall, kind = 0, 0.0, "reference"
+    for k in range(a.steps):
+        s, w, kind = cpu_reference_pass(a.ref_steps, a.ref_runs_per_core, cores, seed0=1 + 1000 * k)
+        tot_steps += s
+        tot_wall += w
+    value = tot_steps / tot_wall
+    sample = "%d chains/step (%d per core) x %d steps of the L=32 sweep, bond_flag=0" % (
+        cores * a.ref_runs_per_core, a.ref_runs_per_core, a.ref_steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot_wall / max(a.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64",
+        "data": "synthetic",
+        "config": workload_config(a, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, world: int) -> dict:
+    return {"workload": "L=32 temperature sweep: 64 temperatures in [1.5,3.5] x 64 seed replicas per GPU "
+                        "(BASELINE.json configs[1]); %d worm steps per chain" % a.num_steps,
+            "L": L_BENCH, "n_temperatures": N_T, "replicas_per_gpu": N_REP, "chains_per_gpu": N_T * N_REP,
+            "chains_total": N_T * N_REP * world, "worm_steps_per_chain": a.num_steps,
+            "therm_frac": 0.1, "algo": a.algo, "rng": "philox4x32-10",
+            "sharding": "replicas over ranks, one all-reduce of the per-T sums per pass",
+            "l2": "256 MiB scratch write between timed passes (outside the event pairs); chain state is reset each pass"}
+
+
+# --------------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------------
+def run_b200_arm(a) -> None:
+    import torch
+    import torch.distributed as td
+    from worm_algorithm_b200 import _lib, engine
+    from worm_algorithm_b200.worm_simulation import WormSimulation
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        td.init_process_group("nccl", device_id=dev)
+    _lib.lib()                                                    # fail loudly if the .so is missing
+
+    algo = engine.ALGO_TAYLOR if a.algo == "taylor" else engine.ALGO_BINARY
+    temps = sweep_temperatures()
+    n = N_T * N_REP
+    # replica-major chain table, global replica index = rank * N_REP + r  (== WormSimulation's layout)
+    t_idx = np.tile(np.arange(N_T), N_REP)
+    r_idx = np.repeat(np.arange(N_REP), N_T) + rank * N_REP
+    T_chain = temps[t_idx]
+    seeds = r_idx.astype(np.uint64)
+    chain_id0 = rank * n
+    therm = int(0.1 * a.num_steps)
+
+    st = engine.PhiloxState(L_BENCH, T_chain, seeds, algo=algo, chain_id0=chain_id0, device=dev,
+                            group_index=t_idx, n_groups=N_T)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def one_pass():
+        st.reset()
+        st.run(a.num_steps, therm_steps=therm, lanes_per_chain=a.lanes)
+        per_T = st.group_acc
+        if world > 1:
+            td.all_reduce(per_T, op=td.ReduceOp.SUM)
+        return per_T
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(a.warmup):
+        one_pass()
+        flush.fill_(1)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    per_T = None
+    for k in range(a.steps):
+        ev[k][0].record(stream)
+        st.reset()
+        kev[k][0].record(stream)
+        st.run(a.num_steps, therm_steps=therm, lanes_per_chain=a.lanes)
+        kev[k][1].record(stream)
+        per_T = st.group_acc
+        if world > 1:
+            td.all_reduce(per_T, op=td.ReduceOp.SUM)
+        ev[k][1].record(stream)
+        flush.fill_(k)                                            # L2 flush, outside the event pair
+    barrier()
+    t_wall1 = time.perf_counter()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    kern_ms = sum(e0.elapsed_time(e1) for e0, e1 in kev)
+    tt = torch.tensor([dev_ms, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(tt, op=td.ReduceOp.MAX)
+    dev_ms, kern_ms = float(tt[0]), float(tt[1])
+    steps_per_pass_job = float(n) * a.num_steps * world
+    value = steps_per_pass_job * a.steps / (dev_ms * 1e-3)
+    per_T_host = per_T.cpu().numpy()
+
+    # ---- e2e through the public API (host arrays in, host result dicts out) ----------------------
+    def e2e_pass():
+        sim = WormSimulation(L=L_BENCH, run=True, num_steps=a.num_steps, verbose=False, T_arr=temps, bond_flag=0,
+                             n_replicas=N_REP * world, rng="philox", algo=a.algo, therm_frac=0.1,
+                             device=dev, lanes_per_chain=a.lanes, rank=rank, world_size=world)
+        return sim
+    e2e_pass()
+    barrier()
+    t0 = time.perf_counter()
+    sim = None
+    for _ in range(a.e2e_steps):
+        sim = e2e_pass()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(te, op=td.ReduceOp.MAX)
+    e2e_value = steps_per_pass_job * a.e2e_steps / float(te[0])
+    h2d = n * 32 + n * 4                      # PhiloxChain records + group index
+    d2h = N_T * 8 * 8                         # reduced per-temperature sums
+
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return
+
+    # ---- physics sanity of the timed result (cheap; not a parity claim) ---------------------------
+    from worm_algorithm_b200._lib import ACC_NB, ACC_Z
+    Ts = temps
+    E = -Ts * (per_T_host[:, ACC_NB] / np.maximum(per_T_host[:, ACC_Z], 1)) / (L_BENCH * L_BENCH)
+    e2e_E = np.array([sim._E[k] for k in sorted(sim._E, key=float)])
+
+    # ---- rooflines -----------------------------------------------------------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    f_max = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    issue_peak = sm_count * 128 * f_max                            # thread-instructions / s
+    kern_rate = float(n) * a.num_steps * a.steps / (kern_ms * 1e-3)   # per GPU, kernel only
+    achieved = kern_rate * I_ALG
+    roofline = {"bound": "issue", "kernel": "worm_philox_kernel", "achieved": achieved / 1e9, "peak": issue_peak / 1e9,
+                "unit": "G thread-instr/s", "frac": achieved / issue_peak, "traffic": None,
+                "alg_instr_per_worm_step": I_ALG, "kernel_ms_per_launch": kern_ms / a.steps,
+                "worm_steps_per_s_per_gpu": kern_rate,
+                "peak_source": "148 SM x 128 lanes x sm_max_mhz (MEASURED_PEAKS.json)" if peaks else "fallback 1965 MHz",
+                "cycles_per_step_per_chain": f_max * n / kern_rate}
+    roofline_blocking = bench_blocking(torch, engine, dev, peaks)
+    cpu = None
+    if world == 1 and not a.no_cpu:
+        cores = host_cores()
+        s, w, kind = cpu_reference_pass(a.cpu_steps, a.cpu_runs_per_core, cores)
+        cpu = {"value": s / w, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "%d chains (%d per core) x %d steps of the same L=32 sweep, bond_flag=0, %.1f s wall" % (
+                   cores * a.cpu_runs_per_core, a.cpu_runs_per_core, a.cpu_steps, w)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32/uint8 state, u32 Philox, int64 accumulators", "data": "synthetic",
+        "config": workload_config(a, world),
+        "sweeps_per_s": value / (2 * L_BENCH * L_BENCH),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "WormSimulation(L=32, T_arr=64 temps, n_replicas=64/GPU, rng='philox')", "passes": a.e2e_steps},
+        "gpu_launches": a.steps * st.launches_per_run,
+        "clocks": clocks,
+        "roofline": roofline,
+        "roofline_blocking": roofline_blocking,
+        "cpu_baseline": cpu,
+        "check": {"E_T1.5": float(E[0]), "E_T3.5": float(E[-1]), "e2e_E_T1.5": float(e2e_E[0]),
+                  "kaufman_E_T1.5": -1.9511165659, "kaufman_E_T3.5": -0.6601217470},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+
+
+def bench_blocking(torch, engine, dev, peaks) -> dict:
+    """HBM roofline of the RG blocking kernel at L=64 (int32 [n,128,128] -> [n,64,64]), inputs larger than L2."""
+    L, n = 64, 8192                                            # 512 MiB in, 128 MiB out
+    img = (torch.rand((n, 2 * L, 2 * L), device=dev) < 0.2).to(torch.int32)
+    for _ in range(3):
+        out = engine.block(img, 0)
+    torch.cuda.synchronize(dev)
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = engine.block(img, 0)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    alg = 20.0 * L * L * n
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    del out
+    return {"bound": "hbm", "kernel": "block_kernel_vec", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak,
+            "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+            "alg_bytes_per_config": 20 * L * L, "configs_per_launch": n, "ms_per_launch": ms,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}
+
+
+def main() -> None:
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--num-steps", type=int, default=10_000_000, help="worm steps per chain per pass")
+    p.add_argument("--algo", default="taylor", choices=["taylor", "binary"])
+    p.add_argument("--lanes", type=int, default=0)
+    p.add_argument("--e2e-steps", type=int, default=2)
+    p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--cpu-steps", type=int, default=10_000_000)
+    p.add_argument("--cpu-runs-per-core", type=int, default=2)
+    p.add_argument("--ref-steps", type=int, default=10_000_000)
+    p.add_argument("--ref-runs-per-core", type=int, default=2)
+    a = p.parse_args()
+    a.warmup = max(a.warmup, 0)
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_b200_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -108,9 +108,13 @@ int worm_mt_run(int L, int64_t n_chains, const double *h_T, const double *h_seed
  *   algo                     WORM_ALGO_TAYLOR or WORM_ALGO_BINARY
  *   chain_id0                global id of chain 0 of this call (chain c uses id chain_id0 + c)
  *   h_T[n], h_seed[n]        per-chain temperature and 64-bit seed
- *   d_hist_index i32 [n], d_hist i64 [n_hist][N]   optional G(r): every measured iteration adds 1 to
- *                            d_hist[d_hist_index[c]][dy*L + dx], (dx,dy) = head - tail mod L, taken
- *                            before the kick, so bin 0 collects Z.  NULL to skip.
+ *   d_group_index i32 [n]    optional: group (e.g. temperature index) of every chain, < n_groups
+ *   d_hist i64 [n_groups][N] optional G(r) (needs d_group_index): every measured iteration adds 1 to
+ *                            d_hist[group][dy*L + dx], (dx,dy) = head - tail mod L, taken before the
+ *                            kick, so bin 0 collects Z.  NULL to skip.
+ *   d_group_acc i64 [n_groups][8]  optional (needs d_group_index): what this call added to each chain's
+ *                            WORM_ACC_* record is also added (atomically) to its group's record, so a
+ *                            caller that only wants per-temperature sums reads n_groups records back.
  *   dump_every, max_dumps    a measured closed iteration with step % dump_every == 0 stores
  *                            d_events[c][e] = {step, Z so far, sum Nb so far} and (d_dumps != NULL)
  *                            the occupations d_dumps[c][e][2N]; d_n_dumps[c] (in/out) counts them.
@@ -125,7 +129,7 @@ int worm_philox_run(int L, int algo, int64_t n_chains, uint64_t chain_id0,
                     const double *h_T, const uint64_t *h_seed,
                     uint64_t step_begin, uint64_t n_steps, uint64_t therm_steps,
                     uint8_t *d_bonds, int32_t *d_head, int32_t *d_tail, int64_t *d_acc,
-                    const int32_t *d_hist_index, int64_t *d_hist, int32_t n_hist,
+                    const int32_t *d_group_index, int32_t n_groups, int64_t *d_hist, int64_t *d_group_acc,
                     uint64_t dump_every, int32_t max_dumps, int32_t *d_n_dumps,
                     int64_t *d_events, uint8_t *d_dumps,
                     int lanes_per_chain, void *d_workspace, size_t workspace_bytes, void *stream);

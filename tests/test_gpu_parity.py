@@ -103,7 +103,7 @@ def test_philox_matches_oracle(eng, algo, lanes, L):
     seeds = rng.integers(0, 2 ** 63, n, dtype=np.uint64)
     hidx = np.arange(n) % 3
     steps, therm, cid0 = 2500, 400, 1000
-    st = eng.PhiloxState(L, T, seeds, algo=algo, chain_id0=cid0, hist_index=hidx, n_hist=3, max_dumps=16)
+    st = eng.PhiloxState(L, T, seeds, algo=algo, chain_id0=cid0, group_index=hidx, n_groups=3, hist=True, max_dumps=16)
     st.run(1000, therm_steps=therm, dump_every=50, lanes_per_chain=lanes)      # resumable: two launches
     st.run(steps - 1000, therm_steps=therm, dump_every=50, lanes_per_chain=lanes)
     acc = st.acc.cpu().numpy()
@@ -125,6 +125,9 @@ def test_philox_matches_oracle(eng, algo, lanes, L):
         assert (dm[c, :k] == o["dumps"]).all()
         hist[hidx[c]] += o["hist"]
     assert (st.hist.cpu().numpy() == hist).all()
+    gacc = np.zeros((3, 8), dtype=np.int64)
+    np.add.at(gacc, hidx, acc)
+    assert (st.group_acc.cpu().numpy() == gacc).all()
 
 
 def test_philox_thresholds_match_oracle(eng):

@@ -1,0 +1,17 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, smoke, bench, then (only if those passed) the ncu captures.
+set -x
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/smoke.log
+python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
+cat gpurun_out/bench_ref.json
+NCU_CMD="python bench.py --steps 1 --warmup 3 --num-steps 200000 --no-cpu --e2e-steps 1"
+$NCU_CMD > gpurun_out/plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $NCU_CMD > gpurun_out/ncu_launches.log 2>&1
+$NCU_CMD > gpurun_out/plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:worm_philox -s 3 -c 1 -o gpurun_out/prof_worm $NCU_CMD > gpurun_out/ncu_full.log 2>&1
+ls -la gpurun_out

@@ -40,7 +40,7 @@ SIGNATURES = {
                               _i32, _vp, _vp, _vp, _sz, _vp]),
     "worm_philox_workspace_bytes": (_sz, [_i64]),
     "worm_philox_run": (C.c_int, [C.c_int, C.c_int, _i64, _u64, _pd, _pu64, _u64, _u64, _u64,
-                                  _vp, _vp, _vp, _vp, _vp, _vp, _i32, _u64, _i32, _vp, _vp, _vp,
+                                  _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _u64, _i32, _vp, _vp, _vp,
                                   C.c_int, _vp, _sz, _vp]),
     "worm_thresholds": (C.c_int, [_dbl, _pu64, _pu64, _pu64]),
     "worm_image": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp]),

@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "worm_kernels.h"
@@ -37,25 +38,36 @@ struct DevInfo {
     int ok = 0, sm = 0, smem_optin = 0, clock_khz = 0, major = 0, minor = 0;
 };
 
+// Device attributes are queried once per device and cached: cudaDevAttrClockRate alone costs
+// milliseconds per query, which would dwarf a 78 us blocking launch.
 int current_device_info(DevInfo &d)
 {
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0) {
-        cudaGetLastError();
-        return fail(WORM_E_NOGPU, "no CUDA device visible (%s); libworm_b200 has no CPU fallback",
-                    e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
-    }
+    constexpr int MAX_DEV = 64;
+    static DevInfo cache[MAX_DEV];
+    static std::mutex mu;
     int dev = 0;
-    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
-    cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, dev);
-    cudaDeviceGetAttribute(&d.minor, cudaDevAttrComputeCapabilityMinor, dev);
-    cudaDeviceGetAttribute(&d.sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaDeviceGetAttribute(&d.clock_khz, cudaDevAttrClockRate, dev);
-    if (d.major != 10)
-        return fail(WORM_E_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", dev, d.major, d.minor);
-    d.ok = 1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(WORM_E_NOGPU, "no CUDA device visible (%s); libworm_b200 has no CPU fallback", cudaGetErrorString(e));
+    }
+    if (dev < 0 || dev >= MAX_DEV) return fail(WORM_E_NOGPU, "device ordinal %d unsupported", dev);
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!cache[dev].ok) {
+            DevInfo q;
+            cudaDeviceGetAttribute(&q.major, cudaDevAttrComputeCapabilityMajor, dev);
+            cudaDeviceGetAttribute(&q.minor, cudaDevAttrComputeCapabilityMinor, dev);
+            cudaDeviceGetAttribute(&q.sm, cudaDevAttrMultiProcessorCount, dev);
+            cudaDeviceGetAttribute(&q.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            cudaDeviceGetAttribute(&q.clock_khz, cudaDevAttrClockRate, dev);
+            if (q.major != 10)
+                return fail(WORM_E_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", dev, q.major, q.minor);
+            q.ok = 1;
+            cache[dev] = q;
+        }
+        d = cache[dev];
+    }
     return WORM_OK;
 }
 
@@ -188,7 +200,7 @@ int worm_philox_run(int L, int algo, int64_t n_chains, uint64_t chain_id0,
                     const double *h_T, const uint64_t *h_seed,
                     uint64_t step_begin, uint64_t n_steps, uint64_t therm_steps,
                     uint8_t *d_bonds, int32_t *d_head, int32_t *d_tail, int64_t *d_acc,
-                    const int32_t *d_hist_index, int64_t *d_hist, int32_t n_hist,
+                    const int32_t *d_group_index, int32_t n_groups, int64_t *d_hist, int64_t *d_group_acc,
                     uint64_t dump_every, int32_t max_dumps, int32_t *d_n_dumps,
                     int64_t *d_events, uint8_t *d_dumps,
                     int lanes_per_chain, void *d_workspace, size_t workspace_bytes, void *stream)
@@ -197,8 +209,8 @@ int worm_philox_run(int L, int algo, int64_t n_chains, uint64_t chain_id0,
     if (algo != WORM_ALGO_TAYLOR && algo != WORM_ALGO_BINARY) return fail(WORM_E_ARG, "algo = %d", algo);
     if (n_chains <= 0) return fail(WORM_E_ARG, "n_chains = %lld must be positive", (long long)n_chains);
     if (!h_T || !h_seed || !d_bonds || !d_head || !d_tail || !d_acc) return fail(WORM_E_ARG, "null required pointer");
-    if ((d_hist == nullptr) != (d_hist_index == nullptr)) return fail(WORM_E_ARG, "d_hist and d_hist_index go together");
-    if (d_hist && n_hist <= 0) return fail(WORM_E_ARG, "n_hist must be positive with d_hist");
+    if ((d_hist || d_group_acc) && !d_group_index) return fail(WORM_E_ARG, "d_hist / d_group_acc need d_group_index");
+    if (d_group_index && n_groups <= 0) return fail(WORM_E_ARG, "n_groups must be positive with d_group_index");
     if (dump_every && (max_dumps <= 0 || !d_n_dumps)) return fail(WORM_E_ARG, "dump_every needs max_dumps > 0 and d_n_dumps");
     if (lanes_per_chain != 0 && lanes_per_chain != 1 && lanes_per_chain != 4 && lanes_per_chain != -1)
         return fail(WORM_E_ARG, "lanes_per_chain = %d (0, 1, 4 or -1)", lanes_per_chain);
@@ -227,7 +239,7 @@ int worm_philox_run(int L, int algo, int64_t n_chains, uint64_t chain_id0,
     a.L = L; a.algo = algo; a.n_chains = n_chains; a.chain_id0 = chain_id0; a.prm = d_prm;
     a.step_begin = step_begin; a.step_end = step_begin + n_steps; a.therm = therm_steps;
     a.bonds = d_bonds; a.head = d_head; a.tail = d_tail; a.acc = d_acc;
-    a.hist_index = d_hist_index; a.hist = d_hist;
+    a.group_index = d_group_index; a.hist = d_hist; a.group_acc = d_group_acc;
     a.dump_every = dump_every; a.max_dumps = max_dumps; a.n_dumps = d_n_dumps; a.events = d_events; a.dumps = d_dumps;
     const char *why = "";
     e = worm::launch_philox(a, lanes_per_chain, dev.smem_optin, dev.sm, st, &why);
@@ -312,7 +324,7 @@ int worm_sim_host(int L, int64_t n_chains, const double *h_T, const double *h_se
         cudaMemsetAsync(tail.p, 0, (size_t)n_chains * 4, nullptr);
         rc = worm_philox_run(L, algo, n_chains, 0, h_T, h_seed_u64, 0, num_steps, therm_steps,
                              (uint8_t *)bonds.p, (int32_t *)head.p, (int32_t *)tail.p, (int64_t *)out.p,
-                             nullptr, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, 0, ws.p, wsb, nullptr);
+                             nullptr, 0, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, 0, ws.p, wsb, nullptr);
     } else {
         return fail(WORM_E_ARG, "rng_mode = %d (0 = MT19937, 1 = Philox)", rng_mode);
     }

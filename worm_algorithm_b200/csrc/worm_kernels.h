@@ -20,8 +20,9 @@ struct PhiloxArgs {
     uint8_t *bonds;           // [n][2N] in/out
     int32_t *head, *tail;     // [n] in/out
     int64_t *acc;             // [n][ACC_STRIDE] in/out
-    const int32_t *hist_index;
-    int64_t *hist;            // [n_hist][N]
+    const int32_t *group_index;   // [n] or null
+    int64_t *hist;            // [n_groups][N] or null
+    int64_t *group_acc;       // [n_groups][ACC_STRIDE] or null
     uint64_t dump_every;
     int32_t max_dumps;
     int32_t *n_dumps;

@@ -228,7 +228,7 @@ worm_philox_kernel(const PhiloxArgs a, const Geo geo)
     }
     int64_t *hist_row = nullptr;
     if constexpr (HIST) {
-        if (a.hist && a.hist_index) hist_row = a.hist + (int64_t)a.hist_index[cl] * geo.N;
+        if (a.hist && a.group_index) hist_row = a.hist + (int64_t)a.group_index[cl] * geo.N;
     }
     int32_t nd = (a.n_dumps && live) ? a.n_dumps[cl] : 0;
 
@@ -322,10 +322,20 @@ worm_philox_kernel(const PhiloxArgs a, const Geo geo)
         a.head[cl] = c.head;
         a.tail[cl] = c.tail;
         int64_t *ac = a.acc + cl * ACC_STRIDE;
+        const uint64_t mb = a.step_begin > a.therm ? a.step_begin : a.therm;
+        const int64_t iters = (a.step_end > mb) ? (int64_t)(a.step_end - mb) : 0;
+        if (a.group_acc && a.group_index) {
+            unsigned long long *ga = reinterpret_cast<unsigned long long *>(a.group_acc + (int64_t)a.group_index[cl] * ACC_STRIDE);
+            atomicAdd(ga + 0, (unsigned long long)(c.Z - (uint64_t)ac[0]));
+            atomicAdd(ga + 1, (unsigned long long)(c.SNb - (uint64_t)ac[1]));
+            atomicAdd(ga + 2, (unsigned long long)(c.SNb2 - (uint64_t)ac[2]));
+            atomicAdd(ga + 3, (unsigned long long)(c.Sn - (uint64_t)ac[3]));
+            atomicAdd(ga + 4, (unsigned long long)(c.Sn2 - (uint64_t)ac[4]));
+            atomicAdd(ga + 5, (unsigned long long)iters);
+        }
         ac[0] = (int64_t)c.Z; ac[1] = (int64_t)c.SNb; ac[2] = (int64_t)c.SNb2;
         ac[3] = (int64_t)c.Sn; ac[4] = (int64_t)c.Sn2;
-        const uint64_t mb = a.step_begin > a.therm ? a.step_begin : a.therm;
-        ac[5] += (a.step_end > mb) ? (int64_t)(a.step_end - mb) : 0;
+        ac[5] += iters;
         if (a.n_dumps) a.n_dumps[cl] = nd;
     }
 }
@@ -386,7 +396,7 @@ cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, int smem_opt
     geo.ch = ch;
     const size_t smem_bytes = smem ? (((size_t)geo.words * ch * 4 + 15) & ~(size_t)15) + rbuf_bytes
                                    : rbuf_bytes;
-    const bool hist = (a.hist != nullptr && a.hist_index != nullptr);
+    const bool hist = (a.hist != nullptr && a.group_index != nullptr);
     if (a.algo == ALGO_TAYLOR) {
         if (G == 1) return launch_g<ALGO_TAYLOR, 1>(a, geo, smem, hist, smem_bytes, st);
         return launch_g<ALGO_TAYLOR, 4>(a, geo, smem, hist, smem_bytes, st);

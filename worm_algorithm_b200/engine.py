@@ -89,11 +89,17 @@ def run_mt(L: int, T, seeds, num_steps: int, bond_flag: int = 0, max_events: int
 
 # ---------------------------------------------------------------------------------------------
 class PhiloxState:
-    """Resumable state + accumulators of a batch of production chains (all device tensors)."""
+    """Resumable state + accumulators of a batch of production chains (all device tensors).
+
+    group_index (one int per chain, e.g. its temperature index) switches on the per-group sums:
+    `group_acc` int64 [n_groups, 8] (the WORM_ACC_* record summed over the group's chains by the
+    kernel itself) and, with hist=True, the G(r) histograms `hist` int64 [n_groups, N]."""
+
+    launches_per_run = 1          # kernels launched by one run() call
 
     def __init__(self, L: int, T, seeds, algo: int = ALGO_TAYLOR, chain_id0: int = 0,
-                 hist_index=None, n_hist: int = 0, max_dumps: int = 0, store_dumps: bool = True,
-                 device=None):
+                 group_index=None, n_groups: int = 0, hist: bool = False,
+                 max_dumps: int = 0, store_dumps: bool = True, device=None):
         self.device = _dev(device)
         self.L = int(L)
         self.N = self.L * self.L
@@ -111,18 +117,23 @@ class PhiloxState:
             self.head = torch.zeros((self.n,), dtype=torch.int32, device=dev)
             self.tail = torch.zeros((self.n,), dtype=torch.int32, device=dev)
             self.acc = torch.zeros((self.n, ACC_STRIDE), dtype=torch.int64, device=dev)
-            self.hist_index = None
+            self.group_index = None
+            self.group_acc = None
             self.hist = None
-            self.n_hist = 0
-            if hist_index is not None:
-                hi = np.ascontiguousarray(np.asarray(hist_index, dtype=np.int32).reshape(-1))
-                if hi.size != self.n:
-                    raise ValueError("hist_index must have one entry per chain")
-                self.n_hist = int(n_hist) if n_hist else int(hi.max()) + 1
-                if hi.min() < 0 or hi.max() >= self.n_hist:
-                    raise ValueError("hist_index out of range")
-                self.hist_index = torch.from_numpy(hi).to(dev)
-                self.hist = torch.zeros((self.n_hist, self.N), dtype=torch.int64, device=dev)
+            self.n_groups = 0
+            if group_index is not None:
+                gi = np.ascontiguousarray(np.asarray(group_index, dtype=np.int32).reshape(-1))
+                if gi.size != self.n:
+                    raise ValueError("group_index must have one entry per chain")
+                self.n_groups = int(n_groups) if n_groups else int(gi.max()) + 1
+                if gi.min() < 0 or gi.max() >= self.n_groups:
+                    raise ValueError("group_index out of range")
+                self.group_index = torch.from_numpy(gi).to(dev)
+                self.group_acc = torch.zeros((self.n_groups, ACC_STRIDE), dtype=torch.int64, device=dev)
+                if hist:
+                    self.hist = torch.zeros((self.n_groups, self.N), dtype=torch.int64, device=dev)
+            elif hist:
+                raise ValueError("hist=True needs group_index")
             self.max_dumps = int(max_dumps)
             self.n_dumps = torch.zeros((self.n,), dtype=torch.int32, device=dev)
             self.events = torch.zeros((self.n, max(self.max_dumps, 1), 3), dtype=torch.int64, device=dev)
@@ -130,6 +141,14 @@ class PhiloxState:
                           if (self.max_dumps and store_dumps) else None)
             self._wsb = lib().worm_philox_workspace_bytes(self.n)
             self._ws = torch.empty((self._wsb,), dtype=torch.uint8, device=dev)
+
+    def reset(self):
+        """Back to step 0: empty lattices, head = tail = 0, zero sums (stream-ordered)."""
+        for t in (self.bonds, self.head, self.tail, self.acc, self.group_acc, self.hist, self.n_dumps):
+            if t is not None:
+                t.zero_()
+        self.step = 0
+        return self
 
     def run(self, n_steps: int, therm_steps: int = 0, dump_every: int = 0, lanes_per_chain: int = 0):
         """Advance every chain by n_steps (stream-ordered, no host synchronisation)."""
@@ -140,7 +159,7 @@ class PhiloxState:
                 self.T.ctypes.data_as(_lib._pd), self.seeds.ctypes.data_as(_lib._pu64),
                 self.step, int(n_steps), int(therm_steps),
                 _ptr(self.bonds), _ptr(self.head), _ptr(self.tail), _ptr(self.acc),
-                _ptr(self.hist_index), _ptr(self.hist), self.n_hist,
+                _ptr(self.group_index), self.n_groups, _ptr(self.hist), _ptr(self.group_acc),
                 int(dump_every) if self.max_dumps else 0, self.max_dumps, _ptr(self.n_dumps),
                 _ptr(self.events), _ptr(self.dumps),
                 int(lanes_per_chain), _ptr(self._ws), self._wsb, _stream_ptr(dev)))

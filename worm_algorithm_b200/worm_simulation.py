@@ -34,7 +34,7 @@ class WormSimulation(object):
                  T_start=1., T_end=3.5, T_step=0.1, T_arr=None, bond_flag=1,
                  seeds=None, n_replicas=1, rng="mt19937", algo="taylor", therm_frac=0.1,
                  write_steps=50, max_dumps=None, data_dir=None, device=None,
-                 lanes_per_chain=0, rank=0, world_size=1):
+                 lanes_per_chain=0, rank=0, world_size=1, hist=False):
         self._L = int(L)
         self._num_steps = int(num_steps)
         self._verbose = verbose
@@ -60,6 +60,7 @@ class WormSimulation(object):
         self._lanes = int(lanes_per_chain)
         self._rank, self._world = int(rank), int(world_size)
         self._seeds = seeds
+        self._hist = bool(hist)
         self._tree = compat_io.DataTree(data_dir, self._L) if data_dir is not None else None
         self.results = None
         if self._run:
@@ -188,11 +189,11 @@ class WormSimulation(object):
         st = None
         if c1 > c0:
             st = engine.PhiloxState(L, Tc[c0:c1], seeds[c0:c1], algo=self._algo, chain_id0=c0,
+                                    group_index=t_idx[c0:c1], n_groups=nT, hist=self._hist,
                                     max_dumps=max_dumps, store_dumps=bool(self._bond_flag), device=self._device)
             st.run(self._num_steps, therm_steps=therm, dump_every=self._write_steps if max_dumps else 0,
                    lanes_per_chain=self._lanes)
-            ti = torch.from_numpy(t_idx[c0:c1].astype(np.int64)).to(st.acc.device)
-            per_T = torch.zeros((nT, 8), dtype=torch.int64, device=st.acc.device).index_add_(0, ti, st.acc)
+            per_T = st.group_acc                  # summed over the chains of each temperature on the device
         per_T = dist.allreduce_sum(per_T, self._world)
         self.results = dict(T=Tc[c0:c1], seeds=seeds[c0:c1], replica=r_idx[c0:c1], t_index=t_idx[c0:c1],
                             chain_range=(c0, c1), acc=(st.acc if st is not None else None), state=st,
