@@ -257,9 +257,16 @@ void worm_oracle_thresholds(double T, uint64_t *kfix, uint64_t *tfix, uint64_t *
 }
 
 /* ------------------------------------------------------------------------------------------
- * Production mode.  One Philox call per worm step, counter = {step_lo, step_hi, chain_lo,
- * chain_hi}, key = {seed_lo, seed_hi}; word 0 = kick site, word 1 = direction, word 2 =
- * increment/decrement coin, word 3 = acceptance draw (the draw order of ref:128,137,141,151).
+ * Production mode.  Random stream (version 2): ONE Philox4x32-10 call serves TWO worm steps.
+ *   pair p = step >> 1, counter = {p_lo, p_hi, chain_lo, chain_hi}, key = {seed_lo, seed_hi},
+ *   output (x, y, z, w); an even step uses (a, b) = (x, y), an odd step (a, b) = (z, w):
+ *     a                      acceptance draw, all 32 bits                        (ref:151)
+ *     b >> 30                direction 0..3                                      (ref:137)
+ *     (b >> 29) & 1          0 = increment proposal, 1 = decrement proposal      (ref:141)
+ *     ((b << 3) * N) >> 32   kick site, from the low 29 bits of b                (ref:128)
+ *   (the reference spends one 32-bit draw on each of the four; the three small decisions use
+ *    disjoint bit fields of one word here.  For power-of-two N the kick is exactly uniform,
+ *    otherwise its bias is below N * 2^-29.)
  *
  * The loop runs steps [step_begin, step_begin + n_steps) of one chain, resuming from
  * (bonds, head, tail).  Iterations with step >= therm are measured:
@@ -288,9 +295,12 @@ int worm_oracle_philox_run(int L, int algo, uint64_t chain_id, uint64_t seed,
     int64_t nd = n_dumps_io ? *n_dumps_io : 0;
     const uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
     for (uint64_t s = step_begin; s < step_begin + n_steps; s++) {
-        const uint32_t ctr[4] = { (uint32_t)s, (uint32_t)(s >> 32), (uint32_t)chain_id, (uint32_t)(chain_id >> 32) };
+        const uint64_t pair = s >> 1;
+        const uint32_t ctr[4] = { (uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)chain_id, (uint32_t)(chain_id >> 32) };
         uint32_t r[4];
         philox4x32_10(ctr, key, r);
+        const uint32_t ra = (s & 1) ? r[2] : r[0];      /* acceptance draw */
+        const uint32_t rb = (s & 1) ? r[3] : r[1];      /* direction | coin | kick bits */
         const int closed = (head == tail);
         if (s >= therm) {
             if (hist) {
@@ -310,8 +320,8 @@ int worm_oracle_philox_run(int L, int algo, uint64_t chain_id, uint64_t seed,
             }
             acc[5] += 1;
         }
-        if (closed) head = tail = (int)(((uint64_t)r[0] * (uint64_t)N) >> 32);
-        const int d = (int)(r[1] >> 30);
+        if (closed) head = tail = (int)(((uint64_t)(uint32_t)(rb << 3) * (uint64_t)N) >> 32);
+        const int d = (int)(rb >> 30);
         const int x = head % L, y = head / L;
         int nh, ib;
         switch (d) {                       /* closed form of ref:88-95 + ref:214-244, valid for L >= 3 */
@@ -323,11 +333,11 @@ int worm_oracle_philox_run(int L, int algo, uint64_t chain_id, uint64_t seed,
         const uint32_t nb = bonds[ib];
         int accept, delta;
         if (algo == 0) {
-            if (r[2] < 0x80000000u) { delta = 1;  accept = (nb < 255) && ((uint64_t)(nb + 1) * r[3] < kfix); }
-            else                    { delta = -1; accept = ((uint64_t)r[3] < (uint64_t)nb * tfix); }
+            if (((rb >> 29) & 1u) == 0) { delta = 1;  accept = (nb < 255) && ((uint64_t)(nb + 1) * ra < kfix); }
+            else                        { delta = -1; accept = ((uint64_t)ra < (uint64_t)nb * tfix); }
         } else {
             if (nb) { delta = -1; accept = 1; }
-            else    { delta = 1;  accept = ((uint64_t)r[3] < hfix); }
+            else    { delta = 1;  accept = ((uint64_t)ra < hfix); }
         }
         if (accept) {
             const uint32_t nn = nb + delta;

@@ -212,8 +212,9 @@ int worm_philox_run(int L, int algo, int64_t n_chains, uint64_t chain_id0,
     if ((d_hist || d_group_acc) && !d_group_index) return fail(WORM_E_ARG, "d_hist / d_group_acc need d_group_index");
     if (d_group_index && n_groups <= 0) return fail(WORM_E_ARG, "n_groups must be positive with d_group_index");
     if (dump_every && (max_dumps <= 0 || !d_n_dumps)) return fail(WORM_E_ARG, "dump_every needs max_dumps > 0 and d_n_dumps");
-    if (lanes_per_chain != 0 && lanes_per_chain != 1 && lanes_per_chain != 4 && lanes_per_chain != -1)
-        return fail(WORM_E_ARG, "lanes_per_chain = %d (0, 1, 4 or -1)", lanes_per_chain);
+    if (lanes_per_chain != 0 && lanes_per_chain != 1 && lanes_per_chain != 4 && lanes_per_chain != 8 &&
+        lanes_per_chain != 32 && lanes_per_chain != -1)
+        return fail(WORM_E_ARG, "lanes_per_chain = %d (0, 1, 4, 8, 32 or -1)", lanes_per_chain);
     if (step_begin + n_steps < step_begin) return fail(WORM_E_ARG, "step range overflows");
     if (workspace_bytes < worm_philox_workspace_bytes(n_chains) || !d_workspace)
         return fail(WORM_E_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, worm_philox_workspace_bytes(n_chains));
@@ -222,12 +223,14 @@ int worm_philox_run(int L, int algo, int64_t n_chains, uint64_t chain_id0,
     std::vector<worm::PhiloxChain> prm((size_t)n_chains);
     double lastT = -1.0;
     uint64_t k = 0, t = 0, h = 0;
+    bool lowt = false;            // some chain outside the T >= 1 fast path of the record builder
     for (int64_t c = 0; c < n_chains; ++c) {
         const double T = h_T[c];
         if (T != lastT) {
             if (bad_T(T)) return fail(WORM_E_ARG, "temperature[%lld] = %g out of range", (long long)c, T);
             thresholds(T, k, t, h);
             lastT = T;
+            if (k > 0x100000000ull || t < 0x100000000ull) lowt = true;
         }
         prm[(size_t)c] = worm::PhiloxChain{k, t, h, h_seed[c]};
     }
@@ -237,13 +240,26 @@ int worm_philox_run(int L, int algo, int64_t n_chains, uint64_t chain_id0,
     if (e != cudaSuccess) return cuda_fail(e, "upload chain parameters");
     worm::PhiloxArgs a;
     a.L = L; a.algo = algo; a.n_chains = n_chains; a.chain_id0 = chain_id0; a.prm = d_prm;
-    a.step_begin = step_begin; a.step_end = step_begin + n_steps; a.therm = therm_steps;
+    a.therm = therm_steps;
     a.bonds = d_bonds; a.head = d_head; a.tail = d_tail; a.acc = d_acc;
     a.group_index = d_group_index; a.hist = d_hist; a.group_acc = d_group_acc;
     a.dump_every = dump_every; a.max_dumps = max_dumps; a.n_dumps = d_n_dumps; a.events = d_events; a.dumps = d_dumps;
-    const char *why = "";
-    e = worm::launch_philox(a, lanes_per_chain, dev.smem_optin, dev.sm, st, &why);
-    if (e != cudaSuccess) return cuda_fail(e, why[0] ? why : "worm_philox_kernel launch");
+    // One launch per chunk of <= 2^31 steps: the latency kernel keeps the G(r) bins of a launch in
+    // 32-bit shared-memory counters.  Chunking does not change any result (counter-based stream).
+    const uint64_t chunk = 0x80000000ull;
+    uint64_t s = step_begin;
+    const uint64_t s_end = step_begin + n_steps;
+    do {
+        a.step_begin = s;
+        a.step_end = (s_end - s > chunk) ? s + chunk : s_end;
+        const char *why = "";
+        e = worm::launch_philox(a, lanes_per_chain, lowt, dev.smem_optin, dev.sm, st, &why);
+        if (e != cudaSuccess) {
+            if (why[0]) return fail(WORM_E_ARG, "%s", why);
+            return cuda_fail(e, "worm kernel launch");
+        }
+        s = a.step_end;
+    } while (s < s_end);
     // cudaMemcpyAsync from pageable memory has already staged `prm`; nothing else to wait for
     return WORM_OK;
 }

@@ -37,8 +37,11 @@ cudaError_t launch_mt(int L, int64_t n_chains, int64_t n_pad, const MtChain *d_p
                       int32_t max_trace, int32_t *d_n_trace, int64_t *d_trace,
                       uint32_t *d_mt_state, cudaStream_t st);
 
-// lanes_per_chain: 1 or 4 (0 = choose).  smem_optin = max opt-in dynamic shared memory per block.
-cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, int smem_optin, int sm_count,
+// lanes_per_chain: 0 = choose; 4 / 8 / 32 = latency mode with that many lanes per chain; 1 = thread
+// per chain, bonds in shared memory when they fit; -1 = thread per chain, bonds in global memory.
+// lowt: some chain has kfix > 2^32 or tfix < 2^32 (T < 1).  smem_optin = max opt-in dynamic shared
+// memory per block.
+cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, bool lowt, int smem_optin, int sm_count,
                           cudaStream_t st, const char **why);
 
 cudaError_t launch_image(int L, int64_t n, const uint8_t *d_bonds, int32_t *d_img, cudaStream_t st);
