@@ -14,10 +14,12 @@
 //     mask, absolute shared-memory address of the bond array (+ y bit), kick site, occupation
 //     threshold.  Records go into a double-buffered shared-memory ring, one round (R steps per
 //     chain) per buffer; pairs meet at a named barrier (bar.sync, 64 threads) once per round.
-//   * a walker warp owns 32/G chains; the G lanes of a chain walk it redundantly (SIMD lanes are
-//     free here, warp issue slots are not).  The record of step j+1 is fetched while step j waits
-//     for its bond, and the kick that follows a closing move is folded into the accept select, so
-//     the head -> head dependency of consecutive steps is a single select after the accept test.
+//   * a walker warp owns CH = 8, 4 or 1 chains, one per lane; its other lanes are predicated off
+//     (SIMD lanes are free here, warp issue slots and shared-memory wavefronts are not: a 128-bit
+//     load by 8 lanes is one wavefront, by 32 lanes four).  Records are fetched two steps ahead,
+//     and the kick that follows a closing move is folded into the accept select, so the
+//     head -> head dependency of consecutive steps is a single select after the accept test.
+//     Walkers are the block's high warps: the sub-partition arbiter prefers the higher warp id.
 // Power-of-two L only: the head is a doubled site index whose x and y bit fields wrap by masking.
 //
 // Algorithm and random stream: oracle/worm_oracle.c:worm_oracle_philox_run (bit-for-bit), i.e. the
@@ -129,8 +131,8 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
 // One worm step on a pre-decoded record.  On entry head2 already holds this step's kick when the
 // worm is closed; on exit it holds the NEXT step's kick (kick2_next) when the worm is closed then.
 template <int ALGO, bool HIST, bool MEAS>
-__device__ __forceinline__ void lat_step(const LatGeo &g, uint32_t hist_abs, uint32_t hist_writer, LatState &c,
-                                         const uint4 ra, const uint4 rb, const int kick2_next)
+__device__ __forceinline__ void lat_step(const LatGeo &g, uint32_t hist_abs, uint32_t hist_writer,
+                                         LatState &c, const uint4 ra, const uint4 rb, const int kick2_next)
 {
     const int add = (int)ra.x, keep = (int)ra.y, addneg = (int)ra.z;
     const uint32_t base = ra.w;
@@ -234,8 +236,8 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int w = warp & (NW - 1);                       // pair index
-    const bool is_producer = warp >= NW;
+    const int w = warp & (NW - 1);                       // pair index: warps w and NW + w share a sub-partition
+    const bool is_producer = warp < NW;                  // walkers are the high warps (arbiter priority)
     const int64_t chain0 = (int64_t)blockIdx.x * BCH;    // first chain of the block
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem8);
     const uint32_t rec_w = sbase + (uint32_t)g.rec_off + (uint32_t)(w * Cfg::RECW);
@@ -263,15 +265,16 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
 
     if (is_producer) {
         // ================================ producer warp ================================
-        // Philox block b = u*32 + lane of a round belongs to chain slot q = b / PR, pair p = b % PR.
+        // Philox block b = u*32 + lane of a round belongs to chain slot q = b % CH, pair p = b / CH:
+        // consecutive lanes store consecutive 16-byte records (conflict-free 128-bit stores).
         PhiloxChain prm[U];
         uint32_t c2[U], c3[U], bonds_abs[U], rec_q[U];
         int p_of[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int b = u * 32 + lane;
-            const int q = b / PR;
-            p_of[u] = b % PR;
+            const int q = b % CH;
+            p_of[u] = b / CH;
             const int64_t cg = chain0 + w * CH + q;
             const int64_t cl = cg < a.n_chains ? cg : 0;
             prm[u] = a.prm[cl];
@@ -307,17 +310,19 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         pair_barrier(bar_id);                            // matches the walker's barrier before its last step
     } else {
         // ================================= walker warp =================================
-        const int sub = lane % G;            // lane within the chain's group
-        const int q = lane / G;              // chain slot within the warp
+        // One lane per chain; the other lanes of the warp retire here (barriers count warps, and a
+        // shared-memory access by CH lanes costs CH/8 wavefronts instead of 4).
+        if (lane >= CH) return;
+        constexpr unsigned wmask = (CH == 32) ? 0xffffffffu : ((1u << CH) - 1u);
+        const int q = lane;                  // chain slot within the warp
         const int cslot = w * CH + q;
         const int64_t cidx = chain0 + cslot;
         const bool live = cidx < a.n_chains;
-        const bool writer = live && (sub == 0);
-        const int64_t cl = live ? cidx : 0;  // dead groups shadow chain 0 in their own shared-memory slot, never write
-        uint8_t *bonds = smem8 + cslot * g.nb2;
+        const int64_t cl = live ? cidx : 0;  // dead slots shadow chain 0 in their own shared-memory slot, never write
+        const uint8_t *bonds = smem8 + cslot * g.nb2;
         uint32_t rec_q = rec_w + (uint32_t)q * 16u;
         uint32_t hist_abs = sbase + (uint32_t)g.hist_off + (uint32_t)(cslot * g.N) * 4u;
-        const uint32_t hist_writer = (HIST && writer && a.hist != nullptr) ? 1u : 0u;
+        const uint32_t hist_writer = (HIST && live && a.hist != nullptr) ? 1u : 0u;
         asm volatile("" : "+r"(rec_q), "+r"(hist_abs));                  // keep them in registers
 
         LatState c;
@@ -331,92 +336,108 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         {
             int Nb = 0, npar = 0;
             const uint4 *src = reinterpret_cast<const uint4 *>(bonds);
-            for (int i = sub; i < g.nb2 / 16; i += G) {
+            for (int i = 0; i < g.nb2 / 16; ++i) {
                 const uint4 v = src[i];
                 Nb += (int)(__vsadu4(v.x, 0) + __vsadu4(v.y, 0) + __vsadu4(v.z, 0) + __vsadu4(v.w, 0));
                 npar += __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) +
                         __popc(v.w & 0x01010101u);
             }
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) {
-                Nb += __shfl_xor_sync(0xffffffffu, Nb, o);
-                npar += __shfl_xor_sync(0xffffffffu, npar, o);
-            }
             c.Nb = Nb; c.npar = npar;
         }
         int32_t nd = (a.n_dumps && live) ? a.n_dumps[cl] : 0;
 
-        // One round: steps [jb, je) of the buffer at `cur`; (ca, cb) is the record of step jb.  The
-        // record of the following step is fetched one step ahead; for the last step of the round it
-        // lives in the other buffer (slot jb_next), complete once the pair barrier has been passed.
-        uint4 ca, cb;
-        auto walk_round = [&](auto meas_tag, uint32_t cur, int jb, int je, uint32_t nxt_rec) {
+        auto rec_addr = [&](uint32_t buf, int j) { return rec_q + buf + (uint32_t)(j * CH * 16); };
+
+        // A full round (steps 0..R-1 of the buffer at `cur`), software-pipelined two steps deep: on
+        // entry (p0a,p0b) / (p1a,p1b) hold the records of steps 0 / 1; step j fetches the record of
+        // step j+2, which for the last two steps lives in the other buffer (complete once the pair
+        // barrier has been passed).  On exit they hold the records of steps 0 / 1 of the next round.
+        uint4 p0a, p0b, p1a, p1b;
+        auto full_round = [&](auto meas_tag, uint32_t cur, uint32_t nxt) {
             constexpr bool MEAS = decltype(meas_tag)::value;
-            if (jb == 0 && je == R) {
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    uint32_t nrec;
-                    if (j < R - 1) nrec = rec_q + cur + (uint32_t)((j + 1) * CH * 16);
-                    else { pair_barrier(bar_id); nrec = nxt_rec; }
-                    const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
-                    lat_step<ALGO, HIST, MEAS>(g, hist_abs, hist_writer, c, ca, cb, (int)fb.x);
-                    ca = fa; cb = fb;
-                }
-            } else {
-                for (int j = jb; j < je; ++j) {
-                    uint32_t nrec;
-                    if (j < je - 1) nrec = rec_q + cur + (uint32_t)((j + 1) * CH * 16);
-                    else { pair_barrier(bar_id); nrec = nxt_rec; }
-                    const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
-                    lat_step<ALGO, HIST, MEAS>(g, hist_abs, hist_writer, c, ca, cb, (int)fb.x);
-                    ca = fa; cb = fb;
-                }
+            for (int j = 0; j < R; ++j) {
+                if (j == R - 2) pair_barrier(bar_id);
+                const uint32_t nrec = (j < R - 2) ? rec_addr(cur, j + 2) : rec_addr(nxt, j + 2 - R);
+                const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
+                lat_step<ALGO, HIST, MEAS>(g, hist_abs, hist_writer, c, p0a, p0b, (int)p1b.x);
+                p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
             }
             if constexpr (MEAS) flush_partials(c);
+        };
+        // Any other round (segment edges): steps [jb, je), records straight from shared memory.  The
+        // kick folded into the last step is the first record of the next round (slot jbn of `nxt`).
+        auto edge_round = [&](auto meas_tag, uint32_t cur, uint32_t nxt, int jb, int je, int jbn) {
+            constexpr bool MEAS = decltype(meas_tag)::value;
+            for (int j = jb; j < je; ++j) {
+                const uint32_t rec = rec_addr(cur, j);
+                const uint4 xa = lds_v4(rec), xb = lds_v4(rec + Cfg::REC_B);
+                uint32_t nrec = rec_addr(cur, j + 1);
+                if (j == je - 1) { pair_barrier(bar_id); nrec = rec_addr(nxt, jbn); }
+                const uint4 nb_ = lds_v4(nrec + Cfg::REC_B);
+                lat_step<ALGO, HIST, MEAS>(g, hist_abs, hist_writer, c, xa, xb, (int)nb_.x);
+            }
+            flush_partials(c);
         };
 
         uint32_t cur = 0u;
         uint64_t s = a.step_begin;
         bool first = true;
+        bool piped = false;                  // (p0, p1) hold the first two records of the coming round
         while (s < a.step_end) {
             bool meas, dump_first;
             const uint64_t seg_end = next_segment(a, s, meas, dump_first);
-            if (dump_first && live && c.closed) {                    // worm_ising_2d.cpp:113-124
-                if (nd < a.max_dumps) {
-                    if (writer && a.events) {
-                        int64_t *e = a.events + ((int64_t)cl * a.max_dumps + nd) * 3;
-                        e[0] = (int64_t)s; e[1] = (int64_t)c.Z; e[2] = (int64_t)c.SNb;
-                    }
-                    if (a.dumps) {
-                        uint4 *dst = reinterpret_cast<uint4 *>(a.dumps + ((int64_t)cl * a.max_dumps + nd) * g.nb2);
-                        const uint4 *src = reinterpret_cast<const uint4 *>(bonds);
-                        for (int i = sub; i < g.nb2 / 16; i += G) dst[i] = src[i];
-                    }
+            if (dump_first) {                                        // worm_ising_2d.cpp:113-124
+                // the whole warp copies the bonds of every chain that dumps now
+                const bool want = live && c.closed;
+                const bool store = want && nd < a.max_dumps;
+                if (store && a.events) {
+                    int64_t *e = a.events + ((int64_t)cl * a.max_dumps + nd) * 3;
+                    e[0] = (int64_t)s; e[1] = (int64_t)c.Z; e[2] = (int64_t)c.SNb;
                 }
-                ++nd;
+                unsigned dm = __ballot_sync(wmask, store && a.dumps != nullptr);
+                while (dm) {
+                    const int src_lane = __ffs(dm) - 1;
+                    dm &= dm - 1;
+                    const long long chain = __shfl_sync(wmask, (long long)cl, src_lane);
+                    const int slot = __shfl_sync(wmask, nd, src_lane);
+                    uint4 *dst = reinterpret_cast<uint4 *>(a.dumps + (chain * a.max_dumps + slot) * g.nb2);
+                    const uint4 *src = reinterpret_cast<const uint4 *>(smem8 + (w * CH + src_lane) * g.nb2);
+                    for (int i = lane; i < g.nb2 / 16; i += CH) dst[i] = src[i];
+                }
+                if (want) ++nd;
             }
             while (s < seg_end) {
                 const Round rd = make_round<R>(s, seg_end);
-                if (first) {
-                    // records of the first round are complete after the first barrier
-                    pair_barrier(bar_id);
-                    const uint32_t rec = rec_q + cur + (uint32_t)(rd.jb * CH * 16);
-                    ca = lds_v4(rec); cb = lds_v4(rec + Cfg::REC_B);
-                    c.head2 = c.closed ? (int)cb.x : c.head2;        // kick of the first step
-                    first = false;
-                }
                 const uint64_t e = rd.s0 + (uint64_t)rd.je;          // first step of the next round
                 const uint32_t nxt = cur ^ (uint32_t)Cfg::BUF;
-                const uint32_t nxt_rec = rec_q + nxt + (uint32_t)((int)(e & 1ull) * CH * 16);
-                if (meas) walk_round(std::true_type{}, cur, rd.jb, rd.je, nxt_rec);
-                else walk_round(std::false_type{}, cur, rd.jb, rd.je, nxt_rec);
+                const bool full = (rd.jb == 0 && rd.je == R);
+                if (first) {
+                    pair_barrier(bar_id);                            // the first round's records are complete
+                    const uint4 kb = lds_v4(rec_addr(cur, rd.jb) + Cfg::REC_B);
+                    c.head2 = c.closed ? (int)kb.x : c.head2;        // kick of the first step
+                    first = false;
+                }
+                if (full) {
+                    if (!piped) {
+                        p0a = lds_v4(rec_addr(cur, 0)); p0b = lds_v4(rec_addr(cur, 0) + Cfg::REC_B);
+                        p1a = lds_v4(rec_addr(cur, 1)); p1b = lds_v4(rec_addr(cur, 1) + Cfg::REC_B);
+                    }
+                    if (meas) full_round(std::true_type{}, cur, nxt);
+                    else full_round(std::false_type{}, cur, nxt);
+                    piped = true;
+                } else {
+                    if (meas) edge_round(std::true_type{}, cur, nxt, rd.jb, rd.je, (int)(e & 1ull));
+                    else edge_round(std::false_type{}, cur, nxt, rd.jb, rd.je, (int)(e & 1ull));
+                    piped = false;
+                }
                 cur = nxt;
                 s = e;
             }
         }
 
         if (first) pair_barrier(bar_id);                             // empty step range: meet the producer once
-        if (writer) {
+        if (live) {
             // a closed worm sits on its tail (head2 holds the folded kick of the step after the last)
             a.head[cl] = (c.closed ? c.tail2 : c.head2) >> 1;
             a.tail[cl] = c.tail2 >> 1;
@@ -430,13 +451,13 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         }
     }
 
-    // ---- write back (all 8 warps)
+    // ---- write back (the producer warps: the walkers' spare lanes have retired)
     __syncthreads();
-    {
+    if (is_producer) {
         const int vec_per_chain = g.nb2 / 16;
         const int total = BCH * vec_per_chain;
         const uint4 *src = reinterpret_cast<const uint4 *>(smem8);
-        for (int i = tid; i < total; i += 2 * NW * 32) {
+        for (int i = tid; i < total; i += NW * 32) {
             const int cslot = i / vec_per_chain;
             const int64_t cg = chain0 + cslot;
             if (cg < a.n_chains)
@@ -445,7 +466,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         if constexpr (HIST) {
             if (a.hist && a.group_index) {
                 const uint32_t *h = reinterpret_cast<const uint32_t *>(smem8 + g.hist_off);
-                for (int i = tid; i < BCH * g.N; i += 2 * NW * 32) {
+                for (int i = tid; i < BCH * g.N; i += NW * 32) {
                     const int cslot = i / g.N;
                     const int64_t cg = chain0 + cslot;
                     const uint32_t v = h[i];
