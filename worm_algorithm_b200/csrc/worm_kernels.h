@@ -44,10 +44,11 @@ cudaError_t launch_mt(int L, int64_t n_chains, int64_t n_pad, const MtChain *d_p
 cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, bool lowt, int smem_optin, int sm_count,
                           cudaStream_t st, const char **why);
 
-// the two kernels behind launch_philox
-size_t lat_smem_bytes(int L, int G, bool hist);       // 0 if L is not a power of two >= 4
-int lat_chains_per_block(int G);
-cudaError_t launch_philox_lat(const PhiloxArgs &a, int G, bool lowt, cudaStream_t st);
+// the two kernels behind launch_philox.  G = lanes_per_chain of the C ABI (4 / 8 / 32 <-> 8 / 4 / 1
+// chains per walker warp of the latency kernel).
+size_t lat_smem_bytes(int L, int G, int smem_optin);           // 0 if this L / G cannot run in latency mode
+int lat_chains_per_block(int L, int G, int smem_optin);
+cudaError_t launch_philox_lat(const PhiloxArgs &a, int G, bool lowt, int smem_optin, cudaStream_t st);
 cudaError_t launch_philox_wide(const PhiloxArgs &a, bool force_global, int smem_optin, cudaStream_t st);
 
 cudaError_t launch_image(int L, int64_t n, const uint8_t *d_bonds, int32_t *d_img, cudaStream_t st);

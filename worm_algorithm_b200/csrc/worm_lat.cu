@@ -4,23 +4,29 @@
 // chains on 148 x 4 SM sub-partitions).  A chain is a sequence of dependent steps, so
 //     throughput = chains / (cycles per step),
 // and the kernel is built around the per-step critical path
-//     head --IADD,LOP3,IADD--> bond address --LDS--> occupation --ISETP--> accept --SEL--> head.
+//     head --IADD--> bond address --LDS--> occupation --IADD,SHF,LOP3--> head.
 //
-// Warp specialisation.  A block is 4 WALKER warps + 4 PRODUCER warps (warp w and warp 4+w form a
-// pair that lands on the same SM sub-partition, so the hardware scheduler fills the walker's
-// dependency stalls with the producer's independent instructions):
+// Warp specialisation.  A block is nw PRODUCER warps + nw WALKER warps (warp w and warp nw+w form
+// a pair that lands on the same SM sub-partition, so the hardware scheduler fills the walker's
+// dependency stalls with the producer's independent instructions; walkers are the high warps
+// because the sub-partition arbiter prefers the higher warp id):
 //   * a producer lane draws Philox blocks (two steps each) for the chains of its pair and turns
 //     them, ahead of time, into ready-to-use step records: pre-decoded head increment and wrap
-//     mask, absolute shared-memory address of the bond array (+ y bit), kick site, occupation
-//     threshold.  Records go into a double-buffered shared-memory ring, one round (R steps per
-//     chain) per buffer; pairs meet at a named barrier (bar.sync, 64 threads) once per round.
-//   * a walker warp owns CH = 8, 4 or 1 chains, one per lane; its other lanes are predicated off
-//     (SIMD lanes are free here, warp issue slots and shared-memory wavefronts are not: a 128-bit
-//     load by 8 lanes is one wavefront, by 32 lanes four).  Records are fetched two steps ahead,
-//     and the kick that follows a closing move is folded into the accept select, so the
-//     head -> head dependency of consecutive steps is a single select after the accept test.
-//     Walkers are the block's high warps: the sub-partition arbiter prefers the higher warp id.
-// Power-of-two L only: the head is a doubled site index whose x and y bit fields wrap by masking.
+//     mask, absolute shared-memory addresses of the two copies of the bond, kick site, occupation
+//     threshold and accept polarity.  Records go into a double-buffered shared-memory ring, one
+//     round (R steps per chain) per buffer; a pair meets at a named barrier once per round.
+//   * a walker warp owns CH = 8, 4 or 1 chains, one per lane; its other lanes retire at once
+//     (SIMD lanes are free here; warp issue slots and shared-memory wavefronts are not: a 128-bit
+//     load by 8 lanes is one wavefront, by 32 lanes four).  Records are fetched two steps ahead.
+//     The kick that follows a closing move is folded into the accept select and the select is a
+//     bit mask ((nb - thr) >> 31, xor polarity, LOP3), so no predicate sits on the head -> head path.
+// Bond storage ("dual" layout): one 32-bit word per SITE holding the occupations of its four
+// bonds (+x, +y, -x, -y), words interleaved across the chains of the walker.  A bond is stored at
+// both of its sites, so the load address is head + constant (one IADD, no neighbour arithmetic on
+// the critical path), a chain only ever touches its own banks (no conflicts between the chains of
+// a warp), and an accepted move stores twice off the critical path.  Lattices whose dual layout
+// does not fit use the compact one-byte-per-bond layout (one chain per walker).
+// Power-of-two L only: the head is a scaled site index whose x and y bit fields wrap by masking.
 //
 // Algorithm and random stream: oracle/worm_oracle.c:worm_oracle_philox_run (bit-for-bit), i.e. the
 // reference loop worm_ising_2d.cpp:111-157 on a Philox4x32-10 stream.
@@ -32,22 +38,20 @@ namespace worm {
 
 namespace {
 
-constexpr int NW = 4;                  // walker warps per block (= producer warps)
-
 struct LatGeo {
-    int L, N, nb2;       // nb2 = 2N bytes of bond storage per chain (uint8 per bond)
-    int XM;              // 2L - 2: x field of a doubled site index
-    int YM;              // (2N - 1) & ~(2L - 1): its y field
-    int rec_off;         // byte offsets inside dynamic shared memory
-    int hist_off;
+    int L, N, nb2;       // nb2 = 2N bonds per chain
+    int nw;              // walker (= producer) warps per block
+    int SC;              // bytes per unit of the scaled site index (dual: 4 * CH, compact: 2)
+    int XM, YM;          // x / y bit fields of a scaled site index
+    int region;          // bytes of bond storage per walker warp
+    int rec_off;         // byte offset of the record rings inside dynamic shared memory
+    int lowt;            // some chain has T < 1 (general record builder)
+    int zero;            // 0 (a value the compiler cannot see through)
 };
 
-template <int G> struct LatCfg {
-    static constexpr int CH = 32 / G;                 // chains per walker warp
-    static constexpr int BCH = NW * CH;               // chains per block
-    static constexpr int U = (G == 4) ? 2 : 1;        // Philox blocks per producer lane per round
+template <int CH> struct LatCfg {
+    static constexpr int U = (CH == 8) ? 2 : 1;       // Philox blocks per producer lane per round
     static constexpr int R = 64 * U / CH;             // steps per chain per round
-    static constexpr int PR = R / 2;                  // Philox blocks (pairs of steps) per chain per round
     static constexpr int BUF = R * CH * 16;           // bytes of one buffer of A (or B) records
     static constexpr int REC_B = 2 * BUF;             // byte offset of the B records (two buffers of A first)
     static constexpr int RECW = 4 * BUF;              // record bytes per walker warp
@@ -59,6 +63,12 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
 {
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr)
@@ -77,35 +87,42 @@ __device__ __forceinline__ void pair_barrier(int id)
 }
 
 struct LatState {
-    int head2, tail2;    // doubled site indices in [0, 2N)
-    uint32_t closed;     // 0 / 1.  When 1, head2 already holds the (folded) kick of the coming step.
+    int head, tail;      // scaled site indices (site * SC)
+    uint32_t closed;     // 0 / 1.  When 1, head already holds the (folded) kick of the coming step.
     int Nb, npar;
     uint32_t z32, snb32, sn32;           // partial sums, flushed once per round
     uint64_t Z, SNb, SNb2, Sn, Sn2;
 };
 
 // A step record: everything about step s that does not depend on the chain's state.
-//   ra = {add, keep, addneg, base}:  nh2  = (head2 & keep) | ((head2 + add) & ~keep)      new head
-//                                    own2 = (head2 & keep) | ((head2 + addneg) & ~keep)   site owning the bond
-//                                    bond address = own2 + base      (base = chain's bonds + y bit)
-//   rb = {kick2, thr, delta, -}:     accept iff (nb < thr) != (delta < 0);  Taylor: nb += delta
-template <int ALGO, bool LOWT>
+//   ra = {add, keep, p, q}:  new head  nh = (head & keep) | ((head + add) & ~keep)
+//        dual:    p = address of slot d of site 0, q = address of slot d^2 of site 0:
+//                 the bond is read at head + p and written at head + p and nh + q
+//        compact: p = addneg, q = address of bond byte (y bit) of site 0: the bond is owned by
+//                 own = (head & keep) | ((head + addneg) & ~keep) and lives at own + q
+//   rb = {kick, thr, flip, delta}:  accept iff ((nb < thr) ? ~0 : 0) ^ flip;  Taylor: nb += delta
+template <int ALGO, bool DUAL>
 __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &prm, uint32_t a, uint32_t b,
-                                            uint32_t bonds_abs, uint4 &ra, uint4 &rb)
+                                            uint32_t chain_abs, uint4 &ra, uint4 &rb)
 {
-    const uint32_t d = b >> 30;
+    const uint32_t d = b >> 30;                                  // :137
     const bool ym = d & 1u, neg = d & 2u;
-    const int stepsz = ym ? 2 * g.L : 2;
+    const int stepsz = ym ? g.L * g.SC : g.SC;
     const int add = neg ? -stepsz : stepsz;
     ra.x = (uint32_t)add;
     ra.y = ym ? ~(uint32_t)g.YM : ~(uint32_t)g.XM;
-    ra.z = neg ? (uint32_t)add : 0u;
-    ra.w = bonds_abs + (uint32_t)ym;
-    rb.x = 2u * __umulhi(b << 3, (uint32_t)g.N);                 // kick site :128
+    if constexpr (DUAL) {
+        ra.z = chain_abs + d;
+        ra.w = chain_abs + (d ^ 2u);
+    } else {
+        ra.z = neg ? (uint32_t)add : 0u;
+        ra.w = chain_abs + (uint32_t)ym;
+    }
+    rb.x = (uint32_t)g.SC * __umulhi(b << 3, (uint32_t)g.N);     // kick site :128
     if constexpr (ALGO == ALGO_TAYLOR) {
         const bool dec = (b >> 29) & 1u;                         // :141
         uint32_t qi, qd;
-        if constexpr (!LOWT) {
+        if (!g.lowt) {
             // T >= 1: kfix - 1 < 2^32 and tfix >= 2^32 > a.
             // (nb+1)*a < kfix  <=>  nb < floor((kfix-1)/a); a == 0 accepts up to the storage cap.
             const uint32_t num = (uint32_t)(prm.kfix - 1);
@@ -120,33 +137,34 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
             qd = (uint32_t)(q2 < 256ull ? q2 : 256ull);
         }
         rb.y = dec ? qd : qi;
-        rb.z = dec ? 0xffffffffu : 1u;
+        rb.z = dec ? 0xffffffffu : 0u;
+        rb.w = dec ? 0xffffffffu : 1u;
     } else {
         rb.y = ((uint64_t)a < prm.hfix) ? 0u : 1u;               // accept iff nb >= thr (occupied: always)
         rb.z = 0xffffffffu;
+        rb.w = 0u;
     }
-    rb.w = 0u;
 }
 
-// One worm step on a pre-decoded record.  On entry head2 already holds this step's kick when the
-// worm is closed; on exit it holds the NEXT step's kick (kick2_next) when the worm is closed then.
-template <int ALGO, bool HIST, bool MEAS>
-__device__ __forceinline__ void lat_step(const LatGeo &g, uint32_t hist_abs, uint32_t hist_writer,
-                                         LatState &c, const uint4 ra, const uint4 rb, const int kick2_next)
+// One worm step on a pre-decoded record.  On entry `head` already holds this step's kick when the
+// worm is closed; on exit it holds the NEXT step's kick (kick_next) when the worm is closed then.
+template <int ALGO, bool DUAL, int SCSH, bool HIST, bool MEAS>
+__device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long hist_row, uint32_t hist_writer,
+                                         LatState &c, const uint4 ra, const uint4 rb, const int kick_next)
 {
-    const int add = (int)ra.x, keep = (int)ra.y, addneg = (int)ra.z;
-    const uint32_t base = ra.w;
-    const int kick2 = (int)rb.x, delta = (int)rb.z;
-    const uint32_t thr = rb.y;
+    const int add = (int)ra.x, keep = (int)ra.y;
+    const int kick = (int)rb.x, delta = (int)rb.w;
+    const uint32_t thr = rb.y, flip = rb.z;
     const bool closed = c.closed != 0u;
     if constexpr (MEAS) {
         if constexpr (HIST) {
             // G(r) bin of (head - tail) before the kick; a closed worm is bin 0
-            const int t1 = c.head2 - c.tail2;
-            const int t2 = (c.head2 | g.XM | 1) - (c.tail2 & g.YM);            // y fields, no borrow from x
-            const int bin4 = closed ? 0 : (((t1 & g.XM) | (t2 & g.YM)) << 1);  // byte offset of the u32 bin
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}"
-                         :: "r"(hist_abs + (uint32_t)bin4), "r"(hist_writer) : "memory");
+            const int t1 = c.head - c.tail;
+            const int t2 = (c.head | g.XM | (g.SC - 1)) - (c.tail & g.YM);          // y fields, no borrow from x
+            const uint32_t f = closed ? 0u : (uint32_t)((t1 & g.XM) | (t2 & g.YM)); // site difference * SC
+            const uint32_t off8 = (SCSH >= 3) ? (f >> (SCSH - 3)) : (f << (3 - SCSH));
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.global.add.u64 [%0], 1;\n\t}"
+                         :: "l"(hist_row + off8), "r"(hist_writer) : "memory");
         }
         if (closed) {                                           // worm_ising_2d.cpp:130-132
             c.z32 += 1u;
@@ -156,18 +174,37 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, uint32_t hist_abs, uin
             c.Sn2 += (uint64_t)(uint32_t)c.npar * (uint32_t)c.npar;
         }
     }
-    const int tail2 = closed ? kick2 : c.tail2;                 // kick :128-129 (head2 has it already)
-    c.tail2 = tail2;
-    const int head2 = c.head2;
-    const int t = head2 + add;
-    const int nh2 = (head2 & keep) | (t & ~keep);               // neighbour table :88-95
-    const int u = head2 + addneg;
-    const int own = (head2 & keep) | (u & ~keep);               // bond_number :214-244
-    const uint32_t addr = (uint32_t)own + base;
+    const int tail = closed ? kick : c.tail;                    // kick :128-129 (head has it already)
+    c.tail = tail;
+    const int head = c.head;
+    uint32_t addr, addr2 = 0u;
+    const int t = head + add;
+    const int nh = (head & keep) | (t & ~keep);                 // neighbour table :88-95
+    if constexpr (DUAL) {
+        addr = (uint32_t)head + ra.z;                           // bond_number :214-244: slot d of this site ...
+        addr2 = (uint32_t)nh + ra.w;                            // ... and slot d^2 of the neighbour
+    } else {
+        const int u = head + (int)ra.z;
+        const int own = (head & keep) | (u & ~keep);
+        addr = (uint32_t)own + ra.w;
+    }
     const uint32_t nb = lds_u8(addr);                           // :139
-    const uint32_t pc = (nh2 == tail2) ? 1u : 0u;               // closed after an accepted move?
-    const int A = pc ? kick2_next : nh2;
-    const int B = closed ? kick2_next : head2;
+    // ---- everything from here to the `sub` below is independent of the load and must sit in its
+    // shadow (the warp issues in order and stalls at the first consumer of nb)
+    const uint32_t pc = (nh == tail) ? 1u : 0u;                 // closed after an accepted move?
+    const int A = pc ? kick_next : nh;                          // head if accepted (kick folded in)
+    const int B = closed ? kick_next : head;                    // head if rejected
+    const int Ap = (A & ~(int)flip) | (B & (int)flip);          // pre-swapped by the accept polarity, so the
+    const int Bp = (B & ~(int)flip) | (A & (int)flip);          // select below needs no xor
+    // thr | 0, written so that the compiler has to finish Ap / Bp before the first consumer of nb
+    const uint32_t thrx = thr | ((uint32_t)(Ap | Bp) & (uint32_t)g.zero);
+    // accept test (:151) as a bit mask, m0 = (nb - thr) >> 31 (all ones iff nb < thr); head select
+    // = one LOP3.  No predicate on the head -> head path.  (asm: the compiler must not turn the
+    // shift back into compare + select.)
+    int m0;
+    asm volatile("{\n\t.reg .s32 d;\n\tsub.s32 d, %1, %2;\n\tshr.s32 %0, d, 31;\n\t}" : "=r"(m0) : "r"(nb), "r"(thrx));
+    c.head = (Ap & m0) | (Bp & ~m0);
+    const int m = m0 ^ (int)flip;                               // all ones iff accepted
     uint32_t nn;
     int dNb, dn;
     if constexpr (ALGO == ALGO_TAYLOR) {
@@ -179,28 +216,14 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, uint32_t hist_abs, uin
         dNb = 1 - 2 * (int)nb;
         dn = dNb;
     }
-    // accept test (:151), head select and bond store (:152-154) in one opaque block: the compiler
-    // must not re-associate "closed ? kick : ..." across the select (that puts two more operations
-    // on the head -> head critical path)
-    int head_new;
-    uint32_t acc_i;
-    asm volatile("{\n\t.reg .pred pa, pd;\n\t"
-                 "setp.lt.u32 pa, %2, %3;\n\t"
-                 "setp.lt.s32 pd, %4, 0;\n\t"
-                 "xor.pred pa, pa, pd;\n\t"
-                 "selp.b32 %0, %5, %6, pa;\n\t"
-                 "selp.u32 %1, 1, 0, pa;\n\t"
-                 "@pa st.shared.u8 [%7], %8;\n\t}"
-                 : "=r"(head_new), "=r"(acc_i)
-                 : "r"(nb), "r"(thr), "r"(delta), "r"(A), "r"(B), "r"(addr), "r"(nn)
-                 : "memory");
-    const bool acc = acc_i != 0u;
-    if (acc) {
-        c.Nb += dNb;
-        c.npar += dn;
-    }
-    c.head2 = head_new;
-    c.closed = acc ? pc : c.closed;
+    // unconditional stores of the selected occupation (:152-154): a predicated store would wait for
+    // a predicate in front of the next step's load
+    const uint32_t nsel = (nn & (uint32_t)m) | (nb & ~(uint32_t)m);
+    asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr), "r"(nsel) : "memory");
+    if constexpr (DUAL) asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr2), "r"(nsel) : "memory");
+    c.Nb += dNb & m;
+    c.npar += dn & m;
+    c.closed = (pc & (uint32_t)m) | (c.closed & ~(uint32_t)m);
 }
 
 __device__ __forceinline__ void flush_partials(LatState &c)
@@ -226,39 +249,63 @@ __device__ __forceinline__ Round make_round(uint64_t s, uint64_t seg_end)
     return r;
 }
 
-template <int ALGO, int G, bool HIST, bool LOWT>
-__global__ void __launch_bounds__(2 * NW * 32)
+// ---- bond storage <-> the caller's compact uint8 [2N] array (bond 2*site = +x, 2*site+1 = +y)
+// dual: word of site s of chain slot q (within its walker) at region + (s * CH + q) * 4
+template <int CH>
+__device__ __forceinline__ uint32_t dual_word(const uint8_t *gb, int s, int L, int N)
+{
+    const int x = s & (L - 1);
+    const int left = (x == 0) ? s + L - 1 : s - 1;
+    const int down = (s < L) ? s + N - L : s - L;
+    const uint32_t xy = *reinterpret_cast<const uint16_t *>(gb + 2 * s);        // +x | +y << 8
+    return xy | ((uint32_t)gb[2 * left] << 16) | ((uint32_t)gb[2 * down + 1] << 24);
+}
+
+template <int ALGO, int CH, bool DUAL, bool HIST>
+__global__ void __launch_bounds__(256)
 worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
 {
-    using Cfg = LatCfg<G>;
-    constexpr int R = Cfg::R, CH = Cfg::CH, BCH = Cfg::BCH, PR = Cfg::PR, U = Cfg::U;
+    using Cfg = LatCfg<CH>;
+    constexpr int R = Cfg::R, U = Cfg::U;
+    constexpr int SC = DUAL ? 4 * CH : 2;
+    constexpr int SCSH = (SC == 2) ? 1 : (SC == 4) ? 2 : (SC == 16) ? 4 : 5;
+    static_assert(DUAL || CH == 1, "the compact layout is one chain per walker");
     extern __shared__ __align__(16) uint8_t smem8[];
     const int tid = threadIdx.x;
+    const int nthreads = blockDim.x;
+    const int nw = g.nw;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int w = warp & (NW - 1);                       // pair index: warps w and NW + w share a sub-partition
-    const bool is_producer = warp < NW;                  // walkers are the high warps (arbiter priority)
-    const int64_t chain0 = (int64_t)blockIdx.x * BCH;    // first chain of the block
+    const bool is_producer = warp < nw;                  // walkers are the high warps (arbiter priority)
+    const int w = is_producer ? warp : warp - nw;        // pair index: warps w and nw + w share a sub-partition when nw = 4
+    const int bch = nw * CH;                             // chains per block
+    const int64_t chain0 = (int64_t)blockIdx.x * bch;    // first chain of the block
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem8);
     const uint32_t rec_w = sbase + (uint32_t)g.rec_off + (uint32_t)(w * Cfg::RECW);
     const int bar_id = 1 + w;
 
-    // ---- stage the block's bonds (all 8 warps, 16-byte vectors)
-    {
+    // ---- stage the block's bonds (all warps)
+    if constexpr (DUAL) {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(smem8);
+        const int total = bch * g.N;                     // words; index = (walker * N + s) * CH + q
+        for (int i = tid; i < total; i += nthreads) {
+            const int q = i % CH;
+            const int ws = i / CH;
+            const int wk = ws / g.N, s = ws - wk * g.N;
+            const int64_t cg = chain0 + wk * CH + q;
+            dst[i] = (cg < a.n_chains) ? dual_word<CH>(a.bonds + cg * (int64_t)g.nb2, s, g.L, g.N) : 0u;
+        }
+    } else {
         const int vec_per_chain = g.nb2 / 16;
-        const int total = BCH * vec_per_chain;
+        const int total = bch * vec_per_chain;
         uint4 *dst = reinterpret_cast<uint4 *>(smem8);
-        for (int i = tid; i < total; i += 2 * NW * 32) {
+        for (int i = tid; i < total; i += nthreads) {
             const int cslot = i / vec_per_chain;
             const int64_t cg = chain0 + cslot;
             uint4 v = make_uint4(0, 0, 0, 0);
             if (cg < a.n_chains)
                 v = reinterpret_cast<const uint4 *>(a.bonds + cg * (int64_t)g.nb2)[i - cslot * vec_per_chain];
             dst[i] = v;
-        }
-        if constexpr (HIST) {
-            uint32_t *h = reinterpret_cast<uint32_t *>(smem8 + g.hist_off);
-            for (int i = tid; i < BCH * g.N; i += 2 * NW * 32) h[i] = 0u;
         }
     }
     __syncthreads();
@@ -268,7 +315,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         // Philox block b = u*32 + lane of a round belongs to chain slot q = b % CH, pair p = b / CH:
         // consecutive lanes store consecutive 16-byte records (conflict-free 128-bit stores).
         PhiloxChain prm[U];
-        uint32_t c2[U], c3[U], bonds_abs[U], rec_q[U];
+        uint32_t c2[U], c3[U], chain_abs[U], rec_q[U];
         int p_of[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -280,7 +327,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             prm[u] = a.prm[cl];
             const uint64_t chain_id = a.chain_id0 + (uint64_t)cl;
             c2[u] = (uint32_t)chain_id; c3[u] = (uint32_t)(chain_id >> 32);
-            bonds_abs[u] = sbase + (uint32_t)((w * CH + q) * g.nb2);
+            chain_abs[u] = sbase + (uint32_t)(w * g.region) + (DUAL ? (uint32_t)q * 4u : 0u);
             rec_q[u] = rec_w + (uint32_t)q * 16u + (uint32_t)(2 * p_of[u]) * (CH * 16);
         }
         uint32_t buf = 0u;
@@ -296,8 +343,8 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     const uint4 r = philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), c2[u], c3[u],
                                                   (uint32_t)prm[u].seed, (uint32_t)(prm[u].seed >> 32));
                     uint4 ra0, rb0, ra1, rb1;
-                    make_record<ALGO, LOWT>(g, prm[u], r.x, r.y, bonds_abs[u], ra0, rb0);
-                    make_record<ALGO, LOWT>(g, prm[u], r.z, r.w, bonds_abs[u], ra1, rb1);
+                    make_record<ALGO, DUAL>(g, prm[u], r.x, r.y, chain_abs[u], ra0, rb0);
+                    make_record<ALGO, DUAL>(g, prm[u], r.z, r.w, chain_abs[u], ra1, rb1);
                     const uint32_t p0 = rec_q[u] + buf;
                     sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0);
                     sts_v4(p0 + CH * 16, ra1); sts_v4(p0 + CH * 16 + Cfg::REC_B, rb1);
@@ -315,32 +362,44 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         if (lane >= CH) return;
         constexpr unsigned wmask = (CH == 32) ? 0xffffffffu : ((1u << CH) - 1u);
         const int q = lane;                  // chain slot within the warp
-        const int cslot = w * CH + q;
-        const int64_t cidx = chain0 + cslot;
+        const int64_t cidx = chain0 + w * CH + q;
         const bool live = cidx < a.n_chains;
         const int64_t cl = live ? cidx : 0;  // dead slots shadow chain 0 in their own shared-memory slot, never write
-        const uint8_t *bonds = smem8 + cslot * g.nb2;
+        const uint32_t region_abs = sbase + (uint32_t)(w * g.region);
         uint32_t rec_q = rec_w + (uint32_t)q * 16u;
-        uint32_t hist_abs = sbase + (uint32_t)g.hist_off + (uint32_t)(cslot * g.N) * 4u;
-        const uint32_t hist_writer = (HIST && live && a.hist != nullptr) ? 1u : 0u;
-        asm volatile("" : "+r"(rec_q), "+r"(hist_abs));                  // keep them in registers
+        asm volatile("" : "+r"(rec_q));                                  // keep it in a register
+        unsigned long long hist_row = 0ull;
+        uint32_t hist_writer = 0u;
+        if constexpr (HIST) {
+            if (live && a.hist && a.group_index) {
+                hist_row = (unsigned long long)(a.hist + (int64_t)a.group_index[cl] * g.N);
+                hist_writer = 1u;
+            }
+        }
 
         LatState c;
-        c.head2 = 2 * a.head[cl];
-        c.tail2 = 2 * a.tail[cl];
-        c.closed = (c.head2 == c.tail2) ? 1u : 0u;
+        c.head = SC * a.head[cl];
+        c.tail = SC * a.tail[cl];
+        c.closed = (c.head == c.tail) ? 1u : 0u;
         c.z32 = c.snb32 = c.sn32 = 0u;
         const int64_t *ac0 = a.acc + cl * ACC_STRIDE;
         c.Z = (uint64_t)ac0[0]; c.SNb = (uint64_t)ac0[1]; c.SNb2 = (uint64_t)ac0[2];
         c.Sn = (uint64_t)ac0[3]; c.Sn2 = (uint64_t)ac0[4];
         {
             int Nb = 0, npar = 0;
-            const uint4 *src = reinterpret_cast<const uint4 *>(bonds);
-            for (int i = 0; i < g.nb2 / 16; ++i) {
-                const uint4 v = src[i];
-                Nb += (int)(__vsadu4(v.x, 0) + __vsadu4(v.y, 0) + __vsadu4(v.z, 0) + __vsadu4(v.w, 0));
-                npar += __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) +
-                        __popc(v.w & 0x01010101u);
+            if constexpr (DUAL) {
+                for (int s = 0; s < g.N; ++s) {
+                    const uint32_t v = lds_u32(region_abs + (uint32_t)((s * CH + q) * 4)) & 0xffffu;
+                    Nb += (int)__vsadu4(v, 0);
+                    npar += __popc(v & 0x0101u);
+                }
+            } else {
+                for (int i = 0; i < g.nb2 / 16; ++i) {
+                    const uint4 v = lds_v4(region_abs + (uint32_t)(i * 16));
+                    Nb += (int)(__vsadu4(v.x, 0) + __vsadu4(v.y, 0) + __vsadu4(v.z, 0) + __vsadu4(v.w, 0));
+                    npar += __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) +
+                            __popc(v.w & 0x01010101u);
+                }
             }
             c.Nb = Nb; c.npar = npar;
         }
@@ -360,7 +419,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 if (j == R - 2) pair_barrier(bar_id);
                 const uint32_t nrec = (j < R - 2) ? rec_addr(cur, j + 2) : rec_addr(nxt, j + 2 - R);
                 const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
-                lat_step<ALGO, HIST, MEAS>(g, hist_abs, hist_writer, c, p0a, p0b, (int)p1b.x);
+                lat_step<ALGO, DUAL, SCSH, HIST, MEAS>(g, hist_row, hist_writer, c, p0a, p0b, (int)p1b.x);
                 p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
             }
             if constexpr (MEAS) flush_partials(c);
@@ -375,7 +434,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 uint32_t nrec = rec_addr(cur, j + 1);
                 if (j == je - 1) { pair_barrier(bar_id); nrec = rec_addr(nxt, jbn); }
                 const uint4 nb_ = lds_v4(nrec + Cfg::REC_B);
-                lat_step<ALGO, HIST, MEAS>(g, hist_abs, hist_writer, c, xa, xb, (int)nb_.x);
+                lat_step<ALGO, DUAL, SCSH, HIST, MEAS>(g, hist_row, hist_writer, c, xa, xb, (int)nb_.x);
             }
             flush_partials(c);
         };
@@ -388,7 +447,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             bool meas, dump_first;
             const uint64_t seg_end = next_segment(a, s, meas, dump_first);
             if (dump_first) {                                        // worm_ising_2d.cpp:113-124
-                // the whole warp copies the bonds of every chain that dumps now
+                // the walker's live lanes copy the bonds of every chain that dumps now
                 const bool want = live && c.closed;
                 const bool store = want && nd < a.max_dumps;
                 if (store && a.events) {
@@ -401,9 +460,15 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     dm &= dm - 1;
                     const long long chain = __shfl_sync(wmask, (long long)cl, src_lane);
                     const int slot = __shfl_sync(wmask, nd, src_lane);
-                    uint4 *dst = reinterpret_cast<uint4 *>(a.dumps + (chain * a.max_dumps + slot) * g.nb2);
-                    const uint4 *src = reinterpret_cast<const uint4 *>(smem8 + (w * CH + src_lane) * g.nb2);
-                    for (int i = lane; i < g.nb2 / 16; i += CH) dst[i] = src[i];
+                    uint8_t *dstb = a.dumps + (chain * a.max_dumps + slot) * g.nb2;
+                    if constexpr (DUAL) {
+                        uint16_t *dst = reinterpret_cast<uint16_t *>(dstb);
+                        for (int sI = lane; sI < g.N; sI += CH)
+                            dst[sI] = (uint16_t)lds_u32(region_abs + (uint32_t)((sI * CH + src_lane) * 4));
+                    } else {
+                        uint4 *dst = reinterpret_cast<uint4 *>(dstb);
+                        for (int i = lane; i < g.nb2 / 16; i += CH) dst[i] = lds_v4(region_abs + (uint32_t)(i * 16));
+                    }
                 }
                 if (want) ++nd;
             }
@@ -415,7 +480,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 if (first) {
                     pair_barrier(bar_id);                            // the first round's records are complete
                     const uint4 kb = lds_v4(rec_addr(cur, rd.jb) + Cfg::REC_B);
-                    c.head2 = c.closed ? (int)kb.x : c.head2;        // kick of the first step
+                    c.head = c.closed ? (int)kb.x : c.head;          // kick of the first step
                     first = false;
                 }
                 if (full) {
@@ -438,9 +503,9 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
 
         if (first) pair_barrier(bar_id);                             // empty step range: meet the producer once
         if (live) {
-            // a closed worm sits on its tail (head2 holds the folded kick of the step after the last)
-            a.head[cl] = (c.closed ? c.tail2 : c.head2) >> 1;
-            a.tail[cl] = c.tail2 >> 1;
+            // a closed worm sits on its tail (head holds the folded kick of the step after the last)
+            a.head[cl] = (c.closed ? c.tail : c.head) / SC;
+            a.tail[cl] = c.tail / SC;
             int64_t *ac = a.acc + cl * ACC_STRIDE;
             const int64_t iters = measured_iters(a);
             add_group_acc(a, cl, ac, c.Z, c.SNb, c.SNb2, c.Sn, c.Sn2, iters);
@@ -454,104 +519,120 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
     // ---- write back (the producer warps: the walkers' spare lanes have retired)
     __syncthreads();
     if (is_producer) {
-        const int vec_per_chain = g.nb2 / 16;
-        const int total = BCH * vec_per_chain;
-        const uint4 *src = reinterpret_cast<const uint4 *>(smem8);
-        for (int i = tid; i < total; i += NW * 32) {
-            const int cslot = i / vec_per_chain;
-            const int64_t cg = chain0 + cslot;
-            if (cg < a.n_chains)
-                reinterpret_cast<uint4 *>(a.bonds + cg * (int64_t)g.nb2)[i - cslot * vec_per_chain] = src[i];
-        }
-        if constexpr (HIST) {
-            if (a.hist && a.group_index) {
-                const uint32_t *h = reinterpret_cast<const uint32_t *>(smem8 + g.hist_off);
-                for (int i = tid; i < BCH * g.N; i += NW * 32) {
-                    const int cslot = i / g.N;
-                    const int64_t cg = chain0 + cslot;
-                    const uint32_t v = h[i];
-                    if (cg < a.n_chains && v) {
-                        unsigned long long *row =
-                            reinterpret_cast<unsigned long long *>(a.hist + (int64_t)a.group_index[cg] * g.N);
-                        atomicAdd(row + (i - cslot * g.N), (unsigned long long)v);
-                    }
-                }
+        const int pthreads = nw * 32;
+        if constexpr (DUAL) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(smem8);
+            const int total = bch * g.N;
+            for (int i = tid; i < total; i += pthreads) {
+                const int q = i % CH;
+                const int ws = i / CH;
+                const int wk = ws / g.N, s = ws - wk * g.N;
+                const int64_t cg = chain0 + wk * CH + q;
+                if (cg < a.n_chains)
+                    reinterpret_cast<uint16_t *>(a.bonds + cg * (int64_t)g.nb2)[s] = (uint16_t)src[i];
+            }
+        } else {
+            const int vec_per_chain = g.nb2 / 16;
+            const int total = bch * vec_per_chain;
+            const uint4 *src = reinterpret_cast<const uint4 *>(smem8);
+            for (int i = tid; i < total; i += pthreads) {
+                const int cslot = i / vec_per_chain;
+                const int64_t cg = chain0 + cslot;
+                if (cg < a.n_chains)
+                    reinterpret_cast<uint4 *>(a.bonds + cg * (int64_t)g.nb2)[i - cslot * vec_per_chain] = src[i];
             }
         }
     }
 }
 
-// shared memory layout of a latency-mode block with G lanes per chain (false if L is not a power of two >= 4)
-bool lat_geometry(int L, int G, bool hist, LatGeo &g, size_t &total)
+// ---- launch geometry: layout, warps per block and shared memory for a lattice and CH chains per walker
+struct LatPlan {
+    bool ok = false;
+    bool dual = false;
+    LatGeo g{};
+    size_t smem = 0;
+};
+
+LatPlan lat_plan(int L, int CH, int smem_optin)
 {
-    if (L < 4 || (L & (L - 1))) return false;
-    g.L = L; g.N = L * L; g.nb2 = 2 * g.N;
-    g.XM = 2 * L - 2;
-    g.YM = (g.nb2 - 1) & ~(2 * L - 1);
-    const int ch = 32 / G;
-    const int bch = NW * ch;
-    const int U = (G == 4) ? 2 : 1;
-    const int R = 64 * U / ch;
-    g.rec_off = bch * g.nb2;
-    g.hist_off = g.rec_off + NW * 4 * R * ch * 16;       // per pair: two buffers x (A, B) records
-    total = (size_t)g.hist_off + (hist ? (size_t)bch * g.N * 4 : 0);
-    return true;
+    LatPlan p;
+    if (L < 4 || (L & (L - 1)) || (CH != 8 && CH != 4 && CH != 1)) return p;
+    const int N = L * L;
+    const int U = (CH == 8) ? 2 : 1;
+    const int R = 64 * U / CH;
+    const size_t recw = (size_t)4 * R * CH * 16;
+    for (int dual = 1; dual >= 0; --dual) {
+        if (!dual && CH != 1) continue;
+        const size_t region = dual ? (size_t)4 * N * CH : (size_t)2 * N;
+        for (int nw : {4, 2, 1}) {
+            if (nw != 4 && CH != 1) continue;
+            const size_t need = nw * (region + recw);
+            if (need + 1024 > (size_t)smem_optin) continue;
+            p.ok = true; p.dual = dual; p.smem = need;
+            p.g.L = L; p.g.N = N; p.g.nb2 = 2 * N; p.g.nw = nw;
+            p.g.SC = dual ? 4 * CH : 2;
+            p.g.XM = (L - 1) * p.g.SC;
+            p.g.YM = (L - 1) * L * p.g.SC;
+            p.g.region = (int)region;
+            p.g.rec_off = (int)(nw * region);
+            p.g.lowt = 0;
+            p.g.zero = 0;
+            return p;
+        }
+    }
+    return p;
 }
 
-template <int ALGO, int G, bool HIST, bool LOWT>
-cudaError_t launch_lat(const PhiloxArgs &a, const LatGeo &g, size_t smem_bytes, cudaStream_t st)
+template <int ALGO, int CH, bool DUAL, bool HIST>
+cudaError_t launch_lat(const PhiloxArgs &a, const LatPlan &p, cudaStream_t st)
 {
-    auto kern = worm_lat_kernel<ALGO, G, HIST, LOWT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    auto kern = worm_lat_kernel<ALGO, CH, DUAL, HIST>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
-    constexpr int BCH = LatCfg<G>::BCH;
-    const int64_t blocks = (a.n_chains + BCH - 1) / BCH;
-    kern<<<(unsigned)blocks, 2 * NW * 32, smem_bytes, st>>>(a, g);
+    const int64_t bch = (int64_t)p.g.nw * CH;
+    const int64_t blocks = (a.n_chains + bch - 1) / bch;
+    kern<<<(unsigned)blocks, 2 * p.g.nw * 32, p.smem, st>>>(a, p.g);
     return cudaGetLastError();
 }
 
-template <int ALGO, int G>
-cudaError_t launch_lat_g(const PhiloxArgs &a, const LatGeo &g, bool hist, bool lowt, size_t smem_bytes, cudaStream_t st)
+template <int ALGO, bool HIST>
+cudaError_t launch_lat_ah(const PhiloxArgs &a, const LatPlan &p, int CH, cudaStream_t st)
 {
-    if (hist) {
-        if (lowt) return launch_lat<ALGO, G, true, true>(a, g, smem_bytes, st);
-        return launch_lat<ALGO, G, true, false>(a, g, smem_bytes, st);
-    }
-    if (lowt) return launch_lat<ALGO, G, false, true>(a, g, smem_bytes, st);
-    return launch_lat<ALGO, G, false, false>(a, g, smem_bytes, st);
-}
-
-template <int ALGO>
-cudaError_t launch_lat_a(const PhiloxArgs &a, const LatGeo &g, int G, bool hist, bool lowt, size_t smem_bytes, cudaStream_t st)
-{
-    switch (G) {
-    case 4: return launch_lat_g<ALGO, 4>(a, g, hist, lowt, smem_bytes, st);
-    case 8: return launch_lat_g<ALGO, 8>(a, g, hist, lowt, smem_bytes, st);
-    case 32: return launch_lat_g<ALGO, 32>(a, g, hist, lowt, smem_bytes, st);
+    if (!p.dual) return launch_lat<ALGO, 1, false, HIST>(a, p, st);
+    switch (CH) {
+    case 8: return launch_lat<ALGO, 8, true, HIST>(a, p, st);
+    case 4: return launch_lat<ALGO, 4, true, HIST>(a, p, st);
+    case 1: return launch_lat<ALGO, 1, true, HIST>(a, p, st);
     default: return cudaErrorInvalidValue;
     }
 }
 
 }  // namespace
 
-int lat_chains_per_block(int G) { return NW * (32 / G); }
-
-size_t lat_smem_bytes(int L, int G, bool hist)
+// G = lanes_per_chain of the C ABI: 4 / 8 / 32 <-> 8 / 4 / 1 chains per walker warp
+int lat_chains_per_block(int L, int G, int smem_optin)
 {
-    LatGeo g;
-    size_t total = 0;
-    if (G != 4 && G != 8 && G != 32) return 0;
-    return lat_geometry(L, G, hist, g, total) ? total : 0;
+    const LatPlan p = lat_plan(L, 32 / G, smem_optin);
+    return p.ok ? p.g.nw * (32 / G) : 0;
 }
 
-cudaError_t launch_philox_lat(const PhiloxArgs &a, int G, bool lowt, cudaStream_t st)
+size_t lat_smem_bytes(int L, int G, int smem_optin)
+{
+    if (G != 4 && G != 8 && G != 32) return 0;
+    const LatPlan p = lat_plan(L, 32 / G, smem_optin);
+    return p.ok ? p.smem : 0;
+}
+
+cudaError_t launch_philox_lat(const PhiloxArgs &a, int G, bool lowt, int smem_optin, cudaStream_t st)
 {
     const bool hist = (a.hist != nullptr && a.group_index != nullptr);
-    LatGeo g;
-    size_t total = 0;
-    if (!lat_geometry(a.L, G, hist, g, total)) return cudaErrorInvalidValue;
-    if (a.algo == ALGO_TAYLOR) return launch_lat_a<ALGO_TAYLOR>(a, g, G, hist, lowt, total, st);
-    return launch_lat_a<ALGO_BINARY>(a, g, G, hist, lowt, total, st);
+    LatPlan p = lat_plan(a.L, 32 / G, smem_optin);
+    if (!p.ok) return cudaErrorInvalidValue;
+    p.g.lowt = lowt ? 1 : 0;
+    const int CH = 32 / G;
+    if (a.algo == ALGO_TAYLOR)
+        return hist ? launch_lat_ah<ALGO_TAYLOR, true>(a, p, CH, st) : launch_lat_ah<ALGO_TAYLOR, false>(a, p, CH, st);
+    return hist ? launch_lat_ah<ALGO_BINARY, true>(a, p, CH, st) : launch_lat_ah<ALGO_BINARY, false>(a, p, CH, st);
 }
 
 }  // namespace worm

@@ -7,26 +7,25 @@ cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, bool lowt, i
                           cudaStream_t st, const char **why)
 {
     *why = "";
-    const bool hist = (a.hist != nullptr && a.group_index != nullptr);
     int G = lanes_per_chain;
     if (G == 0) {
-        // Latency mode while the batch fits one block (4 walker/producer warp pairs) per SM: among
-        // the G whose shared memory fits, the largest one; up to two blocks per SM with G = 4.
+        // Latency mode while the batch fits one block (up to 4 walker/producer warp pairs) per SM:
+        // among the chains-per-walker choices whose shared memory fits, the one with the fewest
+        // chains per walker; up to two blocks per SM with 8 chains per walker.
         G = 1;
         for (int cand : {4, 8, 32}) {
-            const size_t need = lat_smem_bytes(a.L, cand, hist);
-            if (need == 0 || need > (size_t)smem_optin) continue;
-            const int64_t bch = lat_chains_per_block(cand);
+            const size_t need = lat_smem_bytes(a.L, cand, smem_optin);
+            if (need == 0) continue;
+            const int64_t bch = lat_chains_per_block(a.L, cand, smem_optin);
             const int64_t blocks = (a.n_chains + bch - 1) / bch;
             if (blocks <= sm_count) G = cand;
             else if (G == 1 && cand == 4 && blocks <= 2 * (int64_t)sm_count && 2 * need + 2048 <= 228 * 1024) G = 4;
         }
     }
     if (G == 4 || G == 8 || G == 32) {
-        const size_t need = lat_smem_bytes(a.L, G, hist);
-        if (need == 0) { *why = "latency mode (lanes_per_chain 4/8/32) needs a power-of-two L >= 4"; return cudaErrorInvalidValue; }
-        if (need > (size_t)smem_optin) { *why = "lattice too large for latency mode with this lanes_per_chain"; return cudaErrorInvalidValue; }
-        return launch_philox_lat(a, G, lowt, st);
+        if (a.L < 4 || (a.L & (a.L - 1))) { *why = "latency mode (lanes_per_chain 4/8/32) needs a power-of-two L >= 4"; return cudaErrorInvalidValue; }
+        if (lat_smem_bytes(a.L, G, smem_optin) == 0) { *why = "lattice too large for latency mode with this lanes_per_chain"; return cudaErrorInvalidValue; }
+        return launch_philox_lat(a, G, lowt, smem_optin, st);
     }
     if (G != 1 && G != -1) { *why = "lanes_per_chain must be 0, 1, 4, 8, 32 or -1"; return cudaErrorInvalidValue; }
     return launch_philox_wide(a, G == -1, smem_optin, st);
