@@ -45,6 +45,7 @@ struct LatGeo {
     int XM, YM;          // x / y bit fields of a scaled site index
     int region;          // bytes of bond storage per walker warp
     int rec_off;         // byte offset of the record rings inside dynamic shared memory
+    int log_off;         // byte offset of the step logs
     int lowt;            // some chain has T < 1 (general record builder)
     int zero;            // 0 (a value the compiler cannot see through)
 };
@@ -55,6 +56,11 @@ template <int CH> struct LatCfg {
     static constexpr int BUF = R * CH * 16;           // bytes of one buffer of A (or B) records
     static constexpr int REC_B = 2 * BUF;             // byte offset of the B records (two buffers of A first)
     static constexpr int RECW = 4 * BUF;              // record bytes per walker warp
+    static constexpr int LOGH = R * CH;               // bytes of one accept (or closed) log of a round
+    static constexpr int LOGB = 2 * LOGH;             // one round's log: accept bytes, then closed bytes
+    static constexpr int LOGW = 3 * LOGB;             // three rounds in flight per walker warp
+    static constexpr int PARTS = 32 / CH;             // accountant lanes per chain
+    static constexpr int SP = R / PARTS;              // steps per accountant lane per round
 };
 
 // ---- shared memory by absolute 32-bit shared-window address.  All hot-loop accesses are volatile
@@ -89,9 +95,17 @@ __device__ __forceinline__ void pair_barrier(int id)
 struct LatState {
     int head, tail;      // scaled site indices (site * SC)
     uint32_t closed;     // 0 / 1.  When 1, head already holds the (folded) kick of the coming step.
-    int Nb, npar;
-    uint32_t z32, snb32, sn32;           // partial sums, flushed once per round
-    uint64_t Z, SNb, SNb2, Sn, Sn2;
+};
+
+// Observables are NOT accumulated by the walker (every instruction of its dependent chain costs
+// ~3 cycles of the step): it logs one byte per accepted step and one per closed step, and the
+// producer warp of the pair replays the log two rounds later (account_round below).
+//   accept log byte: 0x80 | (decrement ? 0x40 : 0) | (old occupation & 1);  0 = rejected
+//   closed log byte: non-zero iff the worm was closed at the start of the step
+struct Account {
+    int Nb, npar;                        // state at the start of the next round to be replayed (all lanes of a chain)
+    uint64_t Z, SNb, SNb2, Sn, Sn2;      // this lane's share of the sums
+    int32_t nd;                          // dump events seen (mirrors the walker's counter)
 };
 
 // A step record: everything about step s that does not depend on the chain's state.
@@ -100,7 +114,7 @@ struct LatState {
 //                 the bond is read at head + p and written at head + p and nh + q
 //        compact: p = addneg, q = address of bond byte (y bit) of site 0: the bond is owned by
 //                 own = (head & keep) | ((head + addneg) & ~keep) and lives at own + q
-//   rb = {kick, thr, flip, delta}:  accept iff ((nb < thr) ? ~0 : 0) ^ flip;  Taylor: nb += delta
+//   rb = {kick, thr, flip, logbits}:  accept iff (nb < thr) xor (flip != 0);  Taylor: nb += 1 | flip
 template <int ALGO, bool DUAL>
 __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &prm, uint32_t a, uint32_t b,
                                             uint32_t chain_abs, uint4 &ra, uint4 &rb)
@@ -138,42 +152,38 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
         }
         rb.y = dec ? qd : qi;
         rb.z = dec ? 0xffffffffu : 0u;
-        rb.w = dec ? 0xffffffffu : 1u;
+        rb.w = dec ? 0xc0u : 0x80u;                              // accept-log bits
     } else {
         rb.y = ((uint64_t)a < prm.hfix) ? 0u : 1u;               // accept iff nb >= thr (occupied: always)
         rb.z = 0xffffffffu;
-        rb.w = 0u;
+        rb.w = 0x80u;
     }
 }
 
 // One worm step on a pre-decoded record.  On entry `head` already holds this step's kick when the
 // worm is closed; on exit it holds the NEXT step's kick (kick_next) when the worm is closed then.
+// alog / clog: shared addresses of this step's accept / closed log bytes.
 template <int ALGO, bool DUAL, int SCSH, bool HIST, bool MEAS>
 __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long hist_row, uint32_t hist_writer,
-                                         LatState &c, const uint4 ra, const uint4 rb, const int kick_next)
+                                         LatState &c, const uint4 ra, const uint4 rb, const int kick_next,
+                                         const uint32_t alog, const uint32_t clog)
 {
     const int add = (int)ra.x, keep = (int)ra.y;
-    const int kick = (int)rb.x, delta = (int)rb.w;
-    const uint32_t thr = rb.y, flip = rb.z;
+    const int kick = (int)rb.x;
+    const uint32_t thr = rb.y, flip = rb.z, logbits = rb.w;
     const bool closed = c.closed != 0u;
-    if constexpr (MEAS) {
-        if constexpr (HIST) {
-            // G(r) bin of (head - tail) before the kick; a closed worm is bin 0
-            const int t1 = c.head - c.tail;
-            const int t2 = (c.head | g.XM | (g.SC - 1)) - (c.tail & g.YM);          // y fields, no borrow from x
-            const uint32_t f = closed ? 0u : (uint32_t)((t1 & g.XM) | (t2 & g.YM)); // site difference * SC
-            const uint32_t off8 = (SCSH >= 3) ? (f >> (SCSH - 3)) : (f << (3 - SCSH));
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.global.add.u64 [%0], 1;\n\t}"
-                         :: "l"(hist_row + off8), "r"(hist_writer) : "memory");
-        }
-        if (closed) {                                           // worm_ising_2d.cpp:130-132
-            c.z32 += 1u;
-            c.snb32 += (uint32_t)c.Nb;
-            c.sn32 += (uint32_t)c.npar;
-            c.SNb2 += (uint64_t)(uint32_t)c.Nb * (uint32_t)c.Nb;
-            c.Sn2 += (uint64_t)(uint32_t)c.npar * (uint32_t)c.npar;
-        }
+    if constexpr (MEAS && HIST) {
+        // G(r) bin of (head - tail) before the kick; a closed worm is bin 0
+        const int t1 = c.head - c.tail;
+        const int t2 = (c.head | g.XM | (g.SC - 1)) - (c.tail & g.YM);          // y fields, no borrow from x
+        const uint32_t f = closed ? 0u : (uint32_t)((t1 & g.XM) | (t2 & g.YM)); // site difference * SC
+        const uint32_t off8 = (SCSH >= 3) ? (f >> (SCSH - 3)) : (f << (3 - SCSH));
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.global.add.u64 [%0], 1;\n\t}"
+                     :: "l"(hist_row + off8), "r"(hist_writer) : "memory");
     }
+    // closed iteration (worm_ising_2d.cpp:130-132): logged, measured by the accountant
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u8 [%1], %2;\n\t}"
+                 :: "r"(c.closed), "r"(clog), "r"(logbits) : "memory");
     const int tail = closed ? kick : c.tail;                    // kick :128-129 (head has it already)
     c.tail = tail;
     const int head = c.head;
@@ -189,47 +199,93 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
         addr = (uint32_t)own + ra.w;
     }
     const uint32_t nb = lds_u8(addr);                           // :139
-    // ---- everything from here to the `sub` below is independent of the load and must sit in its
-    // shadow (the warp issues in order and stalls at the first consumer of nb)
     const uint32_t pc = (nh == tail) ? 1u : 0u;                 // closed after an accepted move?
     const int A = pc ? kick_next : nh;                          // head if accepted (kick folded in)
     const int B = closed ? kick_next : head;                    // head if rejected
-    const int Ap = (A & ~(int)flip) | (B & (int)flip);          // pre-swapped by the accept polarity, so the
-    const int Bp = (B & ~(int)flip) | (A & (int)flip);          // select below needs no xor
-    // thr | 0, written so that the compiler has to finish Ap / Bp before the first consumer of nb
-    const uint32_t thrx = thr | ((uint32_t)(Ap | Bp) & (uint32_t)g.zero);
-    // accept test (:151) as a bit mask, m0 = (nb - thr) >> 31 (all ones iff nb < thr); head select
-    // = one LOP3.  No predicate on the head -> head path.  (asm: the compiler must not turn the
-    // shift back into compare + select.)
-    int m0;
-    asm volatile("{\n\t.reg .s32 d;\n\tsub.s32 d, %1, %2;\n\tshr.s32 %0, d, 31;\n\t}" : "=r"(m0) : "r"(nb), "r"(thrx));
-    c.head = (Ap & m0) | (Bp & ~m0);
-    const int m = m0 ^ (int)flip;                               // all ones iff accepted
-    uint32_t nn;
-    int dNb, dn;
-    if constexpr (ALGO == ALGO_TAYLOR) {
-        nn = nb + (uint32_t)delta;
-        dNb = delta;
-        dn = 1 - 2 * (int)(nb & 1u);
+    const uint32_t nn = (ALGO == ALGO_TAYLOR) ? nb + (1u | flip) : (nb ^ 1u);
+    const uint32_t lg = (nb & 1u) | logbits;
+    // accept test (:151), head select, bond stores (:152-154) and the accept-log byte in one opaque
+    // block: the compiler must not re-associate "closed ? kick : ..." across the select.
+    int head_new;
+    uint32_t acc_i;
+    if constexpr (DUAL) {
+        asm volatile("{\n\t.reg .pred pa, pd;\n\t"
+                     "setp.lt.u32 pa, %2, %3;\n\t"
+                     "setp.ne.s32 pd, %4, 0;\n\t"
+                     "xor.pred pa, pa, pd;\n\t"
+                     "selp.b32 %0, %5, %6, pa;\n\t"
+                     "selp.u32 %1, 1, 0, pa;\n\t"
+                     "@pa st.shared.u8 [%7], %9;\n\t"
+                     "@pa st.shared.u8 [%8], %9;\n\t"
+                     "@pa st.shared.u8 [%10], %11;\n\t}"
+                     : "=&r"(head_new), "=&r"(acc_i)
+                     : "r"(nb), "r"(thr), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(addr2), "r"(nn), "r"(alog), "r"(lg)
+                     : "memory");
     } else {
-        nn = nb ^ 1u;
-        dNb = 1 - 2 * (int)nb;
-        dn = dNb;
+        asm volatile("{\n\t.reg .pred pa, pd;\n\t"
+                     "setp.lt.u32 pa, %2, %3;\n\t"
+                     "setp.ne.s32 pd, %4, 0;\n\t"
+                     "xor.pred pa, pa, pd;\n\t"
+                     "selp.b32 %0, %5, %6, pa;\n\t"
+                     "selp.u32 %1, 1, 0, pa;\n\t"
+                     "@pa st.shared.u8 [%7], %8;\n\t"
+                     "@pa st.shared.u8 [%9], %10;\n\t}"
+                     : "=&r"(head_new), "=&r"(acc_i)
+                     : "r"(nb), "r"(thr), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(nn), "r"(alog), "r"(lg)
+                     : "memory");
     }
-    // unconditional stores of the selected occupation (:152-154): a predicated store would wait for
-    // a predicate in front of the next step's load
-    const uint32_t nsel = (nn & (uint32_t)m) | (nb & ~(uint32_t)m);
-    asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr), "r"(nsel) : "memory");
-    if constexpr (DUAL) asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr2), "r"(nsel) : "memory");
-    c.Nb += dNb & m;
-    c.npar += dn & m;
-    c.closed = (pc & (uint32_t)m) | (c.closed & ~(uint32_t)m);
+    c.head = head_new;
+    c.closed = acc_i ? pc : c.closed;
 }
 
-__device__ __forceinline__ void flush_partials(LatState &c)
+// Replay of one round's log by the producer warp: lane (q, part) owns steps [part*SP, part*SP+SP) of
+// chain slot q.  Occupation-sum / parity-count changes are prefix-summed across the parts, then
+// every lane measures its closed steps (:130-132) with the exact Nb / n of that step.
+template <int ALGO, int CH>
+__device__ __forceinline__ void account_round(Account &k, uint32_t logbuf_abs, int q, int part, bool meas)
 {
-    c.Z += c.z32; c.SNb += c.snb32; c.Sn += c.sn32;
-    c.z32 = c.snb32 = c.sn32 = 0u;
+    using Cfg = LatCfg<CH>;
+    constexpr int SP = Cfg::SP, PARTS = Cfg::PARTS;
+    uint32_t al[SP], cl[SP];
+    int dNb[SP], dn[SP];
+    int sNb = 0, sn = 0;
+#pragma unroll
+    for (int i = 0; i < SP; ++i) {
+        const uint32_t off = (uint32_t)((part * SP + i) * CH + q);
+        al[i] = lds_u8(logbuf_abs + off);
+        cl[i] = lds_u8(logbuf_abs + Cfg::LOGH + off);
+        const int accd = (al[i] >> 7) & 1;
+        const int par = 1 - 2 * (int)(al[i] & 1u);
+        dn[i] = accd * par;
+        dNb[i] = (ALGO == ALGO_TAYLOR) ? accd * (1 - (int)((al[i] >> 5) & 2u)) : dn[i];
+        sNb += dNb[i]; sn += dn[i];
+    }
+    // inclusive scan over the parts of a chain (lanes q, q+CH, q+2CH, ...)
+    int pNb = sNb, pn = sn;
+#pragma unroll
+    for (int o = CH; o < 32; o <<= 1) {
+        const int uNb = __shfl_up_sync(0xffffffffu, pNb, o);
+        const int un = __shfl_up_sync(0xffffffffu, pn, o);
+        if (part * CH >= o) { pNb += uNb; pn += un; }
+    }
+    int Nb = k.Nb + pNb - sNb, npar = k.npar + pn - sn;          // state at this lane's first step
+    const int last = (PARTS - 1) * CH + q;
+    k.Nb += __shfl_sync(0xffffffffu, pNb, last);
+    k.npar += __shfl_sync(0xffffffffu, pn, last);
+#pragma unroll
+    for (int i = 0; i < SP; ++i) {
+        if (meas && cl[i]) {
+            k.Z += 1;
+            k.SNb += (uint32_t)Nb;
+            k.SNb2 += (uint64_t)(uint32_t)Nb * (uint32_t)Nb;
+            k.Sn += (uint32_t)npar;
+            k.Sn2 += (uint64_t)(uint32_t)npar * (uint32_t)npar;
+        }
+        Nb += dNb[i]; npar += dn[i];
+        const uint32_t off = (uint32_t)((part * SP + i) * CH + q);
+        asm volatile("st.shared.u8 [%0], %1;" :: "r"(logbuf_abs + off), "r"(0u) : "memory");
+        asm volatile("st.shared.u8 [%0], %1;" :: "r"(logbuf_abs + Cfg::LOGH + off), "r"(0u) : "memory");
+    }
 }
 
 // The round schedule both roles follow: rounds start on a Philox pair, never straddle a segment
@@ -282,9 +338,11 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
     const int64_t chain0 = (int64_t)blockIdx.x * bch;    // first chain of the block
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem8);
     const uint32_t rec_w = sbase + (uint32_t)g.rec_off + (uint32_t)(w * Cfg::RECW);
+    const uint32_t log_w = sbase + (uint32_t)g.log_off + (uint32_t)(w * Cfg::LOGW);
+    const uint32_t region_abs = sbase + (uint32_t)(w * g.region);
     const int bar_id = 1 + w;
 
-    // ---- stage the block's bonds (all warps)
+    // ---- stage the block's bonds, clear the step logs (all warps)
     if constexpr (DUAL) {
         uint32_t *dst = reinterpret_cast<uint32_t *>(smem8);
         const int total = bch * g.N;                     // words; index = (walker * N + s) * CH + q
@@ -308,10 +366,14 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             dst[i] = v;
         }
     }
+    {
+        uint32_t *lg = reinterpret_cast<uint32_t *>(smem8 + g.log_off);
+        for (int i = tid; i < nw * Cfg::LOGW / 4; i += nthreads) lg[i] = 0u;
+    }
     __syncthreads();
 
     if (is_producer) {
-        // ================================ producer warp ================================
+        // ============================ producer / accountant warp ============================
         // Philox block b = u*32 + lane of a round belongs to chain slot q = b % CH, pair p = b / CH:
         // consecutive lanes store consecutive 16-byte records (conflict-free 128-bit stores).
         PhiloxChain prm[U];
@@ -327,14 +389,79 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             prm[u] = a.prm[cl];
             const uint64_t chain_id = a.chain_id0 + (uint64_t)cl;
             c2[u] = (uint32_t)chain_id; c3[u] = (uint32_t)(chain_id >> 32);
-            chain_abs[u] = sbase + (uint32_t)(w * g.region) + (DUAL ? (uint32_t)q * 4u : 0u);
+            chain_abs[u] = region_abs + (DUAL ? (uint32_t)q * 4u : 0u);
             rec_q[u] = rec_w + (uint32_t)q * 16u + (uint32_t)(2 * p_of[u]) * (CH * 16);
         }
+        // accountant identity of this lane: chain slot aq, part ap of that chain's steps
+        const int aq = lane % CH, ap = lane / CH;
+        const int64_t acg = chain0 + w * CH + aq;
+        const bool alive = acg < a.n_chains;
+        const int64_t acl = alive ? acg : 0;
+        Account k;
+        k.Z = k.SNb = k.SNb2 = k.Sn = k.Sn2 = 0;
+        int64_t *ac = a.acc + acl * ACC_STRIDE;
+        uint64_t old[5] = {0, 0, 0, 0, 0};
+        if (ap == 0) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) old[i] = (uint64_t)ac[i];
+            k.Z = old[0]; k.SNb = old[1]; k.SNb2 = old[2]; k.Sn = old[3]; k.Sn2 = old[4];
+        }
+        k.nd = (a.n_dumps && alive) ? a.n_dumps[acl] : 0;
+        {   // occupation sum / odd-bond count of the staged configuration: the chain's parts share the sites
+            int Nb = 0, npar = 0;
+            if constexpr (DUAL) {
+                for (int s = ap; s < g.N; s += Cfg::PARTS) {
+                    const uint32_t v = lds_u32(region_abs + (uint32_t)((s * CH + aq) * 4)) & 0xffffu;
+                    Nb += (int)__vsadu4(v, 0);
+                    npar += __popc(v & 0x0101u);
+                }
+            } else {
+                for (int i = ap; i < g.nb2 / 16; i += Cfg::PARTS) {
+                    const uint4 v = lds_v4(region_abs + (uint32_t)(i * 16));
+                    Nb += (int)(__vsadu4(v.x, 0) + __vsadu4(v.y, 0) + __vsadu4(v.z, 0) + __vsadu4(v.w, 0));
+                    npar += __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) +
+                            __popc(v.w & 0x01010101u);
+                }
+            }
+#pragma unroll
+            for (int o = CH; o < 32; o <<= 1) {
+                Nb += __shfl_xor_sync(0xffffffffu, Nb, o);
+                npar += __shfl_xor_sync(0xffffffffu, npar, o);
+            }
+            k.Nb = Nb; k.npar = npar;
+        }
+        // replay of a finished round: dump event first (values before the round's first step), then the log
+        struct Pending { uint64_t s; int jb; bool meas, dump_first, valid; };
+        Pending pend[2] = {{0, 0, false, false, false}, {0, 0, false, false, false}};
+        uint32_t lbuf_acc = 0u;                          // log buffer of the oldest pending round
+        auto account = [&](const Pending &pr) {
+            const uint32_t lb = log_w + lbuf_acc;
+            if (pr.dump_first) {                                     // worm_ising_2d.cpp:113-119
+                const uint32_t was_closed = lds_u8(lb + Cfg::LOGH + (uint32_t)(pr.jb * CH + aq));
+                uint64_t Z = k.Z, SNb = k.SNb;
+#pragma unroll
+                for (int o = CH; o < 32; o <<= 1) {
+                    Z += __shfl_xor_sync(0xffffffffu, Z, o);
+                    SNb += __shfl_xor_sync(0xffffffffu, SNb, o);
+                }
+                if (was_closed) {
+                    if (ap == 0 && alive && k.nd < a.max_dumps && a.events) {
+                        int64_t *e = a.events + ((int64_t)acl * a.max_dumps + k.nd) * 3;
+                        e[0] = (int64_t)pr.s; e[1] = (int64_t)Z; e[2] = (int64_t)SNb;
+                    }
+                    ++k.nd;
+                }
+            }
+            account_round<ALGO, CH>(k, lb, aq, ap, pr.meas);
+            lbuf_acc = (lbuf_acc == 2u * Cfg::LOGB) ? 0u : lbuf_acc + (uint32_t)Cfg::LOGB;
+        };
+
         uint32_t buf = 0u;
         uint64_t s = a.step_begin;
         while (s < a.step_end) {
             bool meas, dump_first;
             const uint64_t seg_end = next_segment(a, s, meas, dump_first);
+            bool seg_first = true;
             while (s < seg_end) {
                 const Round rd = make_round<R>(s, seg_end);
 #pragma unroll
@@ -350,11 +477,35 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     sts_v4(p0 + CH * 16, ra1); sts_v4(p0 + CH * 16 + Cfg::REC_B, rb1);
                 }
                 pair_barrier(bar_id);
+                // the walker is now inside the previous round: the one before that is complete
+                if (pend[0].valid) account(pend[0]);
+                pend[0] = pend[1];
+                pend[1] = Pending{s, rd.jb, meas, dump_first && seg_first, true};
+                seg_first = false;
                 buf ^= (uint32_t)Cfg::BUF;
                 s = rd.s0 + (uint64_t)rd.je;
             }
         }
-        pair_barrier(bar_id);                            // matches the walker's barrier before its last step
+        pair_barrier(bar_id);                            // matches the walker's barrier before its last steps
+        pair_barrier(bar_id);                            // the walker has finished its last step
+        if (pend[0].valid) account(pend[0]);
+        if (pend[1].valid) account(pend[1]);
+        // reduce the parts' shares and write the chain's record
+#pragma unroll
+        for (int o = CH; o < 32; o <<= 1) {
+            k.Z += __shfl_xor_sync(0xffffffffu, k.Z, o);
+            k.SNb += __shfl_xor_sync(0xffffffffu, k.SNb, o);
+            k.SNb2 += __shfl_xor_sync(0xffffffffu, k.SNb2, o);
+            k.Sn += __shfl_xor_sync(0xffffffffu, k.Sn, o);
+            k.Sn2 += __shfl_xor_sync(0xffffffffu, k.Sn2, o);
+        }
+        if (ap == 0 && alive) {
+            const int64_t iters = measured_iters(a);
+            add_group_acc(a, acl, ac, k.Z, k.SNb, k.SNb2, k.Sn, k.Sn2, iters);
+            ac[0] = (int64_t)k.Z; ac[1] = (int64_t)k.SNb; ac[2] = (int64_t)k.SNb2;
+            ac[3] = (int64_t)k.Sn; ac[4] = (int64_t)k.Sn2;
+            ac[5] += iters;
+        }
     } else {
         // ================================= walker warp =================================
         // One lane per chain; the other lanes of the warp retire here (barriers count warps, and a
@@ -365,9 +516,9 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         const int64_t cidx = chain0 + w * CH + q;
         const bool live = cidx < a.n_chains;
         const int64_t cl = live ? cidx : 0;  // dead slots shadow chain 0 in their own shared-memory slot, never write
-        const uint32_t region_abs = sbase + (uint32_t)(w * g.region);
         uint32_t rec_q = rec_w + (uint32_t)q * 16u;
-        asm volatile("" : "+r"(rec_q));                                  // keep it in a register
+        uint32_t log_q = log_w + (uint32_t)q;
+        asm volatile("" : "+r"(rec_q), "+r"(log_q));                     // keep them in registers
         unsigned long long hist_row = 0ull;
         uint32_t hist_writer = 0u;
         if constexpr (HIST) {
@@ -381,28 +532,6 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         c.head = SC * a.head[cl];
         c.tail = SC * a.tail[cl];
         c.closed = (c.head == c.tail) ? 1u : 0u;
-        c.z32 = c.snb32 = c.sn32 = 0u;
-        const int64_t *ac0 = a.acc + cl * ACC_STRIDE;
-        c.Z = (uint64_t)ac0[0]; c.SNb = (uint64_t)ac0[1]; c.SNb2 = (uint64_t)ac0[2];
-        c.Sn = (uint64_t)ac0[3]; c.Sn2 = (uint64_t)ac0[4];
-        {
-            int Nb = 0, npar = 0;
-            if constexpr (DUAL) {
-                for (int s = 0; s < g.N; ++s) {
-                    const uint32_t v = lds_u32(region_abs + (uint32_t)((s * CH + q) * 4)) & 0xffffu;
-                    Nb += (int)__vsadu4(v, 0);
-                    npar += __popc(v & 0x0101u);
-                }
-            } else {
-                for (int i = 0; i < g.nb2 / 16; ++i) {
-                    const uint4 v = lds_v4(region_abs + (uint32_t)(i * 16));
-                    Nb += (int)(__vsadu4(v.x, 0) + __vsadu4(v.y, 0) + __vsadu4(v.z, 0) + __vsadu4(v.w, 0));
-                    npar += __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) +
-                            __popc(v.w & 0x01010101u);
-                }
-            }
-            c.Nb = Nb; c.npar = npar;
-        }
         int32_t nd = (a.n_dumps && live) ? a.n_dumps[cl] : 0;
 
         auto rec_addr = [&](uint32_t buf, int j) { return rec_q + buf + (uint32_t)(j * CH * 16); };
@@ -412,21 +541,21 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         // step j+2, which for the last two steps lives in the other buffer (complete once the pair
         // barrier has been passed).  On exit they hold the records of steps 0 / 1 of the next round.
         uint4 p0a, p0b, p1a, p1b;
-        auto full_round = [&](auto meas_tag, uint32_t cur, uint32_t nxt) {
+        auto full_round = [&](auto meas_tag, uint32_t cur, uint32_t nxt, uint32_t lg) {
             constexpr bool MEAS = decltype(meas_tag)::value;
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 if (j == R - 2) pair_barrier(bar_id);
                 const uint32_t nrec = (j < R - 2) ? rec_addr(cur, j + 2) : rec_addr(nxt, j + 2 - R);
                 const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
-                lat_step<ALGO, DUAL, SCSH, HIST, MEAS>(g, hist_row, hist_writer, c, p0a, p0b, (int)p1b.x);
+                lat_step<ALGO, DUAL, SCSH, HIST, MEAS>(g, hist_row, hist_writer, c, p0a, p0b, (int)p1b.x,
+                                                       lg + (uint32_t)(j * CH), lg + (uint32_t)(Cfg::LOGH + j * CH));
                 p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
             }
-            if constexpr (MEAS) flush_partials(c);
         };
         // Any other round (segment edges): steps [jb, je), records straight from shared memory.  The
         // kick folded into the last step is the first record of the next round (slot jbn of `nxt`).
-        auto edge_round = [&](auto meas_tag, uint32_t cur, uint32_t nxt, int jb, int je, int jbn) {
+        auto edge_round = [&](auto meas_tag, uint32_t cur, uint32_t nxt, uint32_t lg, int jb, int je, int jbn) {
             constexpr bool MEAS = decltype(meas_tag)::value;
             for (int j = jb; j < je; ++j) {
                 const uint32_t rec = rec_addr(cur, j);
@@ -434,26 +563,23 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 uint32_t nrec = rec_addr(cur, j + 1);
                 if (j == je - 1) { pair_barrier(bar_id); nrec = rec_addr(nxt, jbn); }
                 const uint4 nb_ = lds_v4(nrec + Cfg::REC_B);
-                lat_step<ALGO, DUAL, SCSH, HIST, MEAS>(g, hist_row, hist_writer, c, xa, xb, (int)nb_.x);
+                lat_step<ALGO, DUAL, SCSH, HIST, MEAS>(g, hist_row, hist_writer, c, xa, xb, (int)nb_.x,
+                                                       lg + (uint32_t)(j * CH), lg + (uint32_t)(Cfg::LOGH + j * CH));
             }
-            flush_partials(c);
         };
 
-        uint32_t cur = 0u;
+        uint32_t cur = 0u, lbuf = 0u;
         uint64_t s = a.step_begin;
         bool first = true;
         bool piped = false;                  // (p0, p1) hold the first two records of the coming round
         while (s < a.step_end) {
             bool meas, dump_first;
             const uint64_t seg_end = next_segment(a, s, meas, dump_first);
-            if (dump_first) {                                        // worm_ising_2d.cpp:113-124
-                // the walker's live lanes copy the bonds of every chain that dumps now
+            if (dump_first) {                                        // worm_ising_2d.cpp:120-124
+                // the walker's live lanes copy the bonds of every chain that dumps now (the event
+                // record {step, Z, sum Nb} is written by the accountant)
                 const bool want = live && c.closed;
                 const bool store = want && nd < a.max_dumps;
-                if (store && a.events) {
-                    int64_t *e = a.events + ((int64_t)cl * a.max_dumps + nd) * 3;
-                    e[0] = (int64_t)s; e[1] = (int64_t)c.Z; e[2] = (int64_t)c.SNb;
-                }
                 unsigned dm = __ballot_sync(wmask, store && a.dumps != nullptr);
                 while (dm) {
                     const int src_lane = __ffs(dm) - 1;
@@ -476,6 +602,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 const Round rd = make_round<R>(s, seg_end);
                 const uint64_t e = rd.s0 + (uint64_t)rd.je;          // first step of the next round
                 const uint32_t nxt = cur ^ (uint32_t)Cfg::BUF;
+                const uint32_t lg = log_q + lbuf;
                 const bool full = (rd.jb == 0 && rd.je == R);
                 if (first) {
                     pair_barrier(bar_id);                            // the first round's records are complete
@@ -488,30 +615,26 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                         p0a = lds_v4(rec_addr(cur, 0)); p0b = lds_v4(rec_addr(cur, 0) + Cfg::REC_B);
                         p1a = lds_v4(rec_addr(cur, 1)); p1b = lds_v4(rec_addr(cur, 1) + Cfg::REC_B);
                     }
-                    if (meas) full_round(std::true_type{}, cur, nxt);
-                    else full_round(std::false_type{}, cur, nxt);
+                    if (meas) full_round(std::true_type{}, cur, nxt, lg);
+                    else full_round(std::false_type{}, cur, nxt, lg);
                     piped = true;
                 } else {
-                    if (meas) edge_round(std::true_type{}, cur, nxt, rd.jb, rd.je, (int)(e & 1ull));
-                    else edge_round(std::false_type{}, cur, nxt, rd.jb, rd.je, (int)(e & 1ull));
+                    if (meas) edge_round(std::true_type{}, cur, nxt, lg, rd.jb, rd.je, (int)(e & 1ull));
+                    else edge_round(std::false_type{}, cur, nxt, lg, rd.jb, rd.je, (int)(e & 1ull));
                     piped = false;
                 }
                 cur = nxt;
+                lbuf = (lbuf == 2u * Cfg::LOGB) ? 0u : lbuf + (uint32_t)Cfg::LOGB;
                 s = e;
             }
         }
 
         if (first) pair_barrier(bar_id);                             // empty step range: meet the producer once
+        pair_barrier(bar_id);                                        // every step is logged: the accountant may finish
         if (live) {
             // a closed worm sits on its tail (head holds the folded kick of the step after the last)
             a.head[cl] = (c.closed ? c.tail : c.head) / SC;
             a.tail[cl] = c.tail / SC;
-            int64_t *ac = a.acc + cl * ACC_STRIDE;
-            const int64_t iters = measured_iters(a);
-            add_group_acc(a, cl, ac, c.Z, c.SNb, c.SNb2, c.Sn, c.Sn2, iters);
-            ac[0] = (int64_t)c.Z; ac[1] = (int64_t)c.SNb; ac[2] = (int64_t)c.SNb2;
-            ac[3] = (int64_t)c.Sn; ac[4] = (int64_t)c.Sn2;
-            ac[5] += iters;
             if (a.n_dumps) a.n_dumps[cl] = nd;
         }
     }
@@ -561,12 +684,13 @@ LatPlan lat_plan(int L, int CH, int smem_optin)
     const int U = (CH == 8) ? 2 : 1;
     const int R = 64 * U / CH;
     const size_t recw = (size_t)4 * R * CH * 16;
+    const size_t logw = (size_t)3 * 2 * R * CH;
     for (int dual = 1; dual >= 0; --dual) {
         if (!dual && CH != 1) continue;
         const size_t region = dual ? (size_t)4 * N * CH : (size_t)2 * N;
         for (int nw : {4, 2, 1}) {
             if (nw != 4 && CH != 1) continue;
-            const size_t need = nw * (region + recw);
+            const size_t need = nw * (region + recw + logw);
             if (need + 1024 > (size_t)smem_optin) continue;
             p.ok = true; p.dual = dual; p.smem = need;
             p.g.L = L; p.g.N = N; p.g.nb2 = 2 * N; p.g.nw = nw;
@@ -575,6 +699,7 @@ LatPlan lat_plan(int L, int CH, int smem_optin)
             p.g.YM = (L - 1) * L * p.g.SC;
             p.g.region = (int)region;
             p.g.rec_off = (int)(nw * region);
+            p.g.log_off = (int)(nw * (region + recw));
             p.g.lowt = 0;
             p.g.zero = 0;
             return p;
