@@ -87,9 +87,10 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, const uint4 v)
 {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// one named barrier per walker group: its two producers, its accountant and the walker (4 warps)
 __device__ __forceinline__ void pair_barrier(int id)
 {
-    asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory");
+    asm volatile("bar.sync %0, 128;" :: "r"(id) : "memory");
 }
 
 struct LatState {
@@ -318,7 +319,7 @@ __device__ __forceinline__ uint32_t dual_word(const uint8_t *gb, int s, int L, i
 }
 
 template <int ALGO, int CH, bool DUAL, bool HIST>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
 {
     using Cfg = LatCfg<CH>;
@@ -332,8 +333,12 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
     const int nw = g.nw;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const bool is_producer = warp < nw;                  // walkers are the high warps (arbiter priority)
-    const int w = is_producer ? warp : warp - nw;        // pair index: warps w and nw + w share a sub-partition when nw = 4
+    // roles by warp: [0, nw) producer of Philox block 0, [nw, 2nw) producer of block 1, [2nw, 3nw)
+    // accountant, [3nw, 4nw) walker.  Warps w, nw+w, 2nw+w, 3nw+w form a group and (nw = 4) share a
+    // sub-partition; the walkers are the high warps because the arbiter prefers the higher warp id.
+    const int role = warp / nw;
+    const int w = warp - role * nw;
+    const bool is_walker = role == 3;
     const int bch = nw * CH;                             // chains per block
     const int64_t chain0 = (int64_t)blockIdx.x * bch;    // first chain of the block
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem8);
@@ -372,26 +377,50 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
     }
     __syncthreads();
 
-    if (is_producer) {
-        // ============================ producer / accountant warp ============================
-        // Philox block b = u*32 + lane of a round belongs to chain slot q = b % CH, pair p = b / CH:
-        // consecutive lanes store consecutive 16-byte records (conflict-free 128-bit stores).
-        PhiloxChain prm[U];
-        uint32_t c2[U], c3[U], chain_abs[U], rec_q[U];
-        int p_of[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int b = u * 32 + lane;
-            const int q = b % CH;
-            p_of[u] = b / CH;
-            const int64_t cg = chain0 + w * CH + q;
-            const int64_t cl = cg < a.n_chains ? cg : 0;
-            prm[u] = a.prm[cl];
-            const uint64_t chain_id = a.chain_id0 + (uint64_t)cl;
-            c2[u] = (uint32_t)chain_id; c3[u] = (uint32_t)(chain_id >> 32);
-            chain_abs[u] = region_abs + (DUAL ? (uint32_t)q * 4u : 0u);
-            rec_q[u] = rec_w + (uint32_t)q * 16u + (uint32_t)(2 * p_of[u]) * (CH * 16);
+    if (role < 2) {
+        // ================================ producer warp ================================
+        // Philox block b = u*32 + lane of a round (u = role: the group's two producers take one
+        // block each) belongs to chain slot q = b % CH, pair p = b / CH: consecutive lanes store
+        // consecutive 16-byte records (conflict-free 128-bit stores).
+        const int u = role;
+        const bool works = u < U;                        // with one block per round the second producer only keeps the barriers
+        const int b = u * 32 + lane;
+        const int q = b % CH;
+        const int p_of = b / CH;
+        const int64_t cg = chain0 + w * CH + q;
+        const int64_t cl = cg < a.n_chains ? cg : 0;
+        const PhiloxChain prm = a.prm[cl];
+        const uint64_t chain_id = a.chain_id0 + (uint64_t)cl;
+        const uint32_t c2 = (uint32_t)chain_id, c3 = (uint32_t)(chain_id >> 32);
+        const uint32_t chain_abs = region_abs + (DUAL ? (uint32_t)q * 4u : 0u);
+        const uint32_t rec_q = rec_w + (uint32_t)q * 16u + (uint32_t)(2 * p_of) * (CH * 16);
+        uint32_t buf = 0u;
+        uint64_t s = a.step_begin;
+        while (s < a.step_end) {
+            bool meas, dump_first;
+            const uint64_t seg_end = next_segment(a, s, meas, dump_first);
+            while (s < seg_end) {
+                const Round rd = make_round<R>(s, seg_end);
+                if (works) {
+                    const uint64_t pair = (rd.s0 >> 1) + (uint64_t)p_of;
+                    const uint4 r = philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), c2, c3,
+                                                  (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
+                    uint4 ra0, rb0, ra1, rb1;
+                    make_record<ALGO, DUAL>(g, prm, r.x, r.y, chain_abs, ra0, rb0);
+                    make_record<ALGO, DUAL>(g, prm, r.z, r.w, chain_abs, ra1, rb1);
+                    const uint32_t p0 = rec_q + buf;
+                    sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0);
+                    sts_v4(p0 + CH * 16, ra1); sts_v4(p0 + CH * 16 + Cfg::REC_B, rb1);
+                }
+                pair_barrier(bar_id);
+                buf ^= (uint32_t)Cfg::BUF;
+                s = rd.s0 + (uint64_t)rd.je;
+            }
         }
+        pair_barrier(bar_id);                            // matches the walker's barrier before its last steps
+        pair_barrier(bar_id);                            // the walker has finished its last step
+    } else if (role == 2) {
+        // ================================ accountant warp ================================
         // accountant identity of this lane: chain slot aq, part ap of that chain's steps
         const int aq = lane % CH, ap = lane / CH;
         const int64_t acg = chain0 + w * CH + aq;
@@ -456,7 +485,6 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             lbuf_acc = (lbuf_acc == 2u * Cfg::LOGB) ? 0u : lbuf_acc + (uint32_t)Cfg::LOGB;
         };
 
-        uint32_t buf = 0u;
         uint64_t s = a.step_begin;
         while (s < a.step_end) {
             bool meas, dump_first;
@@ -464,25 +492,12 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             bool seg_first = true;
             while (s < seg_end) {
                 const Round rd = make_round<R>(s, seg_end);
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const uint64_t pair = (rd.s0 >> 1) + (uint64_t)p_of[u];
-                    const uint4 r = philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), c2[u], c3[u],
-                                                  (uint32_t)prm[u].seed, (uint32_t)(prm[u].seed >> 32));
-                    uint4 ra0, rb0, ra1, rb1;
-                    make_record<ALGO, DUAL>(g, prm[u], r.x, r.y, chain_abs[u], ra0, rb0);
-                    make_record<ALGO, DUAL>(g, prm[u], r.z, r.w, chain_abs[u], ra1, rb1);
-                    const uint32_t p0 = rec_q[u] + buf;
-                    sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0);
-                    sts_v4(p0 + CH * 16, ra1); sts_v4(p0 + CH * 16 + Cfg::REC_B, rb1);
-                }
                 pair_barrier(bar_id);
                 // the walker is now inside the previous round: the one before that is complete
                 if (pend[0].valid) account(pend[0]);
                 pend[0] = pend[1];
                 pend[1] = Pending{s, rd.jb, meas, dump_first && seg_first, true};
                 seg_first = false;
-                buf ^= (uint32_t)Cfg::BUF;
                 s = rd.s0 + (uint64_t)rd.je;
             }
         }
@@ -639,10 +654,10 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         }
     }
 
-    // ---- write back (the producer warps: the walkers' spare lanes have retired)
+    // ---- write back (all but the walker warps, whose spare lanes have retired)
     __syncthreads();
-    if (is_producer) {
-        const int pthreads = nw * 32;
+    if (!is_walker) {
+        const int pthreads = 3 * nw * 32;
         if constexpr (DUAL) {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(smem8);
             const int total = bch * g.N;
@@ -716,7 +731,7 @@ cudaError_t launch_lat(const PhiloxArgs &a, const LatPlan &p, cudaStream_t st)
     if (e != cudaSuccess) return e;
     const int64_t bch = (int64_t)p.g.nw * CH;
     const int64_t blocks = (a.n_chains + bch - 1) / bch;
-    kern<<<(unsigned)blocks, 2 * p.g.nw * 32, p.smem, st>>>(a, p.g);
+    kern<<<(unsigned)blocks, 4 * p.g.nw * 32, p.smem, st>>>(a, p.g);
     return cudaGetLastError();
 }
 
