@@ -119,9 +119,11 @@ int worm_mt_run(int L, int64_t n_chains, const double *h_T, const double *h_seed
  *                            d_events[c][e] = {step, Z so far, sum Nb so far} and (d_dumps != NULL)
  *                            the occupations d_dumps[c][e][2N]; d_n_dumps[c] (in/out) counts them.
  *                            dump_every = 0 disables.
- *   lanes_per_chain          0 = choose; 1 = one thread per chain; 4 = quad per chain (latency mode);
- *                            -1 = one thread per chain with bonds left in global memory (the path
- *                            taken automatically when a lattice does not fit shared memory)
+ *   lanes_per_chain          kernel variant (results are identical for all of them):
+ *                            0 = choose;  2 / 4 / 8 / 32 = latency kernel with 32 / 8 / 4 / 1 chains per
+ *                            walker warp (power-of-two L; 2 gives the walker an SM sub-partition to itself);
+ *                            1 = one thread per chain, bonds in shared memory;  -1 = one thread per chain,
+ *                            bonds left in global memory (taken automatically when a lattice does not fit)
  *   d_workspace              worm_philox_workspace_bytes(n) bytes
  * ------------------------------------------------------------------------------------------- */
 size_t worm_philox_workspace_bytes(int64_t n_chains);

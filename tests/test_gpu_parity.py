@@ -92,14 +92,14 @@ def test_mt_mode_batch_matches_oracle_with_trace(eng):
 # production mode: every kernel variant reproduces the CPU restatement bit for bit
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("algo", [0, 1])
-@pytest.mark.parametrize("lanes", [0, 1, 4, 8, 32, -1])
+@pytest.mark.parametrize("lanes", [0, 1, 2, 4, 8, 32, -1])
 @pytest.mark.parametrize("L,tmin", [(3, 0.8), (8, 0.8), (16, 1.0), (32, 1.2)])
 def test_philox_matches_oracle(eng, algo, lanes, L, tmin):
     """Every kernel variant (latency mode with 4/8/32 lanes per chain, thread per chain with bonds in
     shared or global memory) and both record builders (T >= 1 fast path, general T) against the CPU
     restatement: accumulators, final bonds, head/tail, dumps, events, G(r), per-group sums."""
     from oracle import worm_oracle as wo
-    if lanes in (4, 8, 32) and (L & (L - 1)):
+    if lanes in (2, 4, 8, 32) and (L & (L - 1)):
         pytest.skip("latency mode needs a power-of-two L")
     rng = np.random.default_rng(100 * L + 10 * algo + lanes + 1)
     n = 37                      # not a multiple of the chains per warp: exercises dead lanes
@@ -151,7 +151,7 @@ def test_philox_geometry_independence(eng):
     a = eng.PhiloxState(L, T, seeds, algo=0).run(5000, therm_steps=500, lanes_per_chain=1)
     b = eng.PhiloxState(L, T, seeds, algo=0).run(1233, therm_steps=500, lanes_per_chain=4).run(3767, therm_steps=500, lanes_per_chain=-1)
     assert (a.acc == b.acc).all() and (a.bonds == b.bonds).all()
-    d = eng.PhiloxState(L, T, seeds, algo=0).run(77, therm_steps=500, lanes_per_chain=32).run(4000, therm_steps=500, lanes_per_chain=8).run(923, therm_steps=500)
+    d = eng.PhiloxState(L, T, seeds, algo=0).run(77, therm_steps=500, lanes_per_chain=32).run(2000, therm_steps=500, lanes_per_chain=8).run(2000, therm_steps=500, lanes_per_chain=2).run(923, therm_steps=500)
     assert (a.acc == d.acc).all() and (a.bonds == d.bonds).all() and (a.head == d.head).all() and (a.tail == d.tail).all()
     # second half of the chains run as their own batch with chain_id0 = 32
     c = eng.PhiloxState(L, T[32:], seeds[32:], algo=0, chain_id0=32).run(5000, therm_steps=500)

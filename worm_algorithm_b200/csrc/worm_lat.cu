@@ -51,8 +51,9 @@ struct LatGeo {
 };
 
 template <int CH> struct LatCfg {
-    static constexpr int U = (CH == 8) ? 2 : 1;       // Philox blocks per producer lane per round
-    static constexpr int R = 64 * U / CH;             // steps per chain per round
+    static constexpr int NP = (CH == 32) ? 8 : (CH == 8) ? 2 : 1;   // producer warps per walker (one Philox block per lane per round)
+    static constexpr int GW = NP + 2;                 // warps of a group: producers, accountant, walker
+    static constexpr int R = 64 * NP / CH;            // steps per chain per round
     static constexpr int BUF = R * CH * 16;           // bytes of one buffer of A (or B) records
     static constexpr int REC_B = 2 * BUF;             // byte offset of the B records (two buffers of A first)
     static constexpr int RECW = 4 * BUF;              // record bytes per walker warp
@@ -87,10 +88,11 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, const uint4 v)
 {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-// one named barrier per walker group: its two producers, its accountant and the walker (4 warps)
-__device__ __forceinline__ void pair_barrier(int id)
+// one named barrier per walker group: its producers, its accountant and the walker (GW warps)
+template <int GW>
+__device__ __forceinline__ void group_barrier(int id)
 {
-    asm volatile("bar.sync %0, 128;" :: "r"(id) : "memory");
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(32 * GW) : "memory");
 }
 
 struct LatState {
@@ -323,9 +325,9 @@ __global__ void __launch_bounds__(512)
 worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
 {
     using Cfg = LatCfg<CH>;
-    constexpr int R = Cfg::R, U = Cfg::U;
+    constexpr int R = Cfg::R, NP = Cfg::NP;
     constexpr int SC = DUAL ? 4 * CH : 2;
-    constexpr int SCSH = (SC == 2) ? 1 : (SC == 4) ? 2 : (SC == 16) ? 4 : 5;
+    constexpr int SCSH = (SC == 2) ? 1 : (SC == 4) ? 2 : (SC == 16) ? 4 : (SC == 32) ? 5 : 7;
     static_assert(DUAL || CH == 1, "the compact layout is one chain per walker");
     extern __shared__ __align__(16) uint8_t smem8[];
     const int tid = threadIdx.x;
@@ -333,12 +335,28 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
     const int nw = g.nw;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    // roles by warp: [0, nw) producer of Philox block 0, [nw, 2nw) producer of block 1, [2nw, 3nw)
-    // accountant, [3nw, 4nw) walker.  Warps w, nw+w, 2nw+w, 3nw+w form a group and (nw = 4) share a
-    // sub-partition; the walkers are the high warps because the arbiter prefers the higher warp id.
-    const int role = warp / nw;
-    const int w = warp - role * nw;
-    const bool is_walker = role == 3;
+    // Roles by warp.  CH <= 8: role r = warp / nw of group w = warp % nw -- r < NP producer of Philox
+    // block r, r == NP accountant, r == NP+1 walker; the warps of a group share an SM sub-partition
+    // (nw = 4) and the walker is its highest warp id (the arbiter prefers it).
+    // CH == 32 ("solo"): one group per block; the walker (warp 0) has sub-partition 0 to itself --
+    // warps 4 and 8 stay idle -- and the nine helpers live on the other three sub-partitions.
+    enum { PRODUCER, ACCOUNTANT, WALKER, IDLE };
+    int kind, u = 0, w = 0;
+    if constexpr (CH == 32) {
+        if (warp == 0) kind = WALKER;
+        else if ((warp & 3) == 0) kind = IDLE;
+        else {
+            const int h = warp - 1 - (warp >> 2);            // 0..8 for warps 1,2,3,5,6,7,9,10,11
+            kind = h < NP ? PRODUCER : ACCOUNTANT;
+            u = h;
+        }
+    } else {
+        const int role = warp / nw;
+        w = warp - role * nw;
+        kind = role < NP ? PRODUCER : (role == NP ? ACCOUNTANT : WALKER);
+        u = role;
+    }
+    const bool is_walker = kind == WALKER;
     const int bch = nw * CH;                             // chains per block
     const int64_t chain0 = (int64_t)blockIdx.x * bch;    // first chain of the block
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem8);
@@ -377,13 +395,11 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
     }
     __syncthreads();
 
-    if (role < 2) {
+    if (kind == PRODUCER) {
         // ================================ producer warp ================================
         // Philox block b = u*32 + lane of a round (u = role: the group's two producers take one
         // block each) belongs to chain slot q = b % CH, pair p = b / CH: consecutive lanes store
         // consecutive 16-byte records (conflict-free 128-bit stores).
-        const int u = role;
-        const bool works = u < U;                        // with one block per round the second producer only keeps the barriers
         const int b = u * 32 + lane;
         const int q = b % CH;
         const int p_of = b / CH;
@@ -401,7 +417,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             const uint64_t seg_end = next_segment(a, s, meas, dump_first);
             while (s < seg_end) {
                 const Round rd = make_round<R>(s, seg_end);
-                if (works) {
+                {
                     const uint64_t pair = (rd.s0 >> 1) + (uint64_t)p_of;
                     const uint4 r = philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), c2, c3,
                                                   (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
@@ -412,14 +428,14 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0);
                     sts_v4(p0 + CH * 16, ra1); sts_v4(p0 + CH * 16 + Cfg::REC_B, rb1);
                 }
-                pair_barrier(bar_id);
+                group_barrier<Cfg::GW>(bar_id);
                 buf ^= (uint32_t)Cfg::BUF;
                 s = rd.s0 + (uint64_t)rd.je;
             }
         }
-        pair_barrier(bar_id);                            // matches the walker's barrier before its last steps
-        pair_barrier(bar_id);                            // the walker has finished its last step
-    } else if (role == 2) {
+        group_barrier<Cfg::GW>(bar_id);                            // matches the walker's barrier before its last steps
+        group_barrier<Cfg::GW>(bar_id);                            // the walker has finished its last step
+    } else if (kind == ACCOUNTANT) {
         // ================================ accountant warp ================================
         // accountant identity of this lane: chain slot aq, part ap of that chain's steps
         const int aq = lane % CH, ap = lane / CH;
@@ -492,7 +508,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             bool seg_first = true;
             while (s < seg_end) {
                 const Round rd = make_round<R>(s, seg_end);
-                pair_barrier(bar_id);
+                group_barrier<Cfg::GW>(bar_id);
                 // the walker is now inside the previous round: the one before that is complete
                 if (pend[0].valid) account(pend[0]);
                 pend[0] = pend[1];
@@ -501,8 +517,8 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 s = rd.s0 + (uint64_t)rd.je;
             }
         }
-        pair_barrier(bar_id);                            // matches the walker's barrier before its last steps
-        pair_barrier(bar_id);                            // the walker has finished its last step
+        group_barrier<Cfg::GW>(bar_id);                            // matches the walker's barrier before its last steps
+        group_barrier<Cfg::GW>(bar_id);                            // the walker has finished its last step
         if (pend[0].valid) account(pend[0]);
         if (pend[1].valid) account(pend[1]);
         // reduce the parts' shares and write the chain's record
@@ -521,7 +537,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             ac[3] = (int64_t)k.Sn; ac[4] = (int64_t)k.Sn2;
             ac[5] += iters;
         }
-    } else {
+    } else if (kind == WALKER) {
         // ================================= walker warp =================================
         // One lane per chain; the other lanes of the warp retire here (barriers count warps, and a
         // shared-memory access by CH lanes costs CH/8 wavefronts instead of 4).
@@ -560,7 +576,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             constexpr bool MEAS = decltype(meas_tag)::value;
 #pragma unroll
             for (int j = 0; j < R; ++j) {
-                if (j == R - 2) pair_barrier(bar_id);
+                if (j == R - 2) group_barrier<Cfg::GW>(bar_id);
                 const uint32_t nrec = (j < R - 2) ? rec_addr(cur, j + 2) : rec_addr(nxt, j + 2 - R);
                 const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
                 lat_step<ALGO, DUAL, SCSH, HIST, MEAS>(g, hist_row, hist_writer, c, p0a, p0b, (int)p1b.x,
@@ -576,7 +592,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 const uint32_t rec = rec_addr(cur, j);
                 const uint4 xa = lds_v4(rec), xb = lds_v4(rec + Cfg::REC_B);
                 uint32_t nrec = rec_addr(cur, j + 1);
-                if (j == je - 1) { pair_barrier(bar_id); nrec = rec_addr(nxt, jbn); }
+                if (j == je - 1) { group_barrier<Cfg::GW>(bar_id); nrec = rec_addr(nxt, jbn); }
                 const uint4 nb_ = lds_v4(nrec + Cfg::REC_B);
                 lat_step<ALGO, DUAL, SCSH, HIST, MEAS>(g, hist_row, hist_writer, c, xa, xb, (int)nb_.x,
                                                        lg + (uint32_t)(j * CH), lg + (uint32_t)(Cfg::LOGH + j * CH));
@@ -620,7 +636,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 const uint32_t lg = log_q + lbuf;
                 const bool full = (rd.jb == 0 && rd.je == R);
                 if (first) {
-                    pair_barrier(bar_id);                            // the first round's records are complete
+                    group_barrier<Cfg::GW>(bar_id);                            // the first round's records are complete
                     const uint4 kb = lds_v4(rec_addr(cur, rd.jb) + Cfg::REC_B);
                     c.head = c.closed ? (int)kb.x : c.head;          // kick of the first step
                     first = false;
@@ -644,8 +660,8 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             }
         }
 
-        if (first) pair_barrier(bar_id);                             // empty step range: meet the producer once
-        pair_barrier(bar_id);                                        // every step is logged: the accountant may finish
+        if (first) group_barrier<Cfg::GW>(bar_id);                             // empty step range: meet the producer once
+        group_barrier<Cfg::GW>(bar_id);                                        // every step is logged: the accountant may finish
         if (live) {
             // a closed worm sits on its tail (head holds the folded kick of the step after the last)
             a.head[cl] = (c.closed ? c.tail : c.head) / SC;
@@ -656,12 +672,14 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
 
     // ---- write back (all but the walker warps, whose spare lanes have retired)
     __syncthreads();
+    // participants: every warp but the walkers (CH <= 8: the first (NP+1) nw warps; solo: warps 1..11)
+    const int wb0 = (CH == 32) ? 32 : 0;
+    const int pthreads = (CH == 32) ? nthreads - 32 : (NP + 1) * nw * 32;
     if (!is_walker) {
-        const int pthreads = 3 * nw * 32;
         if constexpr (DUAL) {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(smem8);
             const int total = bch * g.N;
-            for (int i = tid; i < total; i += pthreads) {
+            for (int i = tid - wb0; i < total; i += pthreads) {
                 const int q = i % CH;
                 const int ws = i / CH;
                 const int wk = ws / g.N, s = ws - wk * g.N;
@@ -673,7 +691,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             const int vec_per_chain = g.nb2 / 16;
             const int total = bch * vec_per_chain;
             const uint4 *src = reinterpret_cast<const uint4 *>(smem8);
-            for (int i = tid; i < total; i += pthreads) {
+            for (int i = tid - wb0; i < total; i += pthreads) {
                 const int cslot = i / vec_per_chain;
                 const int64_t cg = chain0 + cslot;
                 if (cg < a.n_chains)
@@ -694,17 +712,18 @@ struct LatPlan {
 LatPlan lat_plan(int L, int CH, int smem_optin)
 {
     LatPlan p;
-    if (L < 4 || (L & (L - 1)) || (CH != 8 && CH != 4 && CH != 1)) return p;
+    if (L < 4 || (L & (L - 1)) || (CH != 32 && CH != 8 && CH != 4 && CH != 1)) return p;
     const int N = L * L;
-    const int U = (CH == 8) ? 2 : 1;
-    const int R = 64 * U / CH;
+    const int NP = (CH == 32) ? 8 : (CH == 8) ? 2 : 1;
+    const int R = 64 * NP / CH;
     const size_t recw = (size_t)4 * R * CH * 16;
     const size_t logw = (size_t)3 * 2 * R * CH;
     for (int dual = 1; dual >= 0; --dual) {
         if (!dual && CH != 1) continue;
         const size_t region = dual ? (size_t)4 * N * CH : (size_t)2 * N;
         for (int nw : {4, 2, 1}) {
-            if (nw != 4 && CH != 1) continue;
+            if (nw != 4 && CH != 1 && CH != 32) continue;
+            if (CH == 32 && nw != 1) continue;
             const size_t need = nw * (region + recw + logw);
             if (need + 1024 > (size_t)smem_optin) continue;
             p.ok = true; p.dual = dual; p.smem = need;
@@ -731,7 +750,8 @@ cudaError_t launch_lat(const PhiloxArgs &a, const LatPlan &p, cudaStream_t st)
     if (e != cudaSuccess) return e;
     const int64_t bch = (int64_t)p.g.nw * CH;
     const int64_t blocks = (a.n_chains + bch - 1) / bch;
-    kern<<<(unsigned)blocks, 4 * p.g.nw * 32, p.smem, st>>>(a, p.g);
+    const int warps = (CH == 32) ? 12 : LatCfg<CH>::GW * p.g.nw;
+    kern<<<(unsigned)blocks, warps * 32, p.smem, st>>>(a, p.g);
     return cudaGetLastError();
 }
 
@@ -740,6 +760,7 @@ cudaError_t launch_lat_ah(const PhiloxArgs &a, const LatPlan &p, int CH, cudaStr
 {
     if (!p.dual) return launch_lat<ALGO, 1, false, HIST>(a, p, st);
     switch (CH) {
+    case 32: return launch_lat<ALGO, 32, true, HIST>(a, p, st);
     case 8: return launch_lat<ALGO, 8, true, HIST>(a, p, st);
     case 4: return launch_lat<ALGO, 4, true, HIST>(a, p, st);
     case 1: return launch_lat<ALGO, 1, true, HIST>(a, p, st);
@@ -749,27 +770,29 @@ cudaError_t launch_lat_ah(const PhiloxArgs &a, const LatPlan &p, int CH, cudaStr
 
 }  // namespace
 
-// G = lanes_per_chain of the C ABI: 4 / 8 / 32 <-> 8 / 4 / 1 chains per walker warp
+// G = lanes_per_chain of the C ABI: 2 / 4 / 8 / 32 <-> 32 / 8 / 4 / 1 chains per walker warp
+static int chains_per_walker(int G) { return G == 2 ? 32 : 32 / G; }
+
 int lat_chains_per_block(int L, int G, int smem_optin)
 {
-    const LatPlan p = lat_plan(L, 32 / G, smem_optin);
-    return p.ok ? p.g.nw * (32 / G) : 0;
+    const LatPlan p = lat_plan(L, chains_per_walker(G), smem_optin);
+    return p.ok ? p.g.nw * chains_per_walker(G) : 0;
 }
 
 size_t lat_smem_bytes(int L, int G, int smem_optin)
 {
-    if (G != 4 && G != 8 && G != 32) return 0;
-    const LatPlan p = lat_plan(L, 32 / G, smem_optin);
+    if (G != 2 && G != 4 && G != 8 && G != 32) return 0;
+    const LatPlan p = lat_plan(L, chains_per_walker(G), smem_optin);
     return p.ok ? p.smem : 0;
 }
 
 cudaError_t launch_philox_lat(const PhiloxArgs &a, int G, bool lowt, int smem_optin, cudaStream_t st)
 {
     const bool hist = (a.hist != nullptr && a.group_index != nullptr);
-    LatPlan p = lat_plan(a.L, 32 / G, smem_optin);
+    const int CH = chains_per_walker(G);
+    LatPlan p = lat_plan(a.L, CH, smem_optin);
     if (!p.ok) return cudaErrorInvalidValue;
     p.g.lowt = lowt ? 1 : 0;
-    const int CH = 32 / G;
     if (a.algo == ALGO_TAYLOR)
         return hist ? launch_lat_ah<ALGO_TAYLOR, true>(a, p, CH, st) : launch_lat_ah<ALGO_TAYLOR, false>(a, p, CH, st);
     return hist ? launch_lat_ah<ALGO_BINARY, true>(a, p, CH, st) : launch_lat_ah<ALGO_BINARY, false>(a, p, CH, st);
