@@ -184,9 +184,6 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.global.add.u64 [%0], 1;\n\t}"
                      :: "l"(hist_row + off8), "r"(hist_writer) : "memory");
     }
-    // closed iteration (worm_ising_2d.cpp:130-132): logged, measured by the accountant
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u8 [%1], %2;\n\t}"
-                 :: "r"(c.closed), "r"(clog), "r"(logbits) : "memory");
     const int tail = closed ? kick : c.tail;                    // kick :128-129 (head has it already)
     c.tail = tail;
     const int head = c.head;
@@ -202,9 +199,18 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
         addr = (uint32_t)own + ra.w;
     }
     const uint32_t nb = lds_u8(addr);                           // :139
+    // closed iteration (worm_ising_2d.cpp:130-132): logged, measured by the accountant.  After the
+    // load in program order: a store ahead of it would sit on the load's issue path (the compiler
+    // cannot reorder shared-memory accesses that may alias).
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u8 [%1], %2;\n\t}"
+                 :: "r"(c.closed), "r"(clog), "r"(logbits) : "memory");
     const uint32_t pc = (nh == tail) ? 1u : 0u;                 // closed after an accepted move?
     const int A = pc ? kick_next : nh;                          // head if accepted (kick folded in)
     const int B = closed ? kick_next : head;                    // head if rejected
+    // thr | 0, written so that the compiler has to finish A, B and the second store address before
+    // the first consumer of nb: the warp issues in order and stalls at that consumer, so everything
+    // that does not depend on the load must sit in front of it (in the load's shadow), not behind
+    const uint32_t thrx = thr | ((uint32_t)(A ^ B ^ (int)addr2) & (uint32_t)g.zero);
     const uint32_t nn = (ALGO == ALGO_TAYLOR) ? nb + (1u | flip) : (nb ^ 1u);
     const uint32_t lg = (nb & 1u) | logbits;
     // accept test (:151), head select, bond stores (:152-154) and the accept-log byte in one opaque
@@ -222,7 +228,7 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
                      "@pa st.shared.u8 [%8], %9;\n\t"
                      "@pa st.shared.u8 [%10], %11;\n\t}"
                      : "=&r"(head_new), "=&r"(acc_i)
-                     : "r"(nb), "r"(thr), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(addr2), "r"(nn), "r"(alog), "r"(lg)
+                     : "r"(nb), "r"(thrx), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(addr2), "r"(nn), "r"(alog), "r"(lg)
                      : "memory");
     } else {
         asm volatile("{\n\t.reg .pred pa, pd;\n\t"
@@ -234,7 +240,7 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
                      "@pa st.shared.u8 [%7], %8;\n\t"
                      "@pa st.shared.u8 [%9], %10;\n\t}"
                      : "=&r"(head_new), "=&r"(acc_i)
-                     : "r"(nb), "r"(thr), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(nn), "r"(alog), "r"(lg)
+                     : "r"(nb), "r"(thrx), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(nn), "r"(alog), "r"(lg)
                      : "memory");
     }
     c.head = head_new;
