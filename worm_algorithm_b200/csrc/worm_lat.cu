@@ -52,7 +52,9 @@ struct LatGeo {
 
 template <int CH> struct LatCfg {
     static constexpr int NP = (CH == 32) ? 8 : (CH == 8) ? 2 : 1;   // producer warps per walker (one Philox block per lane per round)
-    static constexpr int GW = NP + 2;                 // warps of a group: producers, accountant, walker
+    static constexpr int ACH = (CH > 8) ? 8 : CH;     // chains per accountant warp
+    static constexpr int NA = CH / ACH;               // accountant warps per walker
+    static constexpr int GW = NP + NA + 1;            // warps of a group: producers, accountants, walker
     static constexpr int R = 64 * NP / CH;            // steps per chain per round
     static constexpr int BUF = R * CH * 16;           // bytes of one buffer of A (or B) records
     static constexpr int REC_B = 2 * BUF;             // byte offset of the B records (two buffers of A first)
@@ -60,7 +62,7 @@ template <int CH> struct LatCfg {
     static constexpr int LOGH = R * CH;               // bytes of one accept (or closed) log of a round
     static constexpr int LOGB = 2 * LOGH;             // one round's log: accept bytes, then closed bytes
     static constexpr int LOGW = 3 * LOGB;             // three rounds in flight per walker warp
-    static constexpr int PARTS = 32 / CH;             // accountant lanes per chain
+    static constexpr int PARTS = 32 / ACH;            // accountant lanes per chain
     static constexpr int SP = R / PARTS;              // steps per accountant lane per round
 };
 
@@ -269,16 +271,17 @@ __device__ __forceinline__ void account_round(Account &k, uint32_t logbuf_abs, i
         dNb[i] = (ALGO == ALGO_TAYLOR) ? accd * (1 - (int)((al[i] >> 5) & 2u)) : dn[i];
         sNb += dNb[i]; sn += dn[i];
     }
-    // inclusive scan over the parts of a chain (lanes q, q+CH, q+2CH, ...)
+    // inclusive scan over the parts of a chain (lanes aq, aq+ACH, aq+2ACH, ...)
+    constexpr int ACH = Cfg::ACH;
     int pNb = sNb, pn = sn;
 #pragma unroll
-    for (int o = CH; o < 32; o <<= 1) {
+    for (int o = ACH; o < 32; o <<= 1) {
         const int uNb = __shfl_up_sync(0xffffffffu, pNb, o);
         const int un = __shfl_up_sync(0xffffffffu, pn, o);
-        if (part * CH >= o) { pNb += uNb; pn += un; }
+        if (part * ACH >= o) { pNb += uNb; pn += un; }
     }
     int Nb = k.Nb + pNb - sNb, npar = k.npar + pn - sn;          // state at this lane's first step
-    const int last = (PARTS - 1) * CH + q;
+    const int last = (PARTS - 1) * ACH + (q % ACH);
     k.Nb += __shfl_sync(0xffffffffu, pNb, last);
     k.npar += __shfl_sync(0xffffffffu, pn, last);
 #pragma unroll
@@ -345,22 +348,24 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
     // block r, r == NP accountant, r == NP+1 walker; the warps of a group share an SM sub-partition
     // (nw = 4) and the walker is its highest warp id (the arbiter prefers it).
     // CH == 32 ("solo"): one group per block; the walker (warp 0) has sub-partition 0 to itself --
-    // warps 4 and 8 stay idle -- and the nine helpers live on the other three sub-partitions.
+    // warps 4, 8, 12 stay idle -- and the twelve helpers (8 producers, 4 accountants of 8 chains each)
+    // live on the other three sub-partitions.
     enum { PRODUCER, ACCOUNTANT, WALKER, IDLE };
+    constexpr int NA = Cfg::NA, ACH = Cfg::ACH;
     int kind, u = 0, w = 0;
     if constexpr (CH == 32) {
         if (warp == 0) kind = WALKER;
         else if ((warp & 3) == 0) kind = IDLE;
         else {
-            const int h = warp - 1 - (warp >> 2);            // 0..8 for warps 1,2,3,5,6,7,9,10,11
+            const int h = warp - 1 - (warp >> 2);            // 0..11 for warps 1,2,3,5,6,7,9,10,11,13,14,15
             kind = h < NP ? PRODUCER : ACCOUNTANT;
-            u = h;
+            u = h < NP ? h : h - NP;                         // producer: Philox block; accountant: which 8 chains
         }
     } else {
         const int role = warp / nw;
         w = warp - role * nw;
-        kind = role < NP ? PRODUCER : (role == NP ? ACCOUNTANT : WALKER);
-        u = role;
+        kind = role < NP ? PRODUCER : (role < NP + NA ? ACCOUNTANT : WALKER);
+        u = role < NP ? role : role - NP;
     }
     const bool is_walker = kind == WALKER;
     const int bch = nw * CH;                             // chains per block
@@ -444,7 +449,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
     } else if (kind == ACCOUNTANT) {
         // ================================ accountant warp ================================
         // accountant identity of this lane: chain slot aq, part ap of that chain's steps
-        const int aq = lane % CH, ap = lane / CH;
+        const int aq = u * ACH + lane % ACH, ap = lane / ACH;
         const int64_t acg = chain0 + w * CH + aq;
         const bool alive = acg < a.n_chains;
         const int64_t acl = alive ? acg : 0;
@@ -475,7 +480,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 }
             }
 #pragma unroll
-            for (int o = CH; o < 32; o <<= 1) {
+            for (int o = ACH; o < 32; o <<= 1) {
                 Nb += __shfl_xor_sync(0xffffffffu, Nb, o);
                 npar += __shfl_xor_sync(0xffffffffu, npar, o);
             }
@@ -491,7 +496,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 const uint32_t was_closed = lds_u8(lb + Cfg::LOGH + (uint32_t)(pr.jb * CH + aq));
                 uint64_t Z = k.Z, SNb = k.SNb;
 #pragma unroll
-                for (int o = CH; o < 32; o <<= 1) {
+                for (int o = ACH; o < 32; o <<= 1) {
                     Z += __shfl_xor_sync(0xffffffffu, Z, o);
                     SNb += __shfl_xor_sync(0xffffffffu, SNb, o);
                 }
@@ -529,7 +534,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         if (pend[1].valid) account(pend[1]);
         // reduce the parts' shares and write the chain's record
 #pragma unroll
-        for (int o = CH; o < 32; o <<= 1) {
+        for (int o = ACH; o < 32; o <<= 1) {
             k.Z += __shfl_xor_sync(0xffffffffu, k.Z, o);
             k.SNb += __shfl_xor_sync(0xffffffffu, k.SNb, o);
             k.SNb2 += __shfl_xor_sync(0xffffffffu, k.SNb2, o);
@@ -678,9 +683,9 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
 
     // ---- write back (all but the walker warps, whose spare lanes have retired)
     __syncthreads();
-    // participants: every warp but the walkers (CH <= 8: the first (NP+1) nw warps; solo: warps 1..11)
+    // participants: every warp but the walkers (CH <= 8: the first (NP+NA) nw warps; solo: warps 1..15)
     const int wb0 = (CH == 32) ? 32 : 0;
-    const int pthreads = (CH == 32) ? nthreads - 32 : (NP + 1) * nw * 32;
+    const int pthreads = (CH == 32) ? nthreads - 32 : (NP + NA) * nw * 32;
     if (!is_walker) {
         if constexpr (DUAL) {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(smem8);
@@ -756,7 +761,7 @@ cudaError_t launch_lat(const PhiloxArgs &a, const LatPlan &p, cudaStream_t st)
     if (e != cudaSuccess) return e;
     const int64_t bch = (int64_t)p.g.nw * CH;
     const int64_t blocks = (a.n_chains + bch - 1) / bch;
-    const int warps = (CH == 32) ? 12 : LatCfg<CH>::GW * p.g.nw;
+    const int warps = (CH == 32) ? 16 : LatCfg<CH>::GW * p.g.nw;
     kern<<<(unsigned)blocks, warps * 32, p.smem, st>>>(a, p.g);
     return cudaGetLastError();
 }
