@@ -59,7 +59,8 @@ template <int CH> struct LatCfg {
     static constexpr int BUF = R * CH * 16;           // bytes of one buffer of A (or B) records
     static constexpr int REC_B = 2 * BUF;             // byte offset of the B records (two buffers of A first)
     static constexpr int RECW = 4 * BUF;              // record bytes per walker warp
-    static constexpr int LOGH = R * CH;               // bytes of one accept (or closed) log of a round
+    static constexpr int LSTR = R + 4;                // pitch of a chain's log row (5 words: 32 lanes hit 32 banks)
+    static constexpr int LOGH = LSTR * CH;            // bytes of one accept (or closed) log of a round
     static constexpr int LOGB = 2 * LOGH;             // one round's log: accept bytes, then closed bytes
     static constexpr int LOGW = 3 * LOGB;             // three rounds in flight per walker warp
     static constexpr int PARTS = 32 / ACH;            // accountant lanes per chain
@@ -256,23 +257,34 @@ template <int ALGO, int CH>
 __device__ __forceinline__ void account_round(Account &k, uint32_t logbuf_abs, int q, int part, bool meas)
 {
     using Cfg = LatCfg<CH>;
-    constexpr int SP = Cfg::SP, PARTS = Cfg::PARTS;
-    uint32_t al[SP], cl[SP];
+    constexpr int SP = Cfg::SP, PARTS = Cfg::PARTS, ACH = Cfg::ACH;
+    static_assert(SP == 4 || SP == 2, "a lane's steps are one 32- or 16-bit word of the chain's log row");
+    // this lane's SP steps are consecutive bytes of the chain's row: one load per log, one store to clear
+    const uint32_t row = logbuf_abs + (uint32_t)(q * Cfg::LSTR + part * SP);
+    uint32_t aw, cw;
+    if constexpr (SP == 4) {
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(aw) : "r"(row) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(row + Cfg::LOGH) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(row), "r"(0u) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(row + Cfg::LOGH), "r"(0u) : "memory");
+    } else {
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(aw) : "r"(row) : "memory");
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(cw) : "r"(row + Cfg::LOGH) : "memory");
+        asm volatile("st.shared.u16 [%0], %1;" :: "r"(row), "r"(0u) : "memory");
+        asm volatile("st.shared.u16 [%0], %1;" :: "r"(row + Cfg::LOGH), "r"(0u) : "memory");
+    }
     int dNb[SP], dn[SP];
     int sNb = 0, sn = 0;
 #pragma unroll
     for (int i = 0; i < SP; ++i) {
-        const uint32_t off = (uint32_t)((part * SP + i) * CH + q);
-        al[i] = lds_u8(logbuf_abs + off);
-        cl[i] = lds_u8(logbuf_abs + Cfg::LOGH + off);
-        const int accd = (al[i] >> 7) & 1;
-        const int par = 1 - 2 * (int)(al[i] & 1u);
+        const uint32_t al = (aw >> (8 * i)) & 0xffu;
+        const int accd = (int)(al >> 7);
+        const int par = 1 - 2 * (int)(al & 1u);
         dn[i] = accd * par;
-        dNb[i] = (ALGO == ALGO_TAYLOR) ? accd * (1 - (int)((al[i] >> 5) & 2u)) : dn[i];
+        dNb[i] = (ALGO == ALGO_TAYLOR) ? accd * (1 - (int)((al >> 5) & 2u)) : dn[i];
         sNb += dNb[i]; sn += dn[i];
     }
     // inclusive scan over the parts of a chain (lanes aq, aq+ACH, aq+2ACH, ...)
-    constexpr int ACH = Cfg::ACH;
     int pNb = sNb, pn = sn;
 #pragma unroll
     for (int o = ACH; o < 32; o <<= 1) {
@@ -284,37 +296,48 @@ __device__ __forceinline__ void account_round(Account &k, uint32_t logbuf_abs, i
     const int last = (PARTS - 1) * ACH + (q % ACH);
     k.Nb += __shfl_sync(0xffffffffu, pNb, last);
     k.npar += __shfl_sync(0xffffffffu, pn, last);
+    if (meas && cw) {
 #pragma unroll
-    for (int i = 0; i < SP; ++i) {
-        if (meas && cl[i]) {
-            k.Z += 1;
-            k.SNb += (uint32_t)Nb;
-            k.SNb2 += (uint64_t)(uint32_t)Nb * (uint32_t)Nb;
-            k.Sn += (uint32_t)npar;
-            k.Sn2 += (uint64_t)(uint32_t)npar * (uint32_t)npar;
+        for (int i = 0; i < SP; ++i) {
+            if ((cw >> (8 * i)) & 0xffu) {                           // closed iteration :130-132
+                k.Z += 1;
+                k.SNb += (uint32_t)Nb;
+                k.SNb2 += (uint64_t)(uint32_t)Nb * (uint32_t)Nb;
+                k.Sn += (uint32_t)npar;
+                k.Sn2 += (uint64_t)(uint32_t)npar * (uint32_t)npar;
+            }
+            Nb += dNb[i]; npar += dn[i];
         }
-        Nb += dNb[i]; npar += dn[i];
-        const uint32_t off = (uint32_t)((part * SP + i) * CH + q);
-        asm volatile("st.shared.u8 [%0], %1;" :: "r"(logbuf_abs + off), "r"(0u) : "memory");
-        asm volatile("st.shared.u8 [%0], %1;" :: "r"(logbuf_abs + Cfg::LOGH + off), "r"(0u) : "memory");
     }
 }
 
-// The round schedule both roles follow: rounds start on a Philox pair, never straddle a segment
-// (MEAS change / dump multiple), and hold at most R steps.
-struct Round {
-    uint64_t s0;     // base step of the record buffer (even)
-    int jb, je;      // steps [s0 + jb, s0 + je) are walked in this round
+// The round schedule every role follows: rounds start on a Philox pair, never straddle a segment
+// (MEAS change / dump multiple), and hold at most R steps.  Consecutive FULL rounds (the steady
+// state) are handed out as one batch so that the per-round bookkeeping is a counter.
+struct Batch {
+    uint64_t s0;     // base step of the first round's record buffer (even)
+    int jb, je;      // the first round walks steps [s0 + jb, s0 + je); all later rounds of the batch are full
+    uint32_t n;      // rounds in the batch (n > 1 only for full rounds)
+    uint64_t s_next; // first step after the batch
 };
 template <int R>
-__device__ __forceinline__ Round make_round(uint64_t s, uint64_t seg_end)
+__device__ __forceinline__ Batch make_batch(uint64_t s, uint64_t seg_end)
 {
-    Round r;
-    r.s0 = s & ~1ull;
-    r.jb = (int)(s - r.s0);
-    const uint64_t left = seg_end - r.s0;
-    r.je = left < (uint64_t)R ? (int)left : R;
-    return r;
+    Batch b;
+    b.s0 = s & ~1ull;
+    b.jb = (int)(s - b.s0);
+    const uint64_t left = seg_end - b.s0;
+    if (b.jb == 0 && left >= (uint64_t)R) {
+        const uint64_t nf = left / (uint64_t)R;
+        b.n = nf > 0x40000000ull ? 0x40000000u : (uint32_t)nf;
+        b.je = R;
+        b.s_next = b.s0 + (uint64_t)b.n * (uint64_t)R;
+    } else {
+        b.n = 1u;
+        b.je = left < (uint64_t)R ? (int)left : R;
+        b.s_next = b.s0 + (uint64_t)b.je;
+    }
+    return b;
 }
 
 // ---- bond storage <-> the caller's compact uint8 [2N] array (bond 2*site = +x, 2*site+1 = +y)
@@ -427,9 +450,9 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             bool meas, dump_first;
             const uint64_t seg_end = next_segment(a, s, meas, dump_first);
             while (s < seg_end) {
-                const Round rd = make_round<R>(s, seg_end);
-                {
-                    const uint64_t pair = (rd.s0 >> 1) + (uint64_t)p_of;
+                const Batch bt = make_batch<R>(s, seg_end);
+                uint64_t pair = (bt.s0 >> 1) + (uint64_t)p_of;
+                for (uint32_t kk = 0; kk < bt.n; ++kk, pair += R / 2) {
                     const uint4 r = philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), c2, c3,
                                                   (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
                     uint4 ra0, rb0, ra1, rb1;
@@ -438,10 +461,10 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     const uint32_t p0 = rec_q + buf;
                     sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0);
                     sts_v4(p0 + CH * 16, ra1); sts_v4(p0 + CH * 16 + Cfg::REC_B, rb1);
+                    group_barrier<Cfg::GW>(bar_id);
+                    buf ^= (uint32_t)Cfg::BUF;
                 }
-                group_barrier<Cfg::GW>(bar_id);
-                buf ^= (uint32_t)Cfg::BUF;
-                s = rd.s0 + (uint64_t)rd.je;
+                s = bt.s_next;
             }
         }
         group_barrier<Cfg::GW>(bar_id);                            // matches the walker's barrier before its last steps
@@ -493,7 +516,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         auto account = [&](const Pending &pr) {
             const uint32_t lb = log_w + lbuf_acc;
             if (pr.dump_first) {                                     // worm_ising_2d.cpp:113-119
-                const uint32_t was_closed = lds_u8(lb + Cfg::LOGH + (uint32_t)(pr.jb * CH + aq));
+                const uint32_t was_closed = lds_u8(lb + Cfg::LOGH + (uint32_t)(aq * Cfg::LSTR + pr.jb));
                 uint64_t Z = k.Z, SNb = k.SNb;
 #pragma unroll
                 for (int o = ACH; o < 32; o <<= 1) {
@@ -518,14 +541,18 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             const uint64_t seg_end = next_segment(a, s, meas, dump_first);
             bool seg_first = true;
             while (s < seg_end) {
-                const Round rd = make_round<R>(s, seg_end);
-                group_barrier<Cfg::GW>(bar_id);
-                // the walker is now inside the previous round: the one before that is complete
-                if (pend[0].valid) account(pend[0]);
-                pend[0] = pend[1];
-                pend[1] = Pending{s, rd.jb, meas, dump_first && seg_first, true};
-                seg_first = false;
-                s = rd.s0 + (uint64_t)rd.je;
+                const Batch bt = make_batch<R>(s, seg_end);
+                uint64_t sr = s;
+                for (uint32_t kk = 0; kk < bt.n; ++kk) {
+                    group_barrier<Cfg::GW>(bar_id);
+                    // the walker is now inside the previous round: the one before that is complete
+                    if (pend[0].valid) account(pend[0]);
+                    pend[0] = pend[1];
+                    pend[1] = Pending{sr, kk ? 0 : bt.jb, meas, dump_first && seg_first, true};
+                    seg_first = false;
+                    sr = bt.s0 + (uint64_t)(kk + 1) * (uint64_t)R;
+                }
+                s = bt.s_next;
             }
         }
         group_barrier<Cfg::GW>(bar_id);                            // matches the walker's barrier before its last steps
@@ -559,7 +586,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         const bool live = cidx < a.n_chains;
         const int64_t cl = live ? cidx : 0;  // dead slots shadow chain 0 in their own shared-memory slot, never write
         uint32_t rec_q = rec_w + (uint32_t)q * 16u;
-        uint32_t log_q = log_w + (uint32_t)q;
+        uint32_t log_q = log_w + (uint32_t)(q * Cfg::LSTR);
         asm volatile("" : "+r"(rec_q), "+r"(log_q));                     // keep them in registers
         unsigned long long hist_row = 0ull;
         uint32_t hist_writer = 0u;
@@ -591,7 +618,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 const uint32_t nrec = (j < R - 2) ? rec_addr(cur, j + 2) : rec_addr(nxt, j + 2 - R);
                 const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
                 lat_step<ALGO, DUAL, SCSH, HIST, MEAS>(g, hist_row, hist_writer, c, p0a, p0b, (int)p1b.x,
-                                                       lg + (uint32_t)(j * CH), lg + (uint32_t)(Cfg::LOGH + j * CH));
+                                                       lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j));
                 p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
             }
         };
@@ -606,7 +633,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 if (j == je - 1) { group_barrier<Cfg::GW>(bar_id); nrec = rec_addr(nxt, jbn); }
                 const uint4 nb_ = lds_v4(nrec + Cfg::REC_B);
                 lat_step<ALGO, DUAL, SCSH, HIST, MEAS>(g, hist_row, hist_writer, c, xa, xb, (int)nb_.x,
-                                                       lg + (uint32_t)(j * CH), lg + (uint32_t)(Cfg::LOGH + j * CH));
+                                                       lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j));
             }
         };
 
@@ -641,33 +668,35 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 if (want) ++nd;
             }
             while (s < seg_end) {
-                const Round rd = make_round<R>(s, seg_end);
-                const uint64_t e = rd.s0 + (uint64_t)rd.je;          // first step of the next round
-                const uint32_t nxt = cur ^ (uint32_t)Cfg::BUF;
-                const uint32_t lg = log_q + lbuf;
-                const bool full = (rd.jb == 0 && rd.je == R);
+                const Batch bt = make_batch<R>(s, seg_end);
                 if (first) {
-                    group_barrier<Cfg::GW>(bar_id);                            // the first round's records are complete
-                    const uint4 kb = lds_v4(rec_addr(cur, rd.jb) + Cfg::REC_B);
+                    group_barrier<Cfg::GW>(bar_id);                  // the first round's records are complete
+                    const uint4 kb = lds_v4(rec_addr(cur, bt.jb) + Cfg::REC_B);
                     c.head = c.closed ? (int)kb.x : c.head;          // kick of the first step
                     first = false;
                 }
-                if (full) {
+                if (bt.jb == 0 && bt.je == R) {
                     if (!piped) {
                         p0a = lds_v4(rec_addr(cur, 0)); p0b = lds_v4(rec_addr(cur, 0) + Cfg::REC_B);
                         p1a = lds_v4(rec_addr(cur, 1)); p1b = lds_v4(rec_addr(cur, 1) + Cfg::REC_B);
                     }
-                    if (meas) full_round(std::true_type{}, cur, nxt, lg);
-                    else full_round(std::false_type{}, cur, nxt, lg);
+                    for (uint32_t kk = 0; kk < bt.n; ++kk) {
+                        const uint32_t nxt = cur ^ (uint32_t)Cfg::BUF;
+                        if (meas) full_round(std::true_type{}, cur, nxt, log_q + lbuf);
+                        else full_round(std::false_type{}, cur, nxt, log_q + lbuf);
+                        cur = nxt;
+                        lbuf = (lbuf == 2u * Cfg::LOGB) ? 0u : lbuf + (uint32_t)Cfg::LOGB;
+                    }
                     piped = true;
                 } else {
-                    if (meas) edge_round(std::true_type{}, cur, nxt, lg, rd.jb, rd.je, (int)(e & 1ull));
-                    else edge_round(std::false_type{}, cur, nxt, lg, rd.jb, rd.je, (int)(e & 1ull));
+                    const uint32_t nxt = cur ^ (uint32_t)Cfg::BUF;
+                    if (meas) edge_round(std::true_type{}, cur, nxt, log_q + lbuf, bt.jb, bt.je, (int)(bt.s_next & 1ull));
+                    else edge_round(std::false_type{}, cur, nxt, log_q + lbuf, bt.jb, bt.je, (int)(bt.s_next & 1ull));
+                    cur = nxt;
+                    lbuf = (lbuf == 2u * Cfg::LOGB) ? 0u : lbuf + (uint32_t)Cfg::LOGB;
                     piped = false;
                 }
-                cur = nxt;
-                lbuf = (lbuf == 2u * Cfg::LOGB) ? 0u : lbuf + (uint32_t)Cfg::LOGB;
-                s = e;
+                s = bt.s_next;
             }
         }
 
@@ -728,7 +757,7 @@ LatPlan lat_plan(int L, int CH, int smem_optin)
     const int NP = (CH == 32) ? 8 : (CH == 8) ? 2 : 1;
     const int R = 64 * NP / CH;
     const size_t recw = (size_t)4 * R * CH * 16;
-    const size_t logw = (size_t)3 * 2 * R * CH;
+    const size_t logw = (size_t)3 * 2 * (R + 4) * CH;
     for (int dual = 1; dual >= 0; --dual) {
         if (!dual && CH != 1) continue;
         const size_t region = dual ? (size_t)4 * N * CH : (size_t)2 * N;
