@@ -44,6 +44,37 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
+// The same function with the key schedule precomputed by the caller (kx[r] = k0 + r*0x9E3779B9,
+// ky[r] = k1 + r*0xBB67AE85): a kernel that draws millions of blocks for one key keeps the twenty
+// round keys in registers instead of re-adding them per block.
+struct PhiloxKeys {
+    uint32_t kx[10], ky[10];
+};
+__device__ __forceinline__ PhiloxKeys philox_keys(uint32_t k0, uint32_t k1)
+{
+    PhiloxKeys k;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        k.kx[r] = k0 + (uint32_t)r * 0x9E3779B9u;
+        k.ky[r] = k1 + (uint32_t)r * 0xBB67AE85u;
+        asm volatile("" : "+r"(k.kx[r]), "+r"(k.ky[r]));     // opaque: keep them, do not rematerialise
+    }
+    return k;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys &k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k.kx[r];
+        c2 = hi0 ^ c3 ^ k.ky[r];
+        c1 = lo1;
+        c3 = lo0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
 // floor(n / d) for n*d < 2^32 with magic = ceil(2^32 / d)  (exact in that range)
 __device__ __forceinline__ uint32_t fastdiv(uint32_t n, uint32_t magic) { return __umulhi(n, magic); }
 

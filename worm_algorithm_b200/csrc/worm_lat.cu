@@ -121,9 +121,10 @@ struct Account {
 //        compact: p = addneg, q = address of bond byte (y bit) of site 0: the bond is owned by
 //                 own = (head & keep) | ((head + addneg) & ~keep) and lives at own + q
 //   rb = {kick, thr, flip, logbits}:  accept iff (nb < thr) xor (flip != 0);  Taylor: nb += 1 | flip
+// numf = float(kfix - 1) * (1 + 2^-18), rounded up (see the threshold computation below)
 template <int ALGO, bool DUAL>
-__device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &prm, uint32_t a, uint32_t b,
-                                            uint32_t chain_abs, uint4 &ra, uint4 &rb)
+__device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &prm, const float numf, uint32_t a,
+                                            uint32_t b, uint32_t chain_abs, uint4 &ra, uint4 &rb)
 {
     const uint32_t d = b >> 30;                                  // :137
     const bool ym = d & 1u, neg = d & 2u;
@@ -144,10 +145,14 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
         uint32_t qi, qd;
         if (!g.lowt) {
             // T >= 1: kfix - 1 < 2^32 and tfix >= 2^32 > a.
-            // (nb+1)*a < kfix  <=>  nb < floor((kfix-1)/a); a == 0 accepts up to the storage cap.
+            // (nb+1)*a < kfix  <=>  nb < floor((kfix-1)/a) =: q, capped at the storage limit 255.
+            // q from a biased float quotient (an overestimate by < 1 whenever q < 257) and one exact
+            // 64-bit check; a == 0 gives +inf -> saturated conversion -> cap, as it must.
             const uint32_t num = (uint32_t)(prm.kfix - 1);
-            const uint32_t q = num / (a | (uint32_t)(a == 0u));
-            qi = (a == 0u) ? 255u : min(q, 255u);
+            const uint32_t q0 = __float2uint_rz(__fdividef(numf, __uint2float_rn(a)));
+            const unsigned long long pq = (unsigned long long)q0 * (unsigned long long)a;
+            const uint32_t q = q0 - (uint32_t)(pq > (unsigned long long)num);
+            qi = min(q, 255u);
             qd = 1u;                                             // a < nb*tfix      <=>  nb >= 1
         } else {
             const unsigned long long num = prm.kfix - 1;
@@ -353,7 +358,7 @@ __device__ __forceinline__ uint32_t dual_word(const uint8_t *gb, int s, int L, i
 }
 
 template <int ALGO, int CH, bool DUAL, bool HIST>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 1)
 worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
 {
     using Cfg = LatCfg<CH>;
@@ -444,6 +449,8 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         const uint32_t c2 = (uint32_t)chain_id, c3 = (uint32_t)(chain_id >> 32);
         const uint32_t chain_abs = region_abs + (DUAL ? (uint32_t)q * 4u : 0u);
         const uint32_t rec_q = rec_w + (uint32_t)q * 16u + (uint32_t)(2 * p_of) * (CH * 16);
+        const PhiloxKeys keys = philox_keys((uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
+        const float numf = __fmul_ru(__uint2float_ru((uint32_t)(prm.kfix - 1)), 1.0f + 1.0f / 262144.0f);
         uint32_t buf = 0u;
         uint64_t s = a.step_begin;
         while (s < a.step_end) {
@@ -453,11 +460,10 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 const Batch bt = make_batch<R>(s, seg_end);
                 uint64_t pair = (bt.s0 >> 1) + (uint64_t)p_of;
                 for (uint32_t kk = 0; kk < bt.n; ++kk, pair += R / 2) {
-                    const uint4 r = philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), c2, c3,
-                                                  (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
+                    const uint4 r = philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), c2, c3, keys);
                     uint4 ra0, rb0, ra1, rb1;
-                    make_record<ALGO, DUAL>(g, prm, r.x, r.y, chain_abs, ra0, rb0);
-                    make_record<ALGO, DUAL>(g, prm, r.z, r.w, chain_abs, ra1, rb1);
+                    make_record<ALGO, DUAL>(g, prm, numf, r.x, r.y, chain_abs, ra0, rb0);
+                    make_record<ALGO, DUAL>(g, prm, numf, r.z, r.w, chain_abs, ra1, rb1);
                     const uint32_t p0 = rec_q + buf;
                     sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0);
                     sts_v4(p0 + CH * 16, ra1); sts_v4(p0 + CH * 16 + Cfg::REC_B, rb1);
