@@ -313,8 +313,15 @@ def run_b200_arm(a) -> None:
     issue_peak = sm_count * 128 * f_max                            # thread-instructions / s
     kern_rate = float(n) * a.num_steps * a.steps / (kern_ms * 1e-3)   # per GPU, kernel only
     achieved = kern_rate * I_ALG
-    roofline = {"bound": "issue", "kernel": "worm_philox_kernel", "achieved": achieved / 1e9, "peak": issue_peak / 1e9,
-                "unit": "G thread-instr/s", "frac": achieved / issue_peak, "traffic": None,
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("worm_lat_kernel")          # dram bytes per launch, from the ncu --set full capture
+    except (OSError, ValueError):
+        pass
+    roofline = {"bound": "issue", "kernel": "worm_lat_kernel", "achieved": achieved / 1e9, "peak": issue_peak / 1e9,
+                "unit": "G thread-instr/s", "frac": achieved / issue_peak, "traffic": traffic,
+                "traffic_note": "dram bytes of one 200k-step launch (profiles/); the chain state is staged in shared memory, HBM is touched at launch start/end only",
                 "alg_instr_per_worm_step": I_ALG, "kernel_ms_per_launch": kern_ms / a.steps,
                 "worm_steps_per_s_per_gpu": kern_rate,
                 "peak_source": "148 SM x 128 lanes x sm_max_mhz (MEASURED_PEAKS.json)" if peaks else "fallback 1965 MHz",
@@ -385,9 +392,9 @@ def main() -> None:
     p.add_argument("--e2e-steps", type=int, default=2)
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--cpu-steps", type=int, default=10_000_000)
-    p.add_argument("--cpu-runs-per-core", type=int, default=2)
+    p.add_argument("--cpu-runs-per-core", type=int, default=4)
     p.add_argument("--ref-steps", type=int, default=10_000_000)
-    p.add_argument("--ref-runs-per-core", type=int, default=2)
+    p.add_argument("--ref-runs-per-core", type=int, default=4)
     a = p.parse_args()
     a.warmup = max(a.warmup, 0)
     if a.impl == "reference":

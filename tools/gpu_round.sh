@@ -13,5 +13,5 @@ NCU_CMD="python bench.py --steps 1 --warmup 3 --num-steps 200000 --no-cpu --e2e-
 $NCU_CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $NCU_CMD > gpurun_out/ncu_launches.log 2>&1
 $NCU_CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:worm_philox -s 3 -c 1 -o gpurun_out/prof_worm $NCU_CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:worm_lat -s 3 -c 1 -o gpurun_out/prof_worm $NCU_CMD > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out
