@@ -274,3 +274,58 @@ def test_host_entry_points(eng, ref_runs):
     # error path: bad argument -> status code + message, no exception from C
     rc = lib.worm_count_host(0, 1, img.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p))
     assert rc == -1 and "W" in _lib.last_error()
+
+
+# ------------------------------------------------------------------------------------------------
+# round / segment edges of the latency kernel: odd starts, runs shorter than a round, odd dump
+# periods, warm-up ending inside a round, empty ranges
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lanes", [2, 4, 8, 32, 1])
+def test_philox_segment_edges_match_oracle(eng, lanes):
+    from oracle import worm_oracle as wo
+    L, n = 8, 11
+    rng = np.random.default_rng(77 + lanes)
+    T = rng.uniform(1.0, 3.5, n)
+    seeds = rng.integers(0, 2 ** 63, n, dtype=np.uint64)
+    cases = [  # (chunks, therm, dump_every)
+        ([1, 1, 1, 2, 3], 0, 0), ([15, 17, 16, 1], 9, 7), ([33, 0, 64, 5], 40, 50), ([7, 250, 3], 123, 13),
+        ([128], 128, 1), ([65], 1000, 3),
+    ]
+    for chunks, therm, dump_every in cases:
+        st = eng.PhiloxState(L, T, seeds, algo=0, chain_id0=5, group_index=np.arange(n) % 2, n_groups=2, hist=True,
+                             max_dumps=300)
+        for ch in chunks:
+            st.run(ch, therm_steps=therm, dump_every=dump_every, lanes_per_chain=lanes)
+        total = sum(chunks)
+        acc, bonds = st.acc.cpu().numpy(), st.bonds.cpu().numpy()
+        head, tail, nd = st.head.cpu().numpy(), st.tail.cpu().numpy(), st.n_dumps.cpu().numpy()
+        ev, dm = st.events.cpu().numpy(), st.dumps.cpu().numpy()
+        hist = np.zeros((2, L * L), dtype=np.int64)
+        for c in range(n):
+            o = wo.run_philox(L, 0, 5 + c, int(seeds[c]), float(T[c]), 0, total, therm, hist=True,
+                              dump_every=dump_every, max_dumps=300)
+            key = (lanes, chunks, therm, dump_every, c)
+            assert (acc[c, :6] == o["acc"][:6]).all(), (key, acc[c], o["acc"])
+            assert (bonds[c] == o["bonds"]).all(), key
+            assert head[c] == o["head"] and tail[c] == o["tail"], key
+            assert nd[c] == o["n_dumps"], key
+            k = min(o["n_dumps"], 300)
+            assert (ev[c, :k] == o["events"]).all(), key
+            assert (dm[c, :k] == o["dumps"]).all(), key
+            hist[c % 2] += o["hist"]
+        assert (st.hist.cpu().numpy() == hist).all(), (lanes, chunks)
+
+
+@pytest.mark.parametrize("L,lanes", [(64, 32), (128, 32), (256, 32), (64, 0), (128, 0), (256, 0)])
+def test_philox_large_lattices_match_oracle(eng, L, lanes):
+    """L = 64 / 128 (one chain per walker, dual layout) and L = 256 (compact layout, one chain per block)."""
+    from oracle import worm_oracle as wo
+    n = 5
+    T = np.array([2.269, 1.2, 3.0, 2.0, 2.5])
+    seeds = np.arange(n, dtype=np.uint64) + 3
+    st = eng.PhiloxState(L, T, seeds, algo=0, max_dumps=4).run(20000, therm_steps=1000, dump_every=50, lanes_per_chain=lanes)
+    acc, bonds = st.acc.cpu().numpy(), st.bonds.cpu().numpy()
+    for c in range(n):
+        o = wo.run_philox(L, 0, c, int(seeds[c]), float(T[c]), 0, 20000, 1000, dump_every=50, max_dumps=4)
+        assert (acc[c, :6] == o["acc"][:6]).all() and (bonds[c] == o["bonds"]).all()
+        assert (st.dumps[c, :min(o["n_dumps"], 4)].cpu().numpy() == o["dumps"]).all()

@@ -9,16 +9,19 @@ cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, bool lowt, i
     *why = "";
     int G = lanes_per_chain;
     if (G == 0) {
-        // Latency mode while the batch fits one block per SM.  Preferred: 32 chains per walker with a
-        // whole SM sub-partition to itself (code 2); else among 8 / 4 / 1 chains per walker (codes
-        // 4 / 8 / 32) the one with the fewest chains per walker that still fits one wave.
+        // Latency mode for every power-of-two lattice that fits shared memory: a chain is a sequence
+        // of dependent steps, so throughput = (chains in flight) / (cycles per step), and the latency
+        // kernel has by far the fewest cycles per step; batches larger than one wave simply run in
+        // waves.  32 chains per walker ("solo", code 2) when the lattice allows it and the batch has
+        // at least two blocks, else one chain per walker (code 32), else 4 or 8.  Thread-per-chain
+        // (code 1) is left for lattices that are not a power of two or do not fit.
+        (void)sm_count;
         G = 1;
-        for (int cand : {4, 8, 32, 2}) {
-            const size_t need = lat_smem_bytes(a.L, cand, smem_optin);
-            if (need == 0) continue;
-            const int64_t bch = lat_chains_per_block(a.L, cand, smem_optin);
-            const int64_t blocks = (a.n_chains + bch - 1) / bch;
-            if (blocks <= sm_count && (cand != 2 || a.n_chains >= 16 * bch)) G = cand;
+        if (a.L >= 4 && !(a.L & (a.L - 1))) {
+            if (lat_smem_bytes(a.L, 2, smem_optin) && a.n_chains >= 64) G = 2;
+            else if (lat_smem_bytes(a.L, 32, smem_optin)) G = 32;
+            else if (lat_smem_bytes(a.L, 8, smem_optin)) G = 8;
+            else if (lat_smem_bytes(a.L, 4, smem_optin)) G = 4;
         }
     }
     if (G == 2 || G == 4 || G == 8 || G == 32) {
