@@ -46,8 +46,8 @@ cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, bool lowt, i
 
 // the two kernels behind launch_philox.  G = lanes_per_chain of the C ABI (4 / 8 / 32 <-> 8 / 4 / 1
 // chains per walker warp of the latency kernel).
-size_t lat_smem_bytes(int L, int G, int smem_optin);           // 0 if this L / G cannot run in latency mode
-int lat_chains_per_block(int L, int G, int smem_optin);
+size_t lat_smem_bytes(int L, int G, bool hist, int smem_optin);   // 0 if this L / G cannot run in latency mode
+int lat_chains_per_block(int L, int G, bool hist, int smem_optin);
 cudaError_t launch_philox_lat(const PhiloxArgs &a, int G, bool lowt, int smem_optin, cudaStream_t st);
 cudaError_t launch_philox_wide(const PhiloxArgs &a, bool force_global, int smem_optin, cudaStream_t st);
 

@@ -46,12 +46,15 @@ struct LatGeo {
     int region;          // bytes of bond storage per walker warp
     int rec_off;         // byte offset of the record rings inside dynamic shared memory
     int log_off;         // byte offset of the step logs
+    int hist_off;        // byte offset of the 16-bit G(r) bins (solo mode with histograms)
     int lowt;            // some chain has T < 1 (general record builder)
     int zero;            // 0 (a value the compiler cannot see through)
 };
 
-template <int CH> struct LatCfg {
-    static constexpr int NP = (CH == 32) ? 8 : (CH == 8) ? 2 : 1;   // producer warps per walker (one Philox block per lane per round)
+// SH: per-chain G(r) bins in shared memory (solo mode with histograms): rounds are half as long to
+// make room for them.
+template <int CH, bool SH = false> struct LatCfg {
+    static constexpr int NP = (CH == 32) ? (SH ? 4 : 8) : (CH == 8) ? 2 : 1;   // producer warps per walker (one Philox block per lane per round)
     static constexpr int ACH = (CH > 8) ? 8 : CH;     // chains per accountant warp
     static constexpr int NA = CH / ACH;               // accountant warps per walker
     static constexpr int GW = NP + NA + 1;            // warps of a group: producers, accountants, walker
@@ -65,6 +68,7 @@ template <int CH> struct LatCfg {
     static constexpr int LOGW = 3 * LOGB;             // three rounds in flight per walker warp
     static constexpr int PARTS = 32 / ACH;            // accountant lanes per chain
     static constexpr int SP = R / PARTS;              // steps per accountant lane per round
+    static constexpr int FLUSH = 4096;                // SH: rounds between flushes of the 16-bit bins (FLUSH * R < 65536)
 };
 
 // ---- shared memory by absolute 32-bit shared-window address.  All hot-loop accesses are volatile
@@ -174,7 +178,7 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
 // One worm step on a pre-decoded record.  On entry `head` already holds this step's kick when the
 // worm is closed; on exit it holds the NEXT step's kick (kick_next) when the worm is closed then.
 // alog / clog: shared addresses of this step's accept / closed log bytes.
-template <int ALGO, bool DUAL, int SCSH, bool HIST, bool MEAS>
+template <int ALGO, bool DUAL, int SCSH, bool HIST, bool SH, bool MEAS>
 __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long hist_row, uint32_t hist_writer,
                                          LatState &c, const uint4 ra, const uint4 rb, const int kick_next,
                                          const uint32_t alog, const uint32_t clog)
@@ -188,9 +192,18 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
         const int t1 = c.head - c.tail;
         const int t2 = (c.head | g.XM | (g.SC - 1)) - (c.tail & g.YM);          // y fields, no borrow from x
         const uint32_t f = closed ? 0u : (uint32_t)((t1 & g.XM) | (t2 & g.YM)); // site difference * SC
-        const uint32_t off8 = (SCSH >= 3) ? (f >> (SCSH - 3)) : (f << (3 - SCSH));
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.global.add.u64 [%0], 1;\n\t}"
-                     :: "l"(hist_row + off8), "r"(hist_writer) : "memory");
+        if constexpr (SH) {
+            // 16-bit bins of this chain in shared memory, two per word (hist_row = their shared address);
+            // the accountants move them to the int64 histogram in HBM every Cfg::FLUSH rounds
+            const uint32_t off2 = (SCSH >= 1) ? (f >> (SCSH - 1)) : (f << 1);
+            const uint32_t ha = (uint32_t)hist_row + off2;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
+                         :: "r"(ha & ~3u), "r"(1u << ((ha & 2u) << 3)), "r"(hist_writer) : "memory");
+        } else {
+            const uint32_t off8 = (SCSH >= 3) ? (f >> (SCSH - 3)) : (f << (3 - SCSH));
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.global.add.u64 [%0], 1;\n\t}"
+                         :: "l"(hist_row + off8), "r"(hist_writer) : "memory");
+        }
     }
     const int tail = closed ? kick : c.tail;                    // kick :128-129 (head has it already)
     c.tail = tail;
@@ -258,10 +271,10 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
 // Replay of one round's log by the producer warp: lane (q, part) owns steps [part*SP, part*SP+SP) of
 // chain slot q.  Occupation-sum / parity-count changes are prefix-summed across the parts, then
 // every lane measures its closed steps (:130-132) with the exact Nb / n of that step.
-template <int ALGO, int CH>
+template <int ALGO, int CH, bool SH>
 __device__ __forceinline__ void account_round(Account &k, uint32_t logbuf_abs, int q, int part, bool meas)
 {
-    using Cfg = LatCfg<CH>;
+    using Cfg = LatCfg<CH, SH>;
     constexpr int SP = Cfg::SP, PARTS = Cfg::PARTS, ACH = Cfg::ACH;
     static_assert(SP == 4 || SP == 2, "a lane's steps are one 32- or 16-bit word of the chain's log row");
     // this lane's SP steps are consecutive bytes of the chain's row: one load per log, one store to clear
@@ -361,7 +374,8 @@ template <int ALGO, int CH, bool DUAL, bool HIST>
 __global__ void __launch_bounds__(512, 1)
 worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
 {
-    using Cfg = LatCfg<CH>;
+    constexpr bool SH = HIST && CH == 32;               // per-chain G(r) bins in shared memory
+    using Cfg = LatCfg<CH, SH>;
     constexpr int R = Cfg::R, NP = Cfg::NP;
     constexpr int SC = DUAL ? 4 * CH : 2;
     constexpr int SCSH = (SC == 2) ? 1 : (SC == 4) ? 2 : (SC == 16) ? 4 : (SC == 32) ? 5 : 7;
@@ -386,7 +400,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         else if ((warp & 3) == 0) kind = IDLE;
         else {
             const int h = warp - 1 - (warp >> 2);            // 0..11 for warps 1,2,3,5,6,7,9,10,11,13,14,15
-            kind = h < NP ? PRODUCER : ACCOUNTANT;
+            kind = h < NP ? PRODUCER : (h - NP < NA ? ACCOUNTANT : IDLE);
             u = h < NP ? h : h - NP;                         // producer: Philox block; accountant: which 8 chains
         }
     } else {
@@ -431,6 +445,10 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
     {
         uint32_t *lg = reinterpret_cast<uint32_t *>(smem8 + g.log_off);
         for (int i = tid; i < nw * Cfg::LOGW / 4; i += nthreads) lg[i] = 0u;
+        if constexpr (SH) {
+            uint32_t *hb = reinterpret_cast<uint32_t *>(smem8 + g.hist_off);
+            for (int i = tid; i < CH * g.N / 2; i += nthreads) hb[i] = 0u;
+        }
     }
     __syncthreads();
 
@@ -537,10 +555,32 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     ++k.nd;
                 }
             }
-            account_round<ALGO, CH>(k, lb, aq, ap, pr.meas);
+            account_round<ALGO, CH, SH>(k, lb, aq, ap, pr.meas);
             lbuf_acc = (lbuf_acc == 2u * Cfg::LOGB) ? 0u : lbuf_acc + (uint32_t)Cfg::LOGB;
         };
 
+        // SH: the group's accountant lanes sweep the block's 16-bit G(r) bins into the HBM histogram
+        auto flush_hist = [&]() {
+            if constexpr (SH) {
+                const int wpc = g.N / 2;                              // words per chain
+                for (int i = u * 32 + lane; i < CH * wpc; i += NA * 32) {
+                    uint32_t v;
+                    asm volatile("atom.shared.exch.b32 %0, [%1], %2;"
+                                 : "=r"(v) : "r"(sbase + (uint32_t)g.hist_off + (uint32_t)i * 4u), "r"(0u) : "memory");
+                    if (v) {
+                        const int qc = i / wpc, wv = i - qc * wpc;
+                        const int64_t cg = chain0 + qc;
+                        if (cg < a.n_chains && a.hist && a.group_index) {
+                            unsigned long long *row =
+                                reinterpret_cast<unsigned long long *>(a.hist + (int64_t)a.group_index[cg] * g.N);
+                            if (v & 0xffffu) atomicAdd(row + 2 * wv, (unsigned long long)(v & 0xffffu));
+                            if (v >> 16) atomicAdd(row + 2 * wv + 1, (unsigned long long)(v >> 16));
+                        }
+                    }
+                }
+            }
+        };
+        int flush_ctr = 0;
         uint64_t s = a.step_begin;
         while (s < a.step_end) {
             bool meas, dump_first;
@@ -557,6 +597,9 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     pend[1] = Pending{sr, kk ? 0 : bt.jb, meas, dump_first && seg_first, true};
                     seg_first = false;
                     sr = bt.s0 + (uint64_t)(kk + 1) * (uint64_t)R;
+                    if constexpr (SH) {
+                        if (++flush_ctr == Cfg::FLUSH) { flush_hist(); flush_ctr = 0; }
+                    }
                 }
                 s = bt.s_next;
             }
@@ -565,6 +608,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         group_barrier<Cfg::GW>(bar_id);                            // the walker has finished its last step
         if (pend[0].valid) account(pend[0]);
         if (pend[1].valid) account(pend[1]);
+        flush_hist();
         // reduce the parts' shares and write the chain's record
 #pragma unroll
         for (int o = ACH; o < 32; o <<= 1) {
@@ -598,7 +642,8 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         uint32_t hist_writer = 0u;
         if constexpr (HIST) {
             if (live && a.hist && a.group_index) {
-                hist_row = (unsigned long long)(a.hist + (int64_t)a.group_index[cl] * g.N);
+                if constexpr (SH) hist_row = (unsigned long long)(sbase + (uint32_t)g.hist_off + (uint32_t)(q * g.N * 2));
+                else hist_row = (unsigned long long)(a.hist + (int64_t)a.group_index[cl] * g.N);
                 hist_writer = 1u;
             }
         }
@@ -623,7 +668,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 if (j == R - 2) group_barrier<Cfg::GW>(bar_id);
                 const uint32_t nrec = (j < R - 2) ? rec_addr(cur, j + 2) : rec_addr(nxt, j + 2 - R);
                 const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
-                lat_step<ALGO, DUAL, SCSH, HIST, MEAS>(g, hist_row, hist_writer, c, p0a, p0b, (int)p1b.x,
+                lat_step<ALGO, DUAL, SCSH, HIST, SH, MEAS>(g, hist_row, hist_writer, c, p0a, p0b, (int)p1b.x,
                                                        lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j));
                 p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
             }
@@ -638,7 +683,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 uint32_t nrec = rec_addr(cur, j + 1);
                 if (j == je - 1) { group_barrier<Cfg::GW>(bar_id); nrec = rec_addr(nxt, jbn); }
                 const uint4 nb_ = lds_v4(nrec + Cfg::REC_B);
-                lat_step<ALGO, DUAL, SCSH, HIST, MEAS>(g, hist_row, hist_writer, c, xa, xb, (int)nb_.x,
+                lat_step<ALGO, DUAL, SCSH, HIST, SH, MEAS>(g, hist_row, hist_writer, c, xa, xb, (int)nb_.x,
                                                        lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j));
             }
         };
@@ -755,13 +800,15 @@ struct LatPlan {
     size_t smem = 0;
 };
 
-LatPlan lat_plan(int L, int CH, int smem_optin)
+LatPlan lat_plan(int L, int CH, bool hist, int smem_optin)
 {
     LatPlan p;
     if (L < 4 || (L & (L - 1)) || (CH != 32 && CH != 8 && CH != 4 && CH != 1)) return p;
     const int N = L * L;
-    const int NP = (CH == 32) ? 8 : (CH == 8) ? 2 : 1;
+    const bool sh = hist && CH == 32;                    // 16-bit G(r) bins in shared memory
+    const int NP = (CH == 32) ? (sh ? 4 : 8) : (CH == 8) ? 2 : 1;
     const int R = 64 * NP / CH;
+    const size_t histb = sh ? (size_t)CH * N * 2 : 0;
     const size_t recw = (size_t)4 * R * CH * 16;
     const size_t logw = (size_t)3 * 2 * (R + 4) * CH;
     for (int dual = 1; dual >= 0; --dual) {
@@ -770,7 +817,7 @@ LatPlan lat_plan(int L, int CH, int smem_optin)
         for (int nw : {4, 2, 1}) {
             if (nw != 4 && CH != 1 && CH != 32) continue;
             if (CH == 32 && nw != 1) continue;
-            const size_t need = nw * (region + recw + logw);
+            const size_t need = (nw * (region + recw + logw) + 15) / 16 * 16 + histb;
             if (need + 1024 > (size_t)smem_optin) continue;
             p.ok = true; p.dual = dual; p.smem = need;
             p.g.L = L; p.g.N = N; p.g.nb2 = 2 * N; p.g.nw = nw;
@@ -780,6 +827,7 @@ LatPlan lat_plan(int L, int CH, int smem_optin)
             p.g.region = (int)region;
             p.g.rec_off = (int)(nw * region);
             p.g.log_off = (int)(nw * (region + recw));
+            p.g.hist_off = (int)((nw * (region + recw + logw) + 15) / 16 * 16);
             p.g.lowt = 0;
             p.g.zero = 0;
             return p;
@@ -796,7 +844,7 @@ cudaError_t launch_lat(const PhiloxArgs &a, const LatPlan &p, cudaStream_t st)
     if (e != cudaSuccess) return e;
     const int64_t bch = (int64_t)p.g.nw * CH;
     const int64_t blocks = (a.n_chains + bch - 1) / bch;
-    const int warps = (CH == 32) ? 16 : LatCfg<CH>::GW * p.g.nw;
+    const int warps = (CH == 32) ? 16 : LatCfg<CH, false>::GW * p.g.nw;
     kern<<<(unsigned)blocks, warps * 32, p.smem, st>>>(a, p.g);
     return cudaGetLastError();
 }
@@ -819,16 +867,16 @@ cudaError_t launch_lat_ah(const PhiloxArgs &a, const LatPlan &p, int CH, cudaStr
 // G = lanes_per_chain of the C ABI: 2 / 4 / 8 / 32 <-> 32 / 8 / 4 / 1 chains per walker warp
 static int chains_per_walker(int G) { return G == 2 ? 32 : 32 / G; }
 
-int lat_chains_per_block(int L, int G, int smem_optin)
+int lat_chains_per_block(int L, int G, bool hist, int smem_optin)
 {
-    const LatPlan p = lat_plan(L, chains_per_walker(G), smem_optin);
+    const LatPlan p = lat_plan(L, chains_per_walker(G), hist, smem_optin);
     return p.ok ? p.g.nw * chains_per_walker(G) : 0;
 }
 
-size_t lat_smem_bytes(int L, int G, int smem_optin)
+size_t lat_smem_bytes(int L, int G, bool hist, int smem_optin)
 {
     if (G != 2 && G != 4 && G != 8 && G != 32) return 0;
-    const LatPlan p = lat_plan(L, chains_per_walker(G), smem_optin);
+    const LatPlan p = lat_plan(L, chains_per_walker(G), hist, smem_optin);
     return p.ok ? p.smem : 0;
 }
 
@@ -836,7 +884,7 @@ cudaError_t launch_philox_lat(const PhiloxArgs &a, int G, bool lowt, int smem_op
 {
     const bool hist = (a.hist != nullptr && a.group_index != nullptr);
     const int CH = chains_per_walker(G);
-    LatPlan p = lat_plan(a.L, CH, smem_optin);
+    LatPlan p = lat_plan(a.L, CH, hist, smem_optin);
     if (!p.ok) return cudaErrorInvalidValue;
     p.g.lowt = lowt ? 1 : 0;
     if (a.algo == ALGO_TAYLOR)

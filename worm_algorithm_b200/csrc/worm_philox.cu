@@ -7,6 +7,7 @@ cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, bool lowt, i
                           cudaStream_t st, const char **why)
 {
     *why = "";
+    const bool hist = (a.hist != nullptr && a.group_index != nullptr);
     int G = lanes_per_chain;
     if (G == 0) {
         // Latency mode for every power-of-two lattice that fits shared memory: a chain is a sequence
@@ -18,15 +19,15 @@ cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, bool lowt, i
         (void)sm_count;
         G = 1;
         if (a.L >= 4 && !(a.L & (a.L - 1))) {
-            if (lat_smem_bytes(a.L, 2, smem_optin) && a.n_chains >= 64) G = 2;
-            else if (lat_smem_bytes(a.L, 32, smem_optin)) G = 32;
-            else if (lat_smem_bytes(a.L, 8, smem_optin)) G = 8;
-            else if (lat_smem_bytes(a.L, 4, smem_optin)) G = 4;
+            if (lat_smem_bytes(a.L, 2, hist, smem_optin) && a.n_chains >= 64) G = 2;
+            else if (lat_smem_bytes(a.L, 32, hist, smem_optin)) G = 32;
+            else if (lat_smem_bytes(a.L, 8, hist, smem_optin)) G = 8;
+            else if (lat_smem_bytes(a.L, 4, hist, smem_optin)) G = 4;
         }
     }
     if (G == 2 || G == 4 || G == 8 || G == 32) {
         if (a.L < 4 || (a.L & (a.L - 1))) { *why = "latency mode (lanes_per_chain 2/4/8/32) needs a power-of-two L >= 4"; return cudaErrorInvalidValue; }
-        if (lat_smem_bytes(a.L, G, smem_optin) == 0) { *why = "lattice too large for latency mode with this lanes_per_chain"; return cudaErrorInvalidValue; }
+        if (lat_smem_bytes(a.L, G, hist, smem_optin) == 0) { *why = "lattice too large for latency mode with this lanes_per_chain"; return cudaErrorInvalidValue; }
         return launch_philox_lat(a, G, lowt, smem_optin, st);
     }
     if (G != 1 && G != -1) { *why = "lanes_per_chain must be 0, 1, 2, 4, 8, 32 or -1"; return cudaErrorInvalidValue; }
