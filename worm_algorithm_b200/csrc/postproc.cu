@@ -30,6 +30,86 @@ __device__ __forceinline__ int par_at(const uint8_t *sp, int pitch, int x, int y
     return sp[y * pitch + 2 * x + dir];
 }
 
+// Fast path (vectorisable shapes): a block handles `cpb` configurations per iteration (cpb > 1 for
+// small lattices, so that an iteration always moves ~64 KiB), and the occupation bytes of the NEXT
+// iteration are already in flight (registers) while the current one is written out: the store
+// phase hides the load latency, and the two block-wide syncs are amortised over cpb configs.
+constexpr int IMG_THREADS = 256;
+constexpr int IMG_MAXV = 8;             // uint4 of occupations per thread per iteration
+
+__global__ void __launch_bounds__(IMG_THREADS)
+image_kernel_pipe(int L, int lgL, int cpb, int64_t n, const uint8_t *__restrict__ bonds, int32_t *__restrict__ img)
+{
+    // L = 2^lgL: every index split below is a shift / mask
+    extern __shared__ __align__(16) uint8_t sp[];
+    const int pitch = 2 * L + 2;                 // bytes per lattice row y (x-major inside), padded
+    const int tile = L * pitch;                  // parity bytes of one configuration
+    const int N = L * L, nb2 = 2 * N, W = 2 * L;
+    const int vpc = nb2 / 16;                    // uint4 per configuration
+    const int vtot = cpb * vpc;                  // uint4 per iteration (<= IMG_THREADS * IMG_MAXV)
+    const int qn = W / 4;                        // int4 per pixel row
+    const int opc = W * qn;                      // int4 per image
+    uint4 v[IMG_MAXV];
+    auto fetch = [&](int64_t cfg0) {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(bonds + cfg0 * (int64_t)nb2);
+        const int64_t lim = (n - cfg0) * vpc;    // uint4 left in the array
+#pragma unroll
+        for (int k = 0; k < IMG_MAXV; ++k) {
+            const int i = threadIdx.x + k * IMG_THREADS;
+            v[k] = (i < vtot && i < lim) ? s4[i] : make_uint4(0, 0, 0, 0);
+        }
+    };
+    int64_t cfg0 = (int64_t)blockIdx.x * cpb;
+    if (cfg0 < n) fetch(cfg0);
+    for (; cfg0 < n; cfg0 += (int64_t)gridDim.x * cpb) {
+        __syncthreads();                         // the previous iteration's reads of the tiles are done
+#pragma unroll
+        for (int k = 0; k < IMG_MAXV; ++k) {
+            const int i = threadIdx.x + k * IMG_THREADS;
+            if (i < vtot) {
+                const int c = i >> (2 * lgL - 3), iv = i & (vpc - 1);           // vpc = 2^(2 lgL - 3)
+                uint8_t *t = sp + c * tile;
+                const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int b = 16 * iv + j;
+                    const int site = b >> 1, y = site >> lgL, x = site & (L - 1);
+                    t[y * pitch + 2 * x + (b & 1)] = (uint8_t)((w[j >> 2] >> (8 * (j & 3))) & 1u);
+                }
+            }
+        }
+        __syncthreads();
+        const int64_t nxt = cfg0 + (int64_t)gridDim.x * cpb;
+        if (nxt < n) fetch(nxt);                 // in flight during the store phase below
+        const int64_t here = (n - cfg0 < cpb) ? (n - cfg0) : cpb;
+        int4 *dst = reinterpret_cast<int4 *>(img + cfg0 * (int64_t)W * W);
+        for (int t = threadIdx.x; t < (int)here * opc; t += IMG_THREADS) {
+            const int c = t >> (2 * lgL), r = t & (opc - 1);                  // opc = 2L * L/2 = 2^(2 lgL)
+            const uint8_t *tp = sp + c * tile;
+            const int px = r >> (lgL - 1), qq = r & (qn - 1);                // qn = L/2
+            const int x = px >> 1, y0 = 2 * qq;        // py = 4*qq .. 4*qq+3  -> y0, y0+1
+            int4 o;
+            if (px & 1) {
+                o.x = par_at(tp, pitch, x, y0, 0);
+                o.y = 0;
+                o.z = par_at(tp, pitch, x, y0 + 1, 0);
+                o.w = 0;
+            } else {
+                const int xm = (x == 0) ? L - 1 : x - 1;
+                const int ym = (y0 == 0) ? L - 1 : y0 - 1;
+                const int yb0 = par_at(tp, pitch, x, y0, 1);
+                const int yb1 = par_at(tp, pitch, x, y0 + 1, 1);
+                o.x = par_at(tp, pitch, x, y0, 0) | yb0 | par_at(tp, pitch, xm, y0, 0) | par_at(tp, pitch, x, ym, 1);
+                o.y = yb0;
+                o.z = par_at(tp, pitch, x, y0 + 1, 0) | yb1 | par_at(tp, pitch, xm, y0 + 1, 0) | yb0;
+                o.w = yb1;
+            }
+            dst[t] = o;
+        }
+    }
+}
+
+// Generic path: any L, any alignment; one configuration per block iteration.
 __global__ void __launch_bounds__(256)
 image_kernel(int L, int64_t n, const uint8_t *__restrict__ bonds, int32_t *__restrict__ img, int vec_out)
 {
@@ -39,66 +119,28 @@ image_kernel(int L, int64_t n, const uint8_t *__restrict__ bonds, int32_t *__res
     for (int64_t cfg = blockIdx.x; cfg < n; cfg += gridDim.x) {
         const uint8_t *src = bonds + cfg * (int64_t)nb2;
         __syncthreads();
-        if ((nb2 & 15) == 0 && ((uintptr_t)src & 15) == 0) {
-            const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-            for (int i = threadIdx.x; i < nb2 / 16; i += blockDim.x) {
-                const uint4 v = s4[i];
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int b = 16 * i + k;
-                    const int site = b >> 1, y = site / L, x = site - y * L;
-                    sp[y * pitch + 2 * x + (b & 1)] = (uint8_t)((w[k >> 2] >> (8 * (k & 3))) & 1u);
-                }
-            }
-        } else {
-            for (int b = threadIdx.x; b < nb2; b += blockDim.x) {
-                const int site = b >> 1, y = site / L, x = site - y * L;
-                sp[y * pitch + 2 * x + (b & 1)] = src[b] & 1u;
-            }
+        for (int b = threadIdx.x; b < nb2; b += blockDim.x) {
+            const int site = b >> 1, y = site / L, x = site - y * L;
+            sp[y * pitch + 2 * x + (b & 1)] = src[b] & 1u;
         }
         __syncthreads();
         int32_t *dst = img + cfg * (int64_t)W * W;
-        if (vec_out) {
-            const int qn = W / 4;                // int4 per pixel row
-            for (int t = threadIdx.x; t < W * qn; t += blockDim.x) {
-                const int px = t / qn, qq = t - px * qn;
-                const int x = px >> 1, y0 = 2 * qq;        // py = 4*qq .. 4*qq+3  -> y0, y0+1
-                int4 o;
-                if (px & 1) {
-                    o.x = par_at(sp, pitch, x, y0, 0);
-                    o.y = 0;
-                    o.z = par_at(sp, pitch, x, y0 + 1, 0);
-                    o.w = 0;
-                } else {
-                    const int xm = (x == 0) ? L - 1 : x - 1;
-                    const int ym = (y0 == 0) ? L - 1 : y0 - 1;
-                    const int yb0 = par_at(sp, pitch, x, y0, 1);
-                    const int yb1 = par_at(sp, pitch, x, y0 + 1, 1);
-                    o.x = par_at(sp, pitch, x, y0, 0) | yb0 | par_at(sp, pitch, xm, y0, 0) | par_at(sp, pitch, x, ym, 1);
-                    o.y = yb0;
-                    o.z = par_at(sp, pitch, x, y0 + 1, 0) | yb1 | par_at(sp, pitch, xm, y0 + 1, 0) | yb0;
-                    o.w = yb1;
-                }
-                reinterpret_cast<int4 *>(dst)[t] = o;
+        for (int t = threadIdx.x; t < W * W; t += blockDim.x) {
+            const int px = t / W, py = t - px * W;
+            const int x = px >> 1, y = py >> 1;
+            int v;
+            if ((px & 1) && (py & 1)) v = 0;
+            else if (px & 1) v = par_at(sp, pitch, x, y, 0);
+            else if (py & 1) v = par_at(sp, pitch, x, y, 1);
+            else {
+                const int xm = (x == 0) ? L - 1 : x - 1;
+                const int ym = (y == 0) ? L - 1 : y - 1;
+                v = par_at(sp, pitch, x, y, 0) | par_at(sp, pitch, x, y, 1) | par_at(sp, pitch, xm, y, 0) |
+                    par_at(sp, pitch, x, ym, 1);
             }
-        } else {
-            for (int t = threadIdx.x; t < W * W; t += blockDim.x) {
-                const int px = t / W, py = t - px * W;
-                const int x = px >> 1, y = py >> 1;
-                int v;
-                if ((px & 1) && (py & 1)) v = 0;
-                else if (px & 1) v = par_at(sp, pitch, x, y, 0);
-                else if (py & 1) v = par_at(sp, pitch, x, y, 1);
-                else {
-                    const int xm = (x == 0) ? L - 1 : x - 1;
-                    const int ym = (y == 0) ? L - 1 : y - 1;
-                    v = par_at(sp, pitch, x, y, 0) | par_at(sp, pitch, x, y, 1) | par_at(sp, pitch, xm, y, 0) |
-                        par_at(sp, pitch, x, ym, 1);
-                }
-                dst[t] = v;
-            }
+            dst[t] = v;
         }
+        (void)vec_out;
     }
 }
 
@@ -273,12 +315,32 @@ int grid_for(int64_t work_items, int threads, int waves_cap = 148 * 16)
 cudaError_t launch_image(int L, int64_t n, const uint8_t *d_bonds, int32_t *d_img, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    const size_t smem = (size_t)L * (2 * L + 2) + 16;
+    const int nb2 = 2 * L * L;
+    const size_t tile = (size_t)L * (2 * L + 2);
+    const bool aligned = (nb2 % 16 == 0) && ((2 * L) % 4 == 0) && (((uintptr_t)d_img & 15) == 0) &&
+                         (((uintptr_t)d_bonds & 15) == 0);
+    const int vpc = nb2 / 16;
+    const bool pow2 = L >= 4 && (L & (L - 1)) == 0;
+    int lgL = 0;
+    while ((1 << lgL) < L) ++lgL;
+    if (aligned && pow2 && vpc <= IMG_THREADS * IMG_MAXV) {
+        // configurations per block iteration: ~64 KiB of output, within the register prefetch budget
+        int cpb = (16384 / (4 * L * L)) > 0 ? 16384 / (4 * L * L) : 1;
+        if (cpb * vpc > IMG_THREADS * IMG_MAXV) cpb = IMG_THREADS * IMG_MAXV / vpc;
+        if ((int64_t)cpb > n) cpb = (int)n;
+        const size_t smem = (size_t)cpb * tile + 16;
+        cudaError_t e = cudaFuncSetAttribute(image_kernel_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const int64_t iters = (n + cpb - 1) / cpb;
+        const int grid = (int)(iters < 148 * 8 ? iters : 148 * 8);
+        image_kernel_pipe<<<grid, IMG_THREADS, smem, st>>>(L, lgL, cpb, n, d_bonds, d_img);
+        return cudaGetLastError();
+    }
+    const size_t smem = tile + 16;
     cudaError_t e = cudaFuncSetAttribute(image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (int)(n < 148 * 8 ? n : 148 * 8);
-    const int vec_out = ((2 * L) % 4 == 0) && (((uintptr_t)d_img & 15) == 0);
-    image_kernel<<<grid, 256, smem, st>>>(L, n, d_bonds, d_img, vec_out);
+    image_kernel<<<grid, 256, smem, st>>>(L, n, d_bonds, d_img, 0);
     return cudaGetLastError();
 }
 
