@@ -142,7 +142,7 @@ size_t worm_mt_workspace_bytes(int64_t n_chains)
 {
     if (n_chains <= 0) return 0;
     const size_t n_pad = align_up((size_t)n_chains, 32);
-    return align_up(n_pad * sizeof(worm::MtChain), 256) + 624 * n_pad * sizeof(uint32_t) + 256;
+    return align_up(n_pad * sizeof(worm::MtChain), 256) + 256;     // chain parameter records (the MT19937 state lives in shared memory)
 }
 
 int worm_mt_run(int L, int64_t n_chains, const double *h_T, const double *h_seed,
@@ -183,7 +183,7 @@ int worm_mt_run(int L, int64_t n_chains, const double *h_T, const double *h_seed
     if (e != cudaSuccess) return cuda_fail(e, "upload chain parameters");
     const uint64_t therm = (uint64_t)(0.1 * (double)num_steps);   // worm_ising_2d.cpp:55
     e = worm::launch_mt(L, n_chains, (int64_t)n_pad, d_prm, num_steps, therm, bond_flag, d_bonds, d_out,
-                        max_events, d_n_events, d_events, d_dumps, max_trace, d_n_trace, d_trace, d_state, st);
+                        max_events, d_n_events, d_events, d_dumps, max_trace, d_n_trace, d_trace, d_state, dev.smem_optin, st);
     if (e != cudaSuccess) return cuda_fail(e, "worm_mt_kernel launch");
     // cudaMemcpyAsync from pageable memory has already staged `prm`; nothing else to wait for
     return WORM_OK;

@@ -35,7 +35,7 @@ cudaError_t launch_mt(int L, int64_t n_chains, int64_t n_pad, const MtChain *d_p
                       uint8_t *d_bonds, int64_t *d_out,
                       int32_t max_events, int32_t *d_n_events, int64_t *d_events, uint8_t *d_dumps,
                       int32_t max_trace, int32_t *d_n_trace, int64_t *d_trace,
-                      uint32_t *d_mt_state, cudaStream_t st);
+                      uint32_t *d_mt_state, int smem_optin, cudaStream_t st);
 
 // lanes_per_chain: 0 = choose; 4 / 8 / 32 = latency mode with that many lanes per chain; 1 = thread
 // per chain, bonds in shared memory when they fit; -1 = thread per chain, bonds in global memory.

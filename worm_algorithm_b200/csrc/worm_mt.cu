@@ -1,166 +1,267 @@
 // worm_mt.cu -- deterministic mode: the reference's Markov chain on the reference's random stream.
 //
-// One thread per chain.  Each thread walks the loop of worm_ising_2d.cpp:111-157 literally --
-// the same draw order (kick :128, direction :137, +/- coin :141, acceptance :151), the same
-// double-precision acceptance ratio K/(nb+1.0) or nb*inv_K (:143,:148; IEEE division and
-// multiplication round identically on the device), the same stop rule (:133-134) -- on its own
-// MT19937 state, seeded as mt19937ar.c:68-81.  The 624-word state lives in global memory,
-// word-major ([624][n_pad]) so a warp's refill is coalesced; bonds are uint8 in d_bonds.
-//
-// This kernel exists for bit-exact parity, not speed: chains stop at chain-specific steps and
-// consume draws conditionally, so lanes diverge.  The production path is worm_philox.cu.
+// One WARP per chain.  Every lane walks the loop of worm_ising_2d.cpp:111-157 redundantly (uniform
+// control flow; shared-memory reads broadcast, all lanes store the same value), so the draw order
+// (kick :128, direction :137, +/- coin :141, acceptance :151) and the stop rule (:133-134) are
+// literally the reference's, while the parts that parallelise use the 32 lanes:
+//   - MT19937 (mt19937ar.c:68-81, :113-148): the 624-word state lives in shared memory; a refill
+//     twists it in three dependency-free phases ([0,227), [227,454), [454,624)) and tempers all 624
+//     words in parallel, so a draw on the walk is one shared-memory load;
+//   - dumps (:120-124, :160-167) are copied by the whole warp.
+// The acceptance test `genrand() < P` is evaluated in integers: genrand() = u32 * 2^-32 exactly, so
+// u32 * 2^-32 < P  <=>  u32 < ceil(P * 2^32), and the thresholds for P = K/(nb+1.0) and nb*inv_K
+// (:143, :148; IEEE doubles, computed with the reference's own expressions on the device with
+// -fmad=false) are tabulated per chain for nb < 64 at kernel start; beyond that the double
+// expression itself is evaluated.  Bonds are uint8 in shared memory when 2N bytes fit, else in the
+// caller's global array.
 #include "worm_common.cuh"
 #include "worm_kernels.h"
 
 namespace worm {
 
-struct MtGen {
-    uint32_t *s;      // this chain's column of the [624][n_pad] state
-    int64_t stride;   // n_pad
-    int pos;
+namespace {
 
-    __device__ __forceinline__ uint32_t &at(int i) { return s[(int64_t)i * stride]; }
+constexpr int MT_N = 624, MT_M = 397;
+constexpr int THR_N = 64;
 
-    __device__ void seed(uint32_t v)
-    {
-        at(0) = v;
-        uint32_t p = v;
-        for (int i = 1; i < 624; ++i) {
-            p = 1812433253u * (p ^ (p >> 30)) + (uint32_t)i;
-            at(i) = p;
-        }
-        pos = 624;
+__device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far)
+{
+    const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+    return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y)
+{
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+// In-place twist of s[624] by the 32 lanes + tempered copy in t[624].  The sequential algorithm
+// updates i = 0..623 in order with s[i+397 mod 624] already NEW for i >= 227 and s[0] NEW for
+// i = 623; the three phases below reproduce exactly those dependencies.
+__device__ __forceinline__ void mt_refill(uint32_t *s, uint32_t *t, int lane)
+{
+    // phase 1: i in [0, 227): old s[i], old s[i+1], old s[i+397]
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = lane + 32 * k;
+        if (i < 227) v[k] = mt_twist(s[i], s[i + 1], s[i + MT_M]);
     }
-
-    __device__ void refill()
-    {
-        // in-place twist; index arithmetic mod 624 reproduces the three-loop form of
-        // mt19937ar.c:121-134 (s[i+397] for i >= 227 is an already-updated word, as there)
-        uint32_t cur = at(0);
-        const uint32_t first_old = cur;
-        for (int i = 0; i < 624; ++i) {
-            const uint32_t nxt = (i + 1 < 624) ? at(i + 1) : at(0);
-            const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
-            const int j = (i + 397 < 624) ? i + 397 : i + 397 - 624;
-            uint32_t v = at(j) ^ (y >> 1);
-            if (y & 1u) v ^= 0x9908b0dfu;
-            at(i) = v;
-            cur = nxt;
-        }
-        (void)first_old;
-        pos = 0;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = lane + 32 * k;
+        if (i < 227) s[i] = v[k];
     }
-
-    __device__ __forceinline__ uint32_t next()
-    {
-        if (pos >= 624) refill();
-        uint32_t y = at(pos++);
-        y ^= y >> 11;
-        y ^= (y << 7) & 0x9d2c5680u;
-        y ^= (y << 15) & 0xefc60000u;
-        y ^= y >> 18;
-        return y;
+    __syncwarp();
+    // phase 2: i in [227, 454): old s[i], old s[i+1], NEW s[i-227]
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = 227 + lane + 32 * k;
+        if (i < 454) v[k] = mt_twist(s[i], s[i + 1], s[i - 227]);
     }
-};
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = 227 + lane + 32 * k;
+        if (i < 454) s[i] = v[k];
+    }
+    __syncwarp();
+    // phase 3: i in [454, 623): old s[i], old s[i+1], NEW s[i-227]; i = 623 uses NEW s[0]
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const int i = 454 + lane + 32 * k;
+        if (i < 623) v[k] = mt_twist(s[i], s[i + 1], s[i - 227]);
+        else if (i == 623) v[k] = mt_twist(s[623], s[0], s[396]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const int i = 454 + lane + 32 * k;
+        if (i < MT_N) s[i] = v[k];
+    }
+    __syncwarp();
+    for (int i = lane; i < MT_N; i += 32) t[i] = mt_temper(s[i]);
+    __syncwarp();
+}
 
-__global__ void __launch_bounds__(64)
-worm_mt_kernel(int L, int64_t n_chains, int64_t n_pad, const MtChain *__restrict__ prm,
+// ceil(P * 2^32) clamped to [0, 2^32]: genrand() < P  <=>  u32 < this
+__device__ __forceinline__ unsigned long long thr_of(double P)
+{
+    const double sc = ceil(ldexp(P, 32));
+    if (!(sc > 0.0)) return 0ull;
+    if (sc >= 4294967296.0) return 4294967296ull;
+    return (unsigned long long)sc;
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(32)
+worm_mt_kernel(int L, int64_t n_chains, const MtChain *__restrict__ prm,
                uint64_t num_steps, uint64_t therm, int bond_flag,
                uint8_t *__restrict__ bonds_all, int64_t *__restrict__ out,
                int32_t max_events, int32_t *__restrict__ n_events, int64_t *__restrict__ events,
                uint8_t *__restrict__ dumps,
-               int32_t max_trace, int32_t *__restrict__ n_trace, int64_t *__restrict__ trace,
-               uint32_t *__restrict__ mt_state)
+               int32_t max_trace, int32_t *__restrict__ n_trace, int64_t *__restrict__ trace)
 {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ __align__(16) uint8_t smem8[];
+    const int lane = threadIdx.x;
+    const int64_t c = blockIdx.x;
     if (c >= n_chains) return;
     const int N = L * L;
     const int nb2 = 2 * N;
     const MtChain p = prm[c];
-    uint8_t *bonds = bonds_all + c * (int64_t)nb2;
-    for (int b = 0; b < nb2; ++b) bonds[b] = 0;                       // worm_ising_2d.cpp:97-101
+    uint32_t *s = reinterpret_cast<uint32_t *>(smem8);                        // MT state
+    uint32_t *t = s + MT_N;                                                   // tempered outputs
+    unsigned long long *thr_inc = reinterpret_cast<unsigned long long *>(t + MT_N);
+    unsigned long long *thr_dec = thr_inc + THR_N;
+    uint8_t *gb = bonds_all + c * (int64_t)nb2;
+    uint8_t *bonds = SMEM ? reinterpret_cast<uint8_t *>(thr_dec + THR_N) : gb;
 
-    MtGen g;
-    g.s = mt_state + c;
-    g.stride = n_pad;
-    g.seed(p.seed);                                                    // :47
+    for (int b = lane; b < nb2; b += 32) bonds[b] = 0;                        // worm_ising_2d.cpp:97-101
+    for (int k = lane; k < THR_N; k += 32) {
+        thr_inc[k] = thr_of(p.K / ((double)k + 1.0));                         // :143
+        thr_dec[k] = thr_of((double)k * p.inv_K);                             // :148
+    }
+    if (lane == 0) {                                                          // init_genrand, mt19937ar.c:68-81
+        uint32_t v = p.seed;
+        s[0] = v;
+        for (int i = 1; i < MT_N; ++i) {
+            v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i;
+            s[i] = v;
+        }
+    }
+    __syncwarp();
+    const uint32_t magicL = (uint32_t)((0x100000000ull + (uint64_t)L - 1) / (uint64_t)L);   // head / L == umulhi(head, magicL)
+    int pos = MT_N;                                                           // forces a refill at the first draw
+    auto draw = [&]() -> uint32_t {
+        if (pos >= MT_N) { mt_refill(s, t, lane); pos = 0; }
+        return t[pos++];
+    };
 
     int head = 0, tail = 0, Nb = 0, status = 0;
     int64_t Nb_tot = 0;
     uint64_t step = 0, Z = 0;
     int32_t ne = 0, nt = 0;
-    const double two_m32 = 1.0 / 4294967296.0;                         // mt19937ar.c:187
 
     for (;;) {
-        if (tail == head) {                                            // :112
-            if (step > therm && step % 50 == 0) {                      // :113-114
+        // the (up to) four draws of this iteration, loaded together when they do not straddle a refill
+        const bool closed = (tail == head);                                   // :112
+        uint32_t r0, r1, r2, r3 = 0u;
+        const int need = closed ? 4 : 3;
+        if (pos + need <= MT_N) {
+            r0 = t[pos]; r1 = t[pos + 1]; r2 = t[pos + 2];
+            if (closed) r3 = t[pos + 3];
+            pos += need;
+        } else if (closed && step >= num_steps) {
+            r0 = draw(); r1 = r2 = 0u;                                        // last iteration: the kick draw only
+        } else {
+            r0 = draw(); r1 = draw(); r2 = draw();
+            if (closed) r3 = draw();
+        }
+        uint32_t u_dir = r0, u_coin = r1, u_acc = r2;
+        if (closed) {
+            if (step > therm && step % 50 == 0) {                             // :113-114
                 if (ne < max_events) {
-                    if (events) {
+                    if (events && lane == 0) {
                         int64_t *e = events + ((int64_t)c * max_events + ne) * 3;
                         e[0] = (int64_t)step; e[1] = (int64_t)Z; e[2] = Nb_tot;
                     }
-                    if (bond_flag && dumps) {                          // :120-124
+                    if (bond_flag && dumps) {                                 // :120-124
+                        __syncwarp();
                         uint8_t *d = dumps + ((int64_t)c * max_events + ne) * nb2;
-                        for (int b = 0; b < nb2; ++b) d[b] = bonds[b];
+                        for (int b = lane; b < nb2; b += 32) d[b] = bonds[b];
                     }
                 }
                 ++ne;
             }
-            if (trace && nt < max_trace) {
-                int64_t *t = trace + ((int64_t)c * max_trace + nt) * 2;
-                t[0] = (int64_t)step; t[1] = Nb;
+            if (trace && nt < max_trace && lane == 0) {
+                int64_t *tr = trace + ((int64_t)c * max_trace + nt) * 2;
+                tr[0] = (int64_t)step; tr[1] = Nb;
             }
             ++nt;
             // (int)floor(genrand()*N) == (u32*N) >> 32: u32*N < 2^53 is exact in double    :128
-            tail = (int)(((uint64_t)g.next() * (uint64_t)N) >> 32);
+            tail = (int)(((uint64_t)r0 * (uint64_t)N) >> 32);
             head = tail;
-            Z += 1;                                                    // :130
-            Nb_tot -= Nb;                                              // :132
-            if (step >= num_steps) break;                              // :133-134
+            Z += 1;                                                           // :130
+            Nb_tot -= Nb;                                                     // :132
+            if (step >= num_steps) {                                          // :133-134
+                break;                                                        // (draws loaded ahead of a shift that never happens change nothing observable)
+            }
+            u_dir = r1; u_coin = r2; u_acc = r3;
         }
-        const int d = (int)(g.next() >> 30);                           // floor(genrand()*4)  :137
-        const int x = head % L, y = head / L;
+        const int d = (int)(u_dir >> 30);                                     // floor(genrand()*4)  :137
+        const int y = (int)fastdiv((uint32_t)head, magicL), x = head - y * L;
         int nh, ib;
-        // neighbour table :88-95 and bond_number :214-244 in closed form; the L == 2 branch
-        // order of bond_number sends both x-directions to the x == 0 site's bond (likewise y)
-        if (d == 0)      { nh = y * L + (x + 1) % L;          ib = 2 * ((L == 2) ? y * L : head); }
-        else if (d == 1) { nh = ((y + 1) % L) * L + x;        ib = 2 * ((L == 2) ? x : head) + 1; }
-        else if (d == 2) { nh = y * L + (x + L - 1) % L;      ib = 2 * ((L == 2) ? y * L : nh); }
-        else             { nh = ((y + L - 1) % L) * L + x;    ib = 2 * ((L == 2) ? x : nh) + 1; }
-        const int nb = bonds[ib];                                      // :139
-        int delta;
-        double P;
-        if ((double)g.next() * two_m32 < 0.5) { delta = 1;  P = p.K / ((double)nb + 1.0); }     // :141-144
-        else                                  { delta = -1; P = (double)nb * p.inv_K; }          // :146-149
-        if ((double)g.next() * two_m32 < P) {                          // :151
+        if (L == 2) {
+            // bond_number's branch order sends both x-directions to the x == 0 site's bond (likewise y)
+            if (d == 0)      { nh = y * L + (x + 1) % L;          ib = 2 * (y * L); }
+            else if (d == 1) { nh = ((y + 1) % L) * L + x;        ib = 2 * x + 1; }
+            else if (d == 2) { nh = y * L + (x + L - 1) % L;      ib = 2 * (y * L); }
+            else             { nh = ((y + L - 1) % L) * L + x;    ib = 2 * x + 1; }
+        } else {
+            // neighbour table :88-95 and bond_number :214-244 in closed form
+            const bool ym = d & 1, neg = d & 2;
+            const int cc = ym ? y : x;
+            const int edge = neg ? 0 : L - 1;
+            const int diff = (cc == edge) ? (neg ? L - 1 : 1 - L) : (neg ? -1 : 1);
+            nh = head + diff * (ym ? L : 1);
+            ib = 2 * (neg ? nh : head) + (int)ym;
+        }
+        const int nb = bonds[ib];                                             // :139
+        const bool inc = u_coin < 0x80000000u;                                // genrand() < 0.5  :141
+        const int delta = inc ? 1 : -1;
+        unsigned long long thr;
+        if (nb < THR_N) thr = inc ? thr_inc[nb] : thr_dec[nb];
+        else thr = inc ? thr_of(p.K / ((double)nb + 1.0)) : thr_of((double)nb * p.inv_K);
+        if ((unsigned long long)u_acc < thr) {                                // genrand() < P  :151
             if (nb + delta > 255) { status = 1; }
             else {
+                __syncwarp();
                 bonds[ib] = (uint8_t)(nb + delta);
+                __syncwarp();
                 Nb += delta;
                 head = nh;
             }
         }
-        ++step;                                                        // :156
+        ++step;                                                               // :156
     }
-    int64_t *o = out + c * MT_STRIDE;
-    o[0] = (int64_t)Z; o[1] = Nb_tot; o[2] = (int64_t)step; o[3] = Nb; o[4] = status;
-    o[5] = 0; o[6] = 0; o[7] = 0;
-    if (n_events) n_events[c] = ne;
-    if (n_trace) n_trace[c] = nt;
+    __syncwarp();
+    if (SMEM) {
+        for (int b = lane; b < nb2; b += 32) gb[b] = bonds[b];
+    }
+    if (lane == 0) {
+        int64_t *o = out + c * MT_STRIDE;
+        o[0] = (int64_t)Z; o[1] = Nb_tot; o[2] = (int64_t)step; o[3] = Nb; o[4] = status;
+        o[5] = 0; o[6] = 0; o[7] = 0;
+        if (n_events) n_events[c] = ne;
+        if (n_trace) n_trace[c] = nt;
+    }
 }
+
+}  // namespace
 
 cudaError_t launch_mt(int L, int64_t n_chains, int64_t n_pad, const MtChain *d_prm,
                       uint64_t num_steps, uint64_t therm, int bond_flag,
                       uint8_t *d_bonds, int64_t *d_out,
                       int32_t max_events, int32_t *d_n_events, int64_t *d_events, uint8_t *d_dumps,
                       int32_t max_trace, int32_t *d_n_trace, int64_t *d_trace,
-                      uint32_t *d_mt_state, cudaStream_t st)
+                      uint32_t *d_mt_state, int smem_optin, cudaStream_t st)
 {
-    const int threads = 32;
-    const int64_t blocks = (n_chains + threads - 1) / threads;
-    worm_mt_kernel<<<(unsigned)blocks, threads, 0, st>>>(L, n_chains, n_pad, d_prm, num_steps, therm, bond_flag,
-                                                         d_bonds, d_out, max_events, d_n_events, d_events, d_dumps,
-                                                         max_trace, d_n_trace, d_trace, d_mt_state);
+    (void)n_pad; (void)d_mt_state;
+    const size_t base = (size_t)2 * MT_N * 4 + (size_t)2 * THR_N * 8;
+    const size_t with_bonds = base + (size_t)2 * L * L;
+    const bool smem = with_bonds + 1024 <= (size_t)smem_optin;
+    const size_t bytes = smem ? with_bonds : base;
+    auto kern = smem ? worm_mt_kernel<true> : worm_mt_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)n_chains, 32, bytes, st>>>(L, n_chains, d_prm, num_steps, therm, bond_flag, d_bonds, d_out,
+                                               max_events, d_n_events, d_events, d_dumps,
+                                               max_trace, d_n_trace, d_trace);
     return cudaGetLastError();
 }
 
