@@ -1,29 +1,34 @@
 // worm_lat.cu -- production worm kernel, "latency mode" (sm_100a, hand-written CUDA + inline PTX).
 //
-// For sweeps with fewer Markov chains than the GPU has issue slots (BASELINE configs[1]: 4096
-// chains on 148 x 4 SM sub-partitions).  A chain is a sequence of dependent steps, so
-//     throughput = chains / (cycles per step),
-// and the kernel is built around the per-step critical path
-//     head --IADD--> bond address --LDS--> occupation --IADD,SHF,LOP3--> head.
+// A Markov chain is a sequence of dependent steps, so
+//     throughput = (chains in flight) / (cycles per step),
+// and BASELINE configs[1] has only 4096 chains for 148 x 4 SM sub-partitions.  The kernel is built
+// around the cycles one step costs the warp that walks the chains: the dependency chain
+//     head --IADD--> bond address --LDS--> occupation --ISETP--> accept --SEL--> head
+// and the number of instructions that warp has to issue (a lone warp issues in order).
 //
-// Warp specialisation.  A block is nw PRODUCER warps + nw WALKER warps (warp w and warp nw+w form
-// a pair that lands on the same SM sub-partition, so the hardware scheduler fills the walker's
-// dependency stalls with the producer's independent instructions; walkers are the high warps
-// because the sub-partition arbiter prefers the higher warp id):
-//   * a producer lane draws Philox blocks (two steps each) for the chains of its pair and turns
-//     them, ahead of time, into ready-to-use step records: pre-decoded head increment and wrap
-//     mask, absolute shared-memory addresses of the two copies of the bond, kick site, occupation
-//     threshold and accept polarity.  Records go into a double-buffered shared-memory ring, one
-//     round (R steps per chain) per buffer; a pair meets at a named barrier once per round.
-//   * a walker warp owns CH = 8, 4 or 1 chains, one per lane; its other lanes retire at once
-//     (SIMD lanes are free here; warp issue slots and shared-memory wavefronts are not: a 128-bit
-//     load by 8 lanes is one wavefront, by 32 lanes four).  Records are fetched two steps ahead.
-//     The kick that follows a closing move is folded into the accept select and the select is a
-//     bit mask ((nb - thr) >> 31, xor polarity, LOP3), so no predicate sits on the head -> head path.
+// Warp specialisation.  The warps of a block form groups of three roles:
+//   * PRODUCER warps draw Philox blocks (two steps each, key schedule in registers) for the chains
+//     of their group and turn them, ahead of time, into ready-to-use step records: pre-decoded head
+//     increment and wrap mask, absolute shared-memory addresses of the two copies of the bond, kick
+//     site, occupation threshold and accept polarity.  Records go into a double-buffered
+//     shared-memory ring, one round (R steps per chain) per buffer.
+//   * the WALKER warp owns CH chains, one per lane (lanes beyond CH retire at once).  Records are
+//     fetched two steps ahead; the kick that follows a closing move is folded into the accept
+//     select; everything independent of the loaded occupation is forced into the load's shadow.
+//     It keeps no observables: it logs one byte per accepted step and one per closed step.
+//   * ACCOUNTANT warps replay those logs two rounds later and accumulate Z, sum Nb, sum Nb^2,
+//     sum n, sum n^2 with the exact Nb / n of every closed step; they also write the dump events
+//     and, in solo mode, sweep the shared-memory G(r) bins into the HBM histogram.
+//   The group meets at one named barrier per round.
+//   CH = 32 ("solo"): one group per block -- the walker has an SM sub-partition to itself, 8 (4 with
+//   histograms) producers and 4 accountants share the other three.  CH = 8 / 4 / 1: up to four
+//   groups per block, the warps of a group on the same sub-partition (walker = highest warp id,
+//   which the sub-partition arbiter prefers).
 // Bond storage ("dual" layout): one 32-bit word per SITE holding the occupations of its four
 // bonds (+x, +y, -x, -y), words interleaved across the chains of the walker.  A bond is stored at
-// both of its sites, so the load address is head + constant (one IADD, no neighbour arithmetic on
-// the critical path), a chain only ever touches its own banks (no conflicts between the chains of
+// both of its sites, so the load address is head + constant (one IADD, no neighbour arithmetic in
+// front of the load), a chain only ever touches its own banks (no conflicts between the chains of
 // a warp), and an accepted move stores twice off the critical path.  Lattices whose dual layout
 // does not fit use the compact one-byte-per-bond layout (one chain per walker).
 // Power-of-two L only: the head is a scaled site index whose x and y bit fields wrap by masking.
@@ -40,7 +45,7 @@ namespace {
 
 struct LatGeo {
     int L, N, nb2;       // nb2 = 2N bonds per chain
-    int nw;              // walker (= producer) warps per block
+    int nw;              // groups (walkers) per block
     int SC;              // bytes per unit of the scaled site index (dual: 4 * CH, compact: 2)
     int XM, YM;          // x / y bit fields of a scaled site index
     int region;          // bytes of bond storage per walker warp
