@@ -195,9 +195,14 @@ class WormSimulation(object):
                    lanes_per_chain=self._lanes)
             per_T = st.group_acc                  # summed over the chains of each temperature on the device
         per_T = dist.allreduce_sum(per_T, self._world)
+        hist = None
+        if self._hist:
+            # G(r) histogram per temperature, [nT, N] with bin dy*L + dx; bin 0 == Z
+            hist = st.hist if st is not None else torch.zeros((nT, N), dtype=torch.int64, device=per_T.device)
+            hist = dist.allreduce_sum(hist, self._world)
         self.results = dict(T=Tc[c0:c1], seeds=seeds[c0:c1], replica=r_idx[c0:c1], t_index=t_idx[c0:c1],
                             chain_range=(c0, c1), acc=(st.acc if st is not None else None), state=st,
-                            per_T=per_T, mode="philox", therm=therm)
+                            per_T=per_T, hist=hist, mode="philox", therm=therm)
         a = per_T.cpu().numpy().astype(np.float64)
         for ti_, T in enumerate(self._T_range):
             Z = a[ti_, ACC_Z]
