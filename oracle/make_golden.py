@@ -51,6 +51,8 @@ RUNS = [
     (12, 2.269185314213022, 50000, 77.0, 0),
     (32, 1.5, 200000, 1.0, 1),
     (64, 2.27, 300000, 31337.0, 1),
+    # BASELINE.json configs[0]: L = 16 at T_c = 2.269, single chain, 1e5 sweeps = 5.12e7 steps
+    (16, 2.269, 51200000, 1.0, 0),
 ]
 
 
@@ -208,5 +210,8 @@ def gen_post():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    gen_runs()
-    gen_post()
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("all", "runs"):
+        gen_runs()
+    if what in ("all", "post"):
+        gen_post()

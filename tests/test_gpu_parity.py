@@ -65,6 +65,19 @@ def test_mt_mode_long_run_survey_vector(eng):
     assert "%.12f" % (int(out[1]) * 2.269 / (int(out[0]) * 1024)) == "-1.407139231916"
 
 
+def test_mt_mode_baseline_config0(eng, ref_runs):
+    """BASELINE.json configs[0]: L = 16 at T_c = 2.269, one chain, 1e5 sweeps (5.12e7 steps), against the
+    reference executable's own output line (tests/golden/ref_runs.json, made by oracle/make_golden.py)."""
+    rec = [r for r in ref_runs if r["num_steps"] == 51200000][0]
+    res = eng.run_mt(rec["L"], [rec["T"]], [rec["seed"]], rec["num_steps"], bond_flag=0, max_events=0)
+    out = res.out[0].cpu().numpy()
+    fields = rec["output_line"].split()
+    assert int(out[4]) == 0 and int(out[2]) == rec["step_num"] == int(fields[6])
+    assert "%.12f" % (int(out[0]) / int(out[2])) == fields[3]
+    assert "%.12f" % (int(out[1]) * rec["T"] / (int(out[0]) * rec["L"] ** 2)) == fields[4]
+    assert int(out[3]) == rec["Nb_final"]
+
+
 def test_mt_mode_batch_matches_oracle_with_trace(eng):
     from oracle import worm_oracle as wo
     rng = np.random.default_rng(11)
