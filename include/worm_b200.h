@@ -157,6 +157,32 @@ int worm_block(int W, int64_t n, const int32_t *d_in, int32_t *d_out,
 int worm_count(int W, int64_t n, const int32_t *d_img, int64_t *d_count, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Leading principal component of a stack of images, with the reference's delete-one-block jackknife
+ * (pca.py:97-147: TruncatedSVD(n_components=1).fit(data).explained_variance_[0] of the un-centred
+ * [n][d] matrix, i.e. the variance of the projection on the leading right singular vector;
+ * utils.py:90-104 block_resampling = the num_blocks KFold training sets; utils.py:123-135).
+ *
+ * d_images      int32 [n][d], small integers (|v| <= 256 and max|v|^2 * ceil(n/num_blocks) < 2^24, so
+ *               that the tensor-core Gram matrices are exact; anything else returns WORM_E_ARG)
+ * num_blocks    1 .. 64 (1 = no resampling); n >= num_blocks
+ * d_explained   f64 [1 + num_blocks]: [0] the full data set, [1 + b] with block b deleted
+ * d_sigma2      f64 [1 + num_blocks] or NULL: leading eigenvalue of X^T X (sigma_1^2) of each set
+ * d_component   f64 [d] or NULL: components_[0] of the full set, sign such that it sums to > 0
+ * h_iters, h_residual   host outputs (may be NULL): power iterations used, last max_j |dv_j|
+ * Synchronises the stream (convergence is checked on the host every few iterations).
+ *
+ * worm_pca_gram is the tensor-core stage alone: d_gram f32 [num_blocks][ldg][ldg], ldg = (d + 3) & ~3,
+ * G_b = X_b^T X_b (exact integers), rows / columns >= d zero.  Workspace: worm_pca_workspace_bytes
+ * with gram_only = 1.
+ * ------------------------------------------------------------------------------------------- */
+size_t worm_pca_workspace_bytes(int d, int64_t n, int num_blocks, int gram_only);
+int worm_pca(int d, int64_t n, const int32_t *d_images, int num_blocks, int max_iters, double tol,
+             double *d_explained, double *d_sigma2, double *d_component, int32_t *h_iters,
+             double *h_residual, void *d_workspace, size_t workspace_bytes, void *stream);
+int worm_pca_gram(int d, int64_t n, const int32_t *d_images, int num_blocks, float *d_gram,
+                  void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer drop-ins (allocate, copy in, run, copy out, free, synchronise).
  * worm_sim_host replaces the per-temperature Popen loop of worm_simulation.py:107-129:
  *   rng_mode 0 = deterministic MT19937 (h_seed read as double bits via h_seed_f64),
@@ -170,6 +196,9 @@ int worm_image_host(int L, int64_t n, const uint8_t *h_bonds, int32_t *h_img);
 int worm_block_host(int W, int64_t n, const int32_t *h_in, int32_t *h_out,
                     int double_bonds_value, int variant);
 int worm_count_host(int W, int64_t n, const int32_t *h_img, int64_t *h_count);
+/* h_explained f64 [1 + num_blocks]; h_component f64 [d] or NULL */
+int worm_pca_host(int d, int64_t n, const int32_t *h_images, int num_blocks, int max_iters, double tol,
+                  double *h_explained, double *h_component, int32_t *h_iters, double *h_residual);
 
 #ifdef __cplusplus
 }

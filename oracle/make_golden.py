@@ -208,6 +208,55 @@ def gen_post():
     print("post.npz:", len(g), "arrays")
 
 
+def gen_pca():
+    """Run the reference's own PrincipalComponent (pca.py, unmodified, sklearn TruncatedSVD) on image files
+    in the reference's `{L}_config_{T}.txt` format built from reference-executable dumps, and keep the
+    images with its answers.  numpy's global RNG is seeded first: TruncatedSVD's default solver is
+    randomised (random_state=None)."""
+    import_reference()
+    import pca as ref_pca                   # noqa  (resolved from REF on sys.path)
+    from oracle import postproc_oracle as po
+    from oracle import pca_oracle
+    g = {}
+    cases = ((4, 2.0, 400000, 3.0, 10), (4, 3.0, 400000, 4.0, 7), (8, 2.269, 1500000, 5.0, 10))
+    root = tempfile.mkdtemp(prefix="wormpca_")
+    by_L = {}
+    for (L, T, steps, seed, nb) in cases:
+        r = rr.run_ref(L, T, steps, seed, 1)
+        imgs = np.stack([po.image_from_bonds(dmp, L) for dmp in r.dumps]).reshape(len(r.dumps), -1)
+        assert imgs.shape[0] >= imgs.shape[1], (L, imgs.shape)
+        imgs = imgs[: 3 * imgs.shape[1] + 5]                     # keep the fixture small, length not a multiple of nb
+        by_L.setdefault((L, nb), []).append((T, imgs))
+    for (L, nb), items in by_L.items():
+        ddir = os.path.join(root, "L%d_nb%d" % (L, nb), "in") + "/"
+        sdir = os.path.join(root, "L%d_nb%d" % (L, nb), "out") + "/"
+        os.makedirs(ddir)
+        for (T, imgs) in items:
+            with open(ddir + "%d_config_%s.txt" % (L, float(T)), "w") as f:
+                for row in imgs:
+                    f.write("%s %s\n" % (T, " ".join(str(int(v)) for v in row)))
+        np.random.seed(12345)
+        pc = ref_pca.PrincipalComponent(L, num_blocks=nb, data_dir=ddir, save_dir=sdir, save=True)
+        saved = open(sdir + "leading_eigenvalue_%d.txt" % L).read()
+        for (T, imgs) in items:
+            key = ("%d_config_%s.txt" % (L, float(T))).split("_")[-1].rstrip(".txt").rstrip("0")
+            tag = "pca_L%d_T%s" % (L, key)
+            lam = float(pc._eig_vals[key][0][0])
+            err = float(pc._err[key])
+            vec = np.asarray(pc._eig_vecs[key])[0]
+            evs, s2, comp, oerr = pca_oracle.pca_leading(imgs, nb)
+            print(tag, imgs.shape, "ref", lam, err, "exact", evs[0], oerr)
+            assert abs(lam - evs[0]) < 1e-7 * abs(lam) and abs(err - oerr) < 1e-5 * abs(err) + 1e-12
+            g[tag + "_images"] = imgs.astype(np.int8)
+            g[tag + "_ref"] = np.array([lam, err, nb], dtype=np.float64)
+            g[tag + "_vec"] = vec if vec.sum() > 0 else -vec
+        g["pca_L%d_nb%d_file" % (L, nb)] = np.frombuffer(saved.encode(), dtype=np.uint8)
+    import shutil
+    shutil.rmtree(root, ignore_errors=True)
+    np.savez_compressed(os.path.join(GOLD, "pca.npz"), **g)
+    print("pca.npz:", len(g), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -215,3 +264,5 @@ if __name__ == "__main__":
         gen_runs()
     if what in ("all", "post"):
         gen_post()
+    if what in ("all", "pca"):
+        gen_pca()

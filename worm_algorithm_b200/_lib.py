@@ -50,6 +50,12 @@ SIGNATURES = {
     "worm_image_host": (C.c_int, [C.c_int, _i64, _vp, _vp]),
     "worm_block_host": (C.c_int, [C.c_int, _i64, _vp, _vp, C.c_int, C.c_int]),
     "worm_count_host": (C.c_int, [C.c_int, _i64, _vp, _vp]),
+    "worm_pca_workspace_bytes": (_sz, [C.c_int, _i64, C.c_int, C.c_int]),
+    "worm_pca": (C.c_int, [C.c_int, _i64, _vp, C.c_int, C.c_int, _dbl, _vp, _vp, _vp,
+                           C.POINTER(C.c_int32), _pd, _vp, _sz, _vp]),
+    "worm_pca_gram": (C.c_int, [C.c_int, _i64, _vp, C.c_int, _vp, _vp, _sz, _vp]),
+    "worm_pca_host": (C.c_int, [C.c_int, _i64, _vp, C.c_int, C.c_int, _dbl, _vp, _vp,
+                                C.POINTER(C.c_int32), _pd]),
 }
 
 _lib = None

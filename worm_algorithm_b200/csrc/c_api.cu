@@ -299,6 +299,55 @@ int worm_count(int W, int64_t n, const int32_t *d_img, int64_t *d_count, void *s
     return WORM_OK;
 }
 
+static int pca_check(int d, int64_t n, int num_blocks)
+{
+    if (d < 1 || d > (1 << 20)) return fail(WORM_E_ARG, "d = %d out of range", d);
+    if (num_blocks < 1 || num_blocks > worm::PCA_MAX_BLOCKS) return fail(WORM_E_ARG, "num_blocks = %d out of range [1, %d]", num_blocks, worm::PCA_MAX_BLOCKS);
+    if (n < num_blocks || n > 0x7fffffffll) return fail(WORM_E_ARG, "n = %lld must be in [num_blocks, 2^31)", (long long)n);
+    return WORM_OK;
+}
+
+size_t worm_pca_workspace_bytes(int d, int64_t n, int num_blocks, int gram_only)
+{
+    if (pca_check(d, n, num_blocks)) return 0;
+    return worm::pca_workspace_bytes(d, n, num_blocks, !gram_only);
+}
+
+int worm_pca_gram(int d, int64_t n, const int32_t *d_images, int num_blocks, float *d_gram,
+                  void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (int rc = pca_check(d, n, num_blocks)) return rc;
+    if (!d_images || !d_gram || !d_workspace) return fail(WORM_E_ARG, "null pointer");
+    if (workspace_bytes < worm::pca_workspace_bytes(d, n, num_blocks, false))
+        return fail(WORM_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, worm::pca_workspace_bytes(d, n, num_blocks, false));
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    const char *why = nullptr;
+    cudaError_t e = worm::launch_pca_gram(d, n, d_images, num_blocks, d_gram, d_workspace, dev.sm, (cudaStream_t)stream, &why);
+    if (e != cudaSuccess) return why ? fail(e == cudaErrorInvalidValue ? WORM_E_ARG : WORM_E_CUDA, "%s", why) : cuda_fail(e, "pca gram");
+    return WORM_OK;
+}
+
+int worm_pca(int d, int64_t n, const int32_t *d_images, int num_blocks, int max_iters, double tol,
+             double *d_explained, double *d_sigma2, double *d_component, int32_t *h_iters,
+             double *h_residual, void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (int rc = pca_check(d, n, num_blocks)) return rc;
+    if (!d_images || !d_explained || !d_workspace) return fail(WORM_E_ARG, "null pointer");
+    if (max_iters < 1 || !(tol > 0.0)) return fail(WORM_E_ARG, "max_iters >= 1 and tol > 0 required");
+    if (workspace_bytes < worm::pca_workspace_bytes(d, n, num_blocks, true))
+        return fail(WORM_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, worm::pca_workspace_bytes(d, n, num_blocks, true));
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    const char *why = nullptr;
+    int iters = 0;
+    cudaError_t e = worm::launch_pca(d, n, d_images, num_blocks, max_iters, tol, d_explained, d_sigma2, d_component, &iters,
+                                     h_residual, d_workspace, dev.sm, (cudaStream_t)stream, &why);
+    if (e != cudaSuccess) return why ? fail(e == cudaErrorInvalidValue ? WORM_E_ARG : WORM_E_CUDA, "%s", why) : cuda_fail(e, "pca");
+    if (h_iters) *h_iters = iters;
+    return WORM_OK;
+}
+
 /* ------------------------------------------------------------------------------------------- */
 namespace {
 struct DevBuf {
@@ -399,6 +448,29 @@ int worm_count_host(int W, int64_t n, const int32_t *h_img, int64_t *h_count)
     if ((e = cudaMemcpy(in.p, h_img, (size_t)n * W * W * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "copy in");
     if (int rc = worm_count(W, n, (const int32_t *)in.p, (int64_t *)out.p, nullptr)) return rc;
     if ((e = cudaMemcpy(h_count, out.p, (size_t)n * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "copy out");
+    return WORM_OK;
+}
+
+int worm_pca_host(int d, int64_t n, const int32_t *h_images, int num_blocks, int max_iters, double tol,
+                  double *h_explained, double *h_component, int32_t *h_iters, double *h_residual)
+{
+    if (int rc = pca_check(d, n, num_blocks)) return rc;
+    if (!h_images || !h_explained) return fail(WORM_E_ARG, "null pointer");
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    DevBuf in, ev, comp, ws;
+    cudaError_t e;
+    const size_t wsb = worm::pca_workspace_bytes(d, n, num_blocks, true);
+    if ((e = in.alloc((size_t)n * d * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = ev.alloc((size_t)(num_blocks + 1) * 8)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = comp.alloc((size_t)d * 8)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = ws.alloc(wsb)) != cudaSuccess) return cuda_fail(e, "cudaMalloc workspace");
+    if ((e = cudaMemcpy(in.p, h_images, (size_t)n * d * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "copy in");
+    if (int rc = worm_pca(d, n, (const int32_t *)in.p, num_blocks, max_iters, tol, (double *)ev.p, nullptr,
+                          h_component ? (double *)comp.p : nullptr, h_iters, h_residual, ws.p, wsb, nullptr))
+        return rc;
+    if ((e = cudaMemcpy(h_explained, ev.p, (size_t)(num_blocks + 1) * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "copy out");
+    if (h_component && (e = cudaMemcpy(h_component, comp.p, (size_t)d * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "copy out");
     return WORM_OK;
 }
 

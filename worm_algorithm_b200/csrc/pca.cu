@@ -1,0 +1,727 @@
+// pca.cu -- leading principal component of a stack of configuration images, with the delete-one-block
+// jackknife of the reference (worm_algorithm/pca.py:97-147: TruncatedSVD(n_components=1) of the
+// un-centred [n_cfg, d] image matrix, explained_variance_ = var(X v1); utils.py:90-104 block_resampling
+// = KFold(num_blocks) training sets; utils.py:123-135 jackknife_err).
+//
+// Device pipeline (everything stays in HBM):
+//   1. pca_pack_kernel   int32 images [n, d] -> bf16 Xt [d, Ktot], pixel-major, each jackknife block in its
+//                        own zero-padded run of 64-wide k tiles; per-block column sums; max |value|.
+//   2. gram_kernel       per-block Gram matrices G_b = X_b^T X_b on the 5th-generation tensor cores
+//                        (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM; TMA 128B-swizzled operand
+//                        tiles; only the lower triangle of 128x256 tiles is computed and mirrored on the
+//                        way out).  Pixel values are small integers, so every product and partial sum
+//                        is an integer below 2^24: the fp32 result is EXACT (checked on the host from
+//                        max|value| and the block length; larger inputs are refused, not rounded).
+//   3. gram_sum_kernel   G_full = sum_b G_b.
+//   4. power iteration   for the 1 + num_blocks problems at once (full data and each delete-one
+//                        set, A_j = G_full - G_{j-1}): fp64 matrix-vector products on the exact fp32
+//                        Gram matrices, HBM-bound.
+//   5. explained variance lambda_j / n_j - (s_j . v_j / n_j)^2.
+#include <cuda.h>   // CUtensorMap and its enums only; cuTensorMapEncodeTiled is fetched through the runtime
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+#include "worm_kernels.h"
+
+namespace worm {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// 1. pack: transpose + convert, block column sums
+// ---------------------------------------------------------------------------------------------------
+struct PackPlan {
+    int d, nb;
+    int64_t ktot;
+    int cfg0[PCA_MAX_BLOCKS + 1];   // first configuration of jackknife block b (cfg0[nb] = n)
+    int kt0[PCA_MAX_BLOCKS + 1];    // first 64-wide k tile of block b in Xt (kt0[nb] = Ktot / 64)
+};
+
+__global__ void __launch_bounds__(256) pca_pack_kernel(const int32_t *__restrict__ img, __nv_bfloat16 *__restrict__ xt,
+                                                       long long *__restrict__ colsum, int *__restrict__ maxabs,
+                                                       const PackPlan p)
+{
+    __shared__ int tile[64][65];
+    const int kt = blockIdx.x, c0 = blockIdx.y * 64, t = threadIdx.x;
+    int b = 0;
+    while (kt >= p.kt0[b + 1]) ++b;
+    const int cfg_first = p.cfg0[b] + (kt - p.kt0[b]) * 64, cfg_end = p.cfg0[b + 1];
+    int mx = 0;
+    {
+        const int c = c0 + (t & 63);
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const int k = (t >> 6) + 4 * i, cfg = cfg_first + k;
+            int v = 0;
+            if (cfg < cfg_end && c < p.d) v = img[(size_t)cfg * p.d + c];
+            tile[k][t & 63] = v;
+            mx = max(mx, abs(v));
+        }
+    }
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((t & 31) == 0 && mx) atomicMax(maxabs, mx);
+    __syncthreads();
+    {
+        const int k2 = t & 31;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int cl = (t >> 5) + 8 * i, c = c0 + cl;
+            if (c < p.d) {
+                __nv_bfloat162 w;
+                w.x = __int2bfloat16_rn(tile[2 * k2][cl]);
+                w.y = __int2bfloat16_rn(tile[2 * k2 + 1][cl]);
+                *reinterpret_cast<__nv_bfloat162 *>(xt + (size_t)c * p.ktot + (size_t)kt * 64 + 2 * k2) = w;
+            }
+        }
+    }
+    if (t < 64 && c0 + t < p.d) {
+        long long s = 0;
+#pragma unroll 8
+        for (int k = 0; k < 64; ++k) s += tile[k][t];
+        if (s) atomicAdd(reinterpret_cast<unsigned long long *>(colsum + (size_t)b * p.d + c0 + t), (unsigned long long)s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 2. Gram matrices on tcgen05
+// ---------------------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2, B_HALF_BYTES = 128 * BK * 2, STAGE_BYTES = A_BYTES + 2 * B_HALF_BYTES;
+constexpr int GRAM_THREADS = 256;
+constexpr int GRAM_SMEM = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int TMEM_COLS = 512;   // two 256-column accumulators: the epilogue of tile i overlaps the MMAs of tile i+1
+
+struct GramPlan {
+    int d, ldg, nb, tm_count, tiles_per_block;
+    int kt0[PCA_MAX_BLOCKS + 1];
+    float *G;   // [nb][ldg][ldg]
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// A protocol error must end the launch with an error, never hang the device: the spin is bounded.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t spins = 0;
+    while (!mbar_try(bar, parity))
+        if (++spins > (1u << 28)) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile, 128-byte rows, 128B swizzle (what the TMA box {64 x rows} with SWIZZLE_128B
+// lays down): 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100), layout type 2.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr)
+{
+    return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t idesc_bf16(int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct Tile {
+    int b, tm, tn, ncols;
+};
+// Lower-triangle enumeration: row tile tm (128 rows) meets column tiles tn (256 columns) with
+// tn * 256 <= tm * 128 + 127.  A tile whose right half lies wholly above the diagonal is computed 128 wide.
+__device__ __forceinline__ Tile decode_tile(int t, const GramPlan &p)
+{
+    Tile r;
+    r.b = t / p.tiles_per_block;
+    int rem = t - r.b * p.tiles_per_block, tm = 0;
+    for (;; ++tm) {
+        const int c = tm / 2 + 1;
+        if (rem < c) break;
+        rem -= c;
+    }
+    r.tm = tm;
+    r.tn = rem;
+    r.ncols = min(BN, (tm + 1) * BM - rem * BN);
+    return r;
+}
+
+__global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramPlan p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t bars = base + STAGES * STAGE_BYTES;
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+    auto tempty = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t slot = bars + 8u * (2 * STAGES + 4);
+    volatile uint32_t *slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = p.nb * p.tiles_per_block;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull(a), 1);
+            mbar_init(tempty(a), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    } else if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        int stage = 0, phase = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const Tile tl = decode_tile(t, p);
+            const int k0 = p.kt0[tl.b], nk = p.kt0[tl.b + 1] - k0;
+            for (int kb = 0; kb < nk; ++kb) {
+                if (lane == 0) {
+                    mbar_wait(empty(stage), phase ^ 1);
+                    const uint32_t a = base + stage * STAGE_BYTES, bsm = a + A_BYTES;
+                    mbar_expect_tx(full(stage), A_BYTES + tl.ncols * BK * 2);
+                    tma_load_2d(a, &tmap, full(stage), (k0 + kb) * BK, tl.tm * BM);
+                    tma_load_2d(bsm, &tmap, full(stage), (k0 + kb) * BK, tl.tn * BN);
+                    if (tl.ncols > 128) tma_load_2d(bsm + B_HALF_BYTES, &tmap, full(stage), (k0 + kb) * BK, tl.tn * BN + 128);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        int stage = 0, phase = 0, it = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+            const Tile tl = decode_tile(t, p);
+            const int nk = p.kt0[tl.b + 1] - p.kt0[tl.b];
+            const int as = it & 1, aphase = (it >> 1) & 1;
+            const uint32_t idesc = idesc_bf16(tl.ncols);
+            if (lane == 0) {
+                mbar_wait(tempty(as), aphase ^ 1);
+                tc_fence_after();
+            }
+            __syncwarp();
+            for (int kb = 0; kb < nk; ++kb) {
+                if (lane == 0) {
+                    mbar_wait(full(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a = base + stage * STAGE_BYTES;
+                    const uint64_t adesc = smem_desc_sw128(a), bdesc = smem_desc_sw128(a + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16(tmem + as * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(empty(stage));
+                    if (kb == nk - 1) umma_commit(tfull(as));
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> G (direct rows, and the mirrored transpose) =====
+        const int w = warp - 4;
+        int it = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+            const Tile tl = decode_tile(t, p);
+            const int as = it & 1, aphase = (it >> 1) & 1;
+            mbar_wait(tfull(as), aphase);
+            tc_fence_after();
+            float *Gb = p.G + (size_t)tl.b * p.ldg * p.ldg;
+            const int row = tl.tm * BM + 32 * w + lane;
+            for (int c0 = 0; c0 < tl.ncols; c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem + (uint32_t)(as * BN + c0) + ((uint32_t)(32 * w) << 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+                    "tcgen05.wait::ld.sync.aligned;"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+                const int col0 = tl.tn * BN + c0;
+                if (row < p.ldg) {
+                    float *dst = Gb + (size_t)row * p.ldg + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (col0 + j < p.ldg)
+                            *reinterpret_cast<float4 *>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                }
+                // columns inside the diagonal 128 x 128 block are already written symmetrically above
+                if (col0 < tl.tm * BM && row < p.ldg) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.ldg) Gb[(size_t)(col0 + j) * p.ldg + row] = __uint_as_float(v[j]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(as));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 3. G_full = sum_b G_b
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gram_sum_kernel(const float4 *__restrict__ G, float4 *__restrict__ out, size_t quads, int nb)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < quads; i += (size_t)gridDim.x * blockDim.x) {
+        float4 s = G[i];
+        for (int b = 1; b < nb; ++b) {
+            const float4 g = G[(size_t)b * quads + i];
+            s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+        }
+        out[i] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 4. power iteration on the nj = 1 + nb problems A_0 = G_full, A_j = G_full - G_{j-1}
+// ---------------------------------------------------------------------------------------------------
+constexpr int MV_ROWS = 2, MV_JC = 6, MV_WARPS = 8;
+
+__device__ __forceinline__ double warp_sum(double x)
+{
+    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// W_j = A_j V_j.  One warp per MV_ROWS rows; the matrices are exact integers in fp32, the vectors and
+// all accumulation fp64.  G: [nb + 1][ldg][ldg] with the full matrix at index nb.  V, W: [nj][ldg].
+__global__ void __launch_bounds__(MV_WARPS * 32) pca_matvec_kernel(const float *__restrict__ G, const double *__restrict__ V,
+                                                                    double *__restrict__ W, int ldg, int nb)
+{
+    const int lane = threadIdx.x & 31;
+    const int r0 = (blockIdx.x * MV_WARPS + (threadIdx.x >> 5)) * MV_ROWS;
+    if (r0 >= ldg) return;
+    const int nj = nb + 1;
+    const size_t mat = (size_t)ldg * ldg;
+    const float *full = G + (size_t)nb * mat;
+    int rr[MV_ROWS];
+#pragma unroll
+    for (int r = 0; r < MV_ROWS; ++r) rr[r] = min(r0 + r, ldg - 1);
+
+    for (int j0 = 0; j0 < nj; j0 += MV_JC) {
+        double acc[MV_ROWS][MV_JC];
+#pragma unroll
+        for (int r = 0; r < MV_ROWS; ++r)
+#pragma unroll
+            for (int j = 0; j < MV_JC; ++j) acc[r][j] = 0.0;
+        for (int c = lane * 4; c < ldg; c += 128) {
+            float4 g[MV_ROWS];
+#pragma unroll
+            for (int r = 0; r < MV_ROWS; ++r) g[r] = *reinterpret_cast<const float4 *>(full + (size_t)rr[r] * ldg + c);
+#pragma unroll
+            for (int j = 0; j < MV_JC; ++j) {
+                if (j0 + j < nj) {
+                    const double2 va = *reinterpret_cast<const double2 *>(V + (size_t)(j0 + j) * ldg + c);
+                    const double2 vb = *reinterpret_cast<const double2 *>(V + (size_t)(j0 + j) * ldg + c + 2);
+#pragma unroll
+                    for (int r = 0; r < MV_ROWS; ++r)
+                        acc[r][j] += (double)g[r].x * va.x + (double)g[r].y * va.y + (double)g[r].z * vb.x + (double)g[r].w * vb.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < MV_JC; ++j) {
+            if (j0 + j >= nj) break;
+            const int jj = j0 + j;
+            double sub[MV_ROWS];
+#pragma unroll
+            for (int r = 0; r < MV_ROWS; ++r) sub[r] = 0.0;
+            if (jj > 0) {   // the deleted block's own contribution
+                const float *Gb = G + (size_t)(jj - 1) * mat;
+                for (int c = lane * 4; c < ldg; c += 128) {
+                    const double2 va = *reinterpret_cast<const double2 *>(V + (size_t)jj * ldg + c);
+                    const double2 vb = *reinterpret_cast<const double2 *>(V + (size_t)jj * ldg + c + 2);
+#pragma unroll
+                    for (int r = 0; r < MV_ROWS; ++r) {
+                        const float4 g = *reinterpret_cast<const float4 *>(Gb + (size_t)rr[r] * ldg + c);
+                        sub[r] += (double)g.x * va.x + (double)g.y * va.y + (double)g.z * vb.x + (double)g.w * vb.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < MV_ROWS; ++r) {
+                const double s = warp_sum(acc[r][j] - sub[r]);
+                if (lane == 0 && r0 + r < ldg) W[(size_t)jj * ldg + r0 + r] = s;
+            }
+        }
+    }
+}
+
+__device__ double block_sum(double x, double *scratch)
+{
+    x = warp_sum(x);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = x;
+    __syncthreads();
+    double s = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += scratch[i];
+    return s;
+}
+
+// start vectors: the normalised column sums of the included configurations (for images, close to the
+// leading singular vector already) plus a small fixed pattern so that no start is exactly zero.
+__global__ void __launch_bounds__(256) pca_init_kernel(const long long *__restrict__ colsum, double *__restrict__ V, int d, int ldg, int nb)
+{
+    __shared__ double scratch[8];
+    const int j = blockIdx.x;
+    double *v = V + (size_t)j * ldg;
+    double ss = 0.0;
+    for (int c = threadIdx.x; c < ldg; c += blockDim.x) {
+        double x = 0.0;
+        if (c < d) {
+            long long s = 0;
+            for (int b = 0; b < nb; ++b)
+                if (b != j - 1) s += colsum[(size_t)b * d + c];
+            x = (double)s;
+        }
+        v[c] = x;
+        ss += x * x;
+    }
+    const double nrm = sqrt(block_sum(ss, scratch));
+    double s2 = 0.0;
+    for (int c = threadIdx.x; c < ldg; c += blockDim.x) {
+        double x = 0.0;
+        if (c < d) {
+            const uint32_t h = (uint32_t)c * 2654435761u + 0x9E3779B9u;
+            x = (nrm > 0.0 ? v[c] / nrm : 0.0) + 1e-3 * (0.5 + (double)(h >> 8) * (1.0 / 16777216.0)) / sqrt((double)d);
+        }
+        v[c] = x;
+        s2 += x * x;
+    }
+    const double n2 = sqrt(block_sum(s2, scratch));
+    for (int c = threadIdx.x; c < ldg; c += blockDim.x) v[c] = v[c] / n2;
+}
+
+// stats[j] = { Rayleigh quotient V.W (|V| = 1), |V_new - V|^2 };  V <- W / |W| when normalise != 0.
+__global__ void __launch_bounds__(256) pca_update_kernel(double *__restrict__ V, const double *__restrict__ W, double *__restrict__ stats,
+                                                         int ldg, int normalise)
+{
+    __shared__ double scratch[8];
+    const int j = blockIdx.x;
+    double *v = V + (size_t)j * ldg;
+    const double *w = W + (size_t)j * ldg;
+    double vw = 0.0, ww = 0.0;
+    for (int c = threadIdx.x; c < ldg; c += blockDim.x) {
+        vw += v[c] * w[c];
+        ww += w[c] * w[c];
+    }
+    vw = block_sum(vw, scratch);
+    ww = block_sum(ww, scratch);
+    double diff = 0.0;
+    if (normalise && ww > 0.0) {
+        const double inv = 1.0 / sqrt(ww);
+        for (int c = threadIdx.x; c < ldg; c += blockDim.x) {
+            const double x = w[c] * inv, dx = x - v[c];
+            diff += dx * dx;
+            v[c] = x;
+        }
+    }
+    diff = block_sum(diff, scratch);
+    if (threadIdx.x == 0) {
+        stats[2 * j] = vw;
+        stats[2 * j + 1] = diff;
+    }
+}
+
+// explained variance of the projection on v_j: mean((X v)^2) - mean(X v)^2 over the included configurations
+__global__ void __launch_bounds__(256) pca_finish_kernel(const double *__restrict__ V, const double *__restrict__ stats,
+                                                         const long long *__restrict__ colsum, const PackPlan p, int ldg,
+                                                         double *__restrict__ explained, double *__restrict__ sigma2,
+                                                         double *__restrict__ component)
+{
+    __shared__ double scratch[8];
+    const int j = blockIdx.x;
+    const double *v = V + (size_t)j * ldg;
+    double sv = 0.0, vs = 0.0;
+    for (int c = threadIdx.x; c < p.d; c += blockDim.x) {
+        long long s = 0;
+        for (int b = 0; b < p.nb; ++b)
+            if (b != j - 1) s += colsum[(size_t)b * p.d + c];
+        sv += (double)s * v[c];
+        vs += v[c];
+    }
+    sv = block_sum(sv, scratch);
+    vs = block_sum(vs, scratch);
+    const double n = (double)(p.cfg0[p.nb] - (j > 0 ? p.cfg0[j] - p.cfg0[j - 1] : 0));
+    if (threadIdx.x == 0) {
+        const double m = sv / n;
+        explained[j] = stats[2 * j] / n - m * m;
+        if (sigma2) sigma2[j] = stats[2 * j];
+    }
+    if (j == 0 && component) {   // sign convention: the component sums to a positive number
+        const double sg = vs < 0.0 ? -1.0 : 1.0;
+        for (int c = threadIdx.x; c < p.d; c += blockDim.x) component[c] = sg * v[c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+void make_pack_plan(int d, int64_t n, int nb, PackPlan &p)
+{
+    p.d = d;
+    p.nb = nb;
+    // sklearn KFold(n_splits = nb) without shuffling: the first n % nb folds hold n / nb + 1 samples
+    int cfg = 0, kt = 0;
+    for (int b = 0; b < nb; ++b) {
+        const int len = (int)(n / nb) + (b < n % nb ? 1 : 0);
+        p.cfg0[b] = cfg;
+        p.kt0[b] = kt;
+        cfg += len;
+        kt += (len + BK - 1) / BK;
+    }
+    p.cfg0[nb] = cfg;
+    p.kt0[nb] = kt;
+    p.ktot = (int64_t)kt * BK;
+}
+
+struct Layout {
+    size_t xt, colsum, maxabs, gram, v, w, stats, total;
+    int ldg;
+};
+
+Layout make_layout(int d, const PackPlan &p, bool with_iteration)
+{
+    Layout l;
+    l.ldg = (d + 3) & ~3;
+    size_t off = 0;
+    l.xt = off;      off = align_up(off + (size_t)d * p.ktot * 2, 1024);
+    l.colsum = off;  off = align_up(off + (size_t)p.nb * d * 8, 256);
+    l.maxabs = off;  off = align_up(off + 256, 256);
+    l.gram = off;
+    if (with_iteration) {
+        off = align_up(off + (size_t)(p.nb + 1) * l.ldg * l.ldg * 4, 256);
+        l.v = off;      off = align_up(off + (size_t)(p.nb + 1) * l.ldg * 8, 256);
+        l.w = off;      off = align_up(off + (size_t)(p.nb + 1) * l.ldg * 8, 256);
+        l.stats = off;  off = align_up(off + (size_t)(p.nb + 1) * 16, 256);
+    } else {
+        l.v = l.w = l.stats = off;
+    }
+    l.total = off;
+    return l;
+}
+
+cudaError_t run_pack_and_gram(int d, int64_t n, const int32_t *d_img, const PackPlan &pp, const Layout &lay, uint8_t *ws,
+                              float *d_gram, int sm_count, cudaStream_t st, const char **why)
+{
+    cudaError_t e;
+    auto *xt = reinterpret_cast<__nv_bfloat16 *>(ws + lay.xt);
+    auto *colsum = reinterpret_cast<long long *>(ws + lay.colsum);
+    int *maxabs = reinterpret_cast<int *>(ws + lay.maxabs);
+    if ((e = cudaMemsetAsync(ws + lay.colsum, 0, (lay.maxabs + 256) - lay.colsum, st)) != cudaSuccess) return e;
+    {
+        dim3 grid((unsigned)pp.kt0[pp.nb], (unsigned)((d + 63) / 64));
+        pca_pack_kernel<<<grid, 256, 0, st>>>(d_img, xt, colsum, maxabs, pp);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    // exactness gate: every partial sum of products must stay below 2^24 (fp32 integers) and every value
+    // must be a bf16 integer (|v| <= 256)
+    int h_max = 0;
+    if ((e = cudaMemcpyAsync(&h_max, maxabs, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    int64_t longest = 0;
+    for (int b = 0; b < pp.nb; ++b) longest = std::max<int64_t>(longest, pp.cfg0[b + 1] - pp.cfg0[b]);
+    if (h_max > 256 || (int64_t)h_max * h_max * longest >= (1ll << 24)) {
+        *why = "pixel values too large for an exact bf16 x bf16 -> fp32 Gram matrix (need max|v| <= 256 and max|v|^2 * block length < 2^24)";
+        return cudaErrorInvalidValue;
+    }
+
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) {
+        *why = "cuTensorMapEncodeTiled not available from this driver";
+        return cudaErrorNotSupported;
+    }
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)pp.ktot, (cuuint64_t)d};
+    const cuuint64_t gstride[1] = {(cuuint64_t)pp.ktot * 2};
+    const cuuint32_t box[2] = {BK, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, xt, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+        *why = "cuTensorMapEncodeTiled failed";
+        return cudaErrorInvalidValue;
+    }
+    GramPlan gp;
+    gp.d = d;
+    gp.ldg = lay.ldg;
+    gp.nb = pp.nb;
+    gp.tm_count = (lay.ldg + BM - 1) / BM;
+    gp.tiles_per_block = 0;
+    for (int tm = 0; tm < gp.tm_count; ++tm) gp.tiles_per_block += tm / 2 + 1;
+    for (int b = 0; b <= pp.nb; ++b) gp.kt0[b] = pp.kt0[b];
+    gp.G = d_gram;
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+        attr_err = cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM);
+    });
+    if (attr_err != cudaSuccess) return attr_err;
+    const int total = gp.nb * gp.tiles_per_block;
+    gram_kernel<<<std::min(total, sm_count), GRAM_THREADS, GRAM_SMEM, st>>>(tmap, gp);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t pca_workspace_bytes(int d, int64_t n, int nb, bool with_iteration)
+{
+    PackPlan pp;
+    make_pack_plan(d, n, nb, pp);
+    return make_layout(d, pp, with_iteration).total;
+}
+
+int pca_ldg(int d) { return (d + 3) & ~3; }
+
+cudaError_t launch_pca_gram(int d, int64_t n, const int32_t *d_img, int nb, float *d_gram, void *d_ws, int sm_count,
+                            cudaStream_t st, const char **why)
+{
+    PackPlan pp;
+    make_pack_plan(d, n, nb, pp);
+    const Layout lay = make_layout(d, pp, false);
+    return run_pack_and_gram(d, n, d_img, pp, lay, static_cast<uint8_t *>(d_ws), d_gram, sm_count, st, why);
+}
+
+cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_iters, double tol, double *d_explained,
+                       double *d_sigma2, double *d_component, int *h_iters, double *h_residual, void *d_ws, int sm_count,
+                       cudaStream_t st, const char **why)
+{
+    PackPlan pp;
+    make_pack_plan(d, n, nb, pp);
+    const Layout lay = make_layout(d, pp, true);
+    uint8_t *ws = static_cast<uint8_t *>(d_ws);
+    float *G = reinterpret_cast<float *>(ws + lay.gram);
+    cudaError_t e = run_pack_and_gram(d, n, d_img, pp, lay, ws, G, sm_count, st, why);
+    if (e != cudaSuccess) return e;
+    const int ldg = lay.ldg, nj = nb + 1;
+    const size_t quads = (size_t)ldg * ldg / 4;
+    gram_sum_kernel<<<(unsigned)std::min<size_t>((quads + 255) / 256, (size_t)sm_count * 8), 256, 0, st>>>(
+        reinterpret_cast<const float4 *>(G), reinterpret_cast<float4 *>(G + (size_t)nb * ldg * ldg), quads, nb);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+
+    auto *colsum = reinterpret_cast<const long long *>(ws + lay.colsum);
+    double *V = reinterpret_cast<double *>(ws + lay.v), *W = reinterpret_cast<double *>(ws + lay.w);
+    double *stats = reinterpret_cast<double *>(ws + lay.stats);
+    pca_init_kernel<<<nj, 256, 0, st>>>(colsum, V, d, ldg, nb);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+
+    const int mv_blocks = (ldg + MV_ROWS * MV_WARPS - 1) / (MV_ROWS * MV_WARPS);
+    std::vector<double> h_stats(2 * (size_t)nj);
+    int iters = 0;
+    double worst = 0.0;
+    constexpr int CHECK_EVERY = 4;
+    while (iters < max_iters) {
+        for (int i = 0; i < CHECK_EVERY && iters < max_iters; ++i, ++iters) {
+            pca_matvec_kernel<<<mv_blocks, MV_WARPS * 32, 0, st>>>(G, V, W, ldg, nb);
+            pca_update_kernel<<<nj, 256, 0, st>>>(V, W, stats, ldg, 1);
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(h_stats.data(), stats, h_stats.size() * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+        worst = 0.0;
+        for (int j = 0; j < nj; ++j) worst = std::max(worst, h_stats[2 * j + 1]);
+        if (worst <= tol * tol) break;
+    }
+    // Rayleigh quotient of the final vectors, then the explained variances
+    pca_matvec_kernel<<<mv_blocks, MV_WARPS * 32, 0, st>>>(G, V, W, ldg, nb);
+    pca_update_kernel<<<nj, 256, 0, st>>>(V, W, stats, ldg, 0);
+    pca_finish_kernel<<<nj, 256, 0, st>>>(V, stats, colsum, pp, ldg, d_explained, d_sigma2, d_component);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    if (h_iters) *h_iters = iters;
+    if (h_residual) *h_residual = std::sqrt(worst);
+    return cudaSuccess;
+}
+
+}  // namespace worm

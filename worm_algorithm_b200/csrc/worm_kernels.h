@@ -56,4 +56,14 @@ cudaError_t launch_block(int W, int64_t n, const int32_t *d_in, int32_t *d_out, 
                          cudaStream_t st);
 cudaError_t launch_count(int W, int64_t n, const int32_t *d_img, int64_t *d_count, cudaStream_t st);
 
+// leading principal component + delete-one-block jackknife (pca.cu)
+constexpr int PCA_MAX_BLOCKS = 64;
+size_t pca_workspace_bytes(int d, int64_t n, int nb, bool with_iteration);
+int pca_ldg(int d);   // leading dimension of the Gram matrices: d rounded up to a multiple of 4
+cudaError_t launch_pca_gram(int d, int64_t n, const int32_t *d_img, int nb, float *d_gram, void *d_ws, int sm_count,
+                            cudaStream_t st, const char **why);
+cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_iters, double tol, double *d_explained,
+                       double *d_sigma2, double *d_component, int *h_iters, double *h_residual, void *d_ws, int sm_count,
+                       cudaStream_t st, const char **why);
+
 }  // namespace worm

@@ -214,3 +214,57 @@ def count(images: torch.Tensor) -> torch.Tensor:
         out = torch.empty((n,), dtype=torch.int64, device=dev)
         check(lib().worm_count(W, n, _ptr(a), _ptr(out), _stream_ptr(dev)))
     return out.reshape(lead) if len(lead) else out.reshape(())
+
+
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class PcaResult:
+    """Leading principal component of an image stack (device tensors) -- pca.py:97-147."""
+    explained: torch.Tensor     # f64 [1 + num_blocks]: full set, then each delete-one-block set
+    sigma2: torch.Tensor        # f64 [1 + num_blocks]: leading eigenvalue of X^T X
+    component: torch.Tensor     # f64 [d]: components_[0] of the full set
+    iters: int
+    residual: float
+
+
+def _flat_images(images: torch.Tensor):
+    a = images.contiguous()
+    if a.dtype != torch.int32:
+        raise TypeError("images must be int32")
+    if a.dim() < 2:
+        raise ValueError("images must be [n, d] or [n, W, W]")
+    n = a.shape[0]
+    return a.reshape(n, -1), n, int(np.prod(a.shape[1:]))
+
+
+def pca(images: torch.Tensor, num_blocks: int = 10, max_iters: int = 2000, tol: float = 1e-11) -> PcaResult:
+    """explained_variance_[0] of TruncatedSVD(1) on the un-centred [n, d] matrix, for the full set and
+    for the `num_blocks` KFold training sets (block_resampling, utils.py:90-104)."""
+    dev = _dev(images.device)
+    a, n, d = _flat_images(images)
+    nb = int(num_blocks)
+    with torch.cuda.device(dev):
+        wsb = lib().worm_pca_workspace_bytes(d, n, nb, 0)
+        ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=dev)
+        ev = torch.empty((nb + 1,), dtype=torch.float64, device=dev)
+        s2 = torch.empty((nb + 1,), dtype=torch.float64, device=dev)
+        comp = torch.empty((d,), dtype=torch.float64, device=dev)
+        it, res = C.c_int32(0), C.c_double(0.0)
+        check(lib().worm_pca(d, n, _ptr(a), nb, int(max_iters), float(tol), _ptr(ev), _ptr(s2), _ptr(comp),
+                             C.byref(it), C.byref(res), _ptr(ws), wsb, _stream_ptr(dev)))
+    return PcaResult(ev, s2, comp, it.value, res.value)
+
+
+def pca_gram(images: torch.Tensor, num_blocks: int = 1) -> torch.Tensor:
+    """The tensor-core stage of `pca` alone: f32 [num_blocks, d, d], G_b = X_b^T X_b, exact integers."""
+    dev = _dev(images.device)
+    a, n, d = _flat_images(images)
+    nb = int(num_blocks)
+    ldg = (d + 3) & ~3
+    with torch.cuda.device(dev):
+        wsb = lib().worm_pca_workspace_bytes(d, n, nb, 1)
+        ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=dev)
+        g = torch.empty((nb, ldg, ldg), dtype=torch.float32, device=dev)
+        check(lib().worm_pca_gram(d, n, _ptr(a), nb, _ptr(g), _ptr(ws), wsb, _stream_ptr(dev)))
+        torch.cuda.current_stream(dev).synchronize()     # the workspace must outlive the kernels
+    return g[:, :d, :d]
