@@ -174,8 +174,13 @@ int worm_count(int W, int64_t n, const int32_t *d_img, int64_t *d_count, void *s
  * worm_pca_gram is the tensor-core stage alone: d_gram f32 [num_blocks][ldg][ldg], ldg = (d + 3) & ~3,
  * G_b = X_b^T X_b (exact integers), rows / columns >= d zero.  Workspace: worm_pca_workspace_bytes
  * with gram_only = 1.
+ * worm_pca_timing(1) makes the following worm_pca / worm_pca_gram calls record CUDA events around
+ * their stages (and worm_pca_gram synchronise); worm_pca_last_timing returns, for the calling thread's
+ * last call, milliseconds of {pack, host gate, Gram kernel, iteration stage} (4 values).
  * ------------------------------------------------------------------------------------------- */
 size_t worm_pca_workspace_bytes(int d, int64_t n, int num_blocks, int gram_only);
+void worm_pca_timing(int enable);
+void worm_pca_last_timing(double *ms4);
 int worm_pca(int d, int64_t n, const int32_t *d_images, int num_blocks, int max_iters, double tol,
              double *d_explained, double *d_sigma2, double *d_component, int32_t *h_iters,
              double *h_residual, void *d_workspace, size_t workspace_bytes, void *stream);

@@ -51,6 +51,8 @@ SIGNATURES = {
     "worm_block_host": (C.c_int, [C.c_int, _i64, _vp, _vp, C.c_int, C.c_int]),
     "worm_count_host": (C.c_int, [C.c_int, _i64, _vp, _vp]),
     "worm_pca_workspace_bytes": (_sz, [C.c_int, _i64, C.c_int, C.c_int]),
+    "worm_pca_timing": (None, [C.c_int]),
+    "worm_pca_last_timing": (None, [_pd]),
     "worm_pca": (C.c_int, [C.c_int, _i64, _vp, C.c_int, C.c_int, _dbl, _vp, _vp, _vp,
                            C.POINTER(C.c_int32), _pd, _vp, _sz, _vp]),
     "worm_pca_gram": (C.c_int, [C.c_int, _i64, _vp, C.c_int, _vp, _vp, _sz, _vp]),

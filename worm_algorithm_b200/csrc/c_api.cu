@@ -313,6 +313,16 @@ size_t worm_pca_workspace_bytes(int d, int64_t n, int num_blocks, int gram_only)
     return worm::pca_workspace_bytes(d, n, num_blocks, !gram_only);
 }
 
+void worm_pca_timing(int enable) { worm::pca_timing(enable); }
+
+void worm_pca_last_timing(double *ms4)
+{
+    double ms[worm::PCA_TIMING_SLOTS];
+    worm::pca_last_timing(ms);
+    if (ms4)
+        for (int i = 0; i < 4; ++i) ms4[i] = ms[i];
+}
+
 int worm_pca_gram(int d, int64_t n, const int32_t *d_images, int num_blocks, float *d_gram,
                   void *d_workspace, size_t workspace_bytes, void *stream)
 {

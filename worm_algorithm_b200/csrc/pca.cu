@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <mutex>
 #include <vector>
@@ -346,7 +347,14 @@ __global__ void __launch_bounds__(256) gram_sum_kernel(const float4 *__restrict_
 // ---------------------------------------------------------------------------------------------------
 // 4. power iteration on the nj = 1 + nb problems A_0 = G_full, A_j = G_full - G_{j-1}
 // ---------------------------------------------------------------------------------------------------
-constexpr int MV_ROWS = 2, MV_JC = 6, MV_WARPS = 8;
+constexpr int MV_ROWS = 2, MV_JC = 12, MV_WARPS = 8, MV_BATCH = 8;
+
+// iteration state shared by the kernels of one worm_pca call
+struct IterState {
+    int done;             // set once every problem has converged; later launches return at once
+    int iters;            // iterations actually executed
+    int cnt[MV_BATCH];    // cnt[i]: problems whose |dv|^2 <= tol^2 at iteration i of the current batch
+};
 
 __device__ __forceinline__ double warp_sum(double x)
 {
@@ -354,65 +362,122 @@ __device__ __forceinline__ double warp_sum(double x)
     return x;
 }
 
-// W_j = A_j V_j.  One warp per MV_ROWS rows; the matrices are exact integers in fp32, the vectors and
-// all accumulation fp64.  G: [nb + 1][ldg][ldg] with the full matrix at index nb.  V, W: [nj][ldg].
-__global__ void __launch_bounds__(MV_WARPS * 32) pca_matvec_kernel(const float *__restrict__ G, const double *__restrict__ V,
-                                                                    double *__restrict__ W, int ldg, int nb)
+__device__ __forceinline__ bool iter_finished(const IterState *s, int slot, int nj)
 {
+    return s->done || (slot > 0 && s->cnt[slot - 1] == nj);
+}
+
+__device__ __forceinline__ double dot4(const float4 g, const double2 va, const double2 vb)
+{
+    return (double)g.x * va.x + (double)g.y * va.y + (double)g.z * vb.x + (double)g.w * vb.y;
+}
+
+// One iteration's matrix-vector products, two kernels.  pca_matvec_block_kernel, blockIdx.y = b:
+// WB_{b+1} = G_b V_{b+1}, the deleted block's own part;  pca_matvec_full_kernel: WA_j = G_full V_j for all nj
+// problems (A_j V_j = WA_j - WB_j).  One warp per MV_ROWS rows, several independent 16-byte loads in flight
+// per lane; the matrices are exact integers in fp32, the vectors and all accumulation fp64.
+// G: [nb + 1][ldg][ldg] (full matrix last), V / WA / WB: [nj][ldg].
+__global__ void __launch_bounds__(MV_WARPS * 32, 4) pca_matvec_block_kernel(const float *__restrict__ G, const double *__restrict__ V,
+                                                                             double *__restrict__ WB, int ldg, int nb,
+                                                                             const IterState *state, int slot)
+{
+    if (iter_finished(state, slot, nb + 1)) return;
     const int lane = threadIdx.x & 31;
     const int r0 = (blockIdx.x * MV_WARPS + (threadIdx.x >> 5)) * MV_ROWS;
     if (r0 >= ldg) return;
-    const int nj = nb + 1;
-    const size_t mat = (size_t)ldg * ldg;
-    const float *full = G + (size_t)nb * mat;
-    int rr[MV_ROWS];
+    const int m = blockIdx.y;
+    const float *M = G + (size_t)m * ldg * ldg;
+    const float *row[MV_ROWS];
 #pragma unroll
-    for (int r = 0; r < MV_ROWS; ++r) rr[r] = min(r0 + r, ldg - 1);
+    for (int r = 0; r < MV_ROWS; ++r) row[r] = M + (size_t)min(r0 + r, ldg - 1) * ldg;
+    {
+        constexpr int U = 4;
+        const double *v = V + (size_t)(m + 1) * ldg;
+        double acc[MV_ROWS];
+#pragma unroll
+        for (int r = 0; r < MV_ROWS; ++r) acc[r] = 0.0;
+        for (int c = lane * 4; c < ldg; c += 128 * U) {
+            float4 g[U][MV_ROWS];
+            double2 va[U], vb[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int cc = c + 128 * u;
+                const bool ok = cc < ldg;
+                const int cl = ok ? cc : 0;
+#pragma unroll
+                for (int r = 0; r < MV_ROWS; ++r)
+                    g[u][r] = ok ? __ldcs(reinterpret_cast<const float4 *>(row[r] + cl)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                va[u] = *reinterpret_cast<const double2 *>(v + cl);
+                vb[u] = *reinterpret_cast<const double2 *>(v + cl + 2);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int r = 0; r < MV_ROWS; ++r) acc[r] += dot4(g[u][r], va[u], vb[u]);
+        }
+#pragma unroll
+        for (int r = 0; r < MV_ROWS; ++r) {
+            const double sum = warp_sum(acc[r]);
+            if (lane == 0 && r0 + r < ldg) WB[(size_t)(m + 1) * ldg + r0 + r] = sum;
+        }
+    }
+}
 
+__global__ void __launch_bounds__(MV_WARPS * 32, 2) pca_matvec_full_kernel(const float *__restrict__ G, const double *__restrict__ V,
+                                                                            double *__restrict__ WA, int ldg, int nb,
+                                                                            const IterState *state, int slot)
+{
+    const int nj = nb + 1;
+    if (iter_finished(state, slot, nj)) return;
+    const int lane = threadIdx.x & 31;
+    const int r0 = (blockIdx.x * MV_WARPS + (threadIdx.x >> 5)) * MV_ROWS;
+    if (r0 >= ldg) return;
+    const float *M = G + (size_t)nb * ldg * ldg;
+    const float *row[MV_ROWS];
+#pragma unroll
+    for (int r = 0; r < MV_ROWS; ++r) row[r] = M + (size_t)min(r0 + r, ldg - 1) * ldg;
+
+    constexpr int U = 2;
     for (int j0 = 0; j0 < nj; j0 += MV_JC) {
         double acc[MV_ROWS][MV_JC];
 #pragma unroll
         for (int r = 0; r < MV_ROWS; ++r)
 #pragma unroll
             for (int j = 0; j < MV_JC; ++j) acc[r][j] = 0.0;
-        for (int c = lane * 4; c < ldg; c += 128) {
-            float4 g[MV_ROWS];
+        for (int c = lane * 4; c < ldg; c += 128 * U) {
+            float4 g[U][MV_ROWS];
+            int cl[U];
 #pragma unroll
-            for (int r = 0; r < MV_ROWS; ++r) g[r] = *reinterpret_cast<const float4 *>(full + (size_t)rr[r] * ldg + c);
+            for (int u = 0; u < U; ++u) {
+                const int cc = c + 128 * u;
+                const bool ok = cc < ldg;
+                cl[u] = ok ? cc : 0;
+#pragma unroll
+                for (int r = 0; r < MV_ROWS; ++r)
+                    g[u][r] = ok ? __ldcs(reinterpret_cast<const float4 *>(row[r] + cl[u])) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
             for (int j = 0; j < MV_JC; ++j) {
                 if (j0 + j < nj) {
-                    const double2 va = *reinterpret_cast<const double2 *>(V + (size_t)(j0 + j) * ldg + c);
-                    const double2 vb = *reinterpret_cast<const double2 *>(V + (size_t)(j0 + j) * ldg + c + 2);
+                    const double *v = V + (size_t)(j0 + j) * ldg;
 #pragma unroll
-                    for (int r = 0; r < MV_ROWS; ++r)
-                        acc[r][j] += (double)g[r].x * va.x + (double)g[r].y * va.y + (double)g[r].z * vb.x + (double)g[r].w * vb.y;
+                    for (int u = 0; u < U; ++u) {
+                        const double2 va = *reinterpret_cast<const double2 *>(v + cl[u]);
+                        const double2 vb = *reinterpret_cast<const double2 *>(v + cl[u] + 2);
+#pragma unroll
+                        for (int r = 0; r < MV_ROWS; ++r) acc[r][j] += dot4(g[u][r], va, vb);
+                    }
                 }
             }
         }
 #pragma unroll
         for (int j = 0; j < MV_JC; ++j) {
-            if (j0 + j >= nj) break;
-            const int jj = j0 + j;
-            double sub[MV_ROWS];
+            if (j0 + j < nj) {
 #pragma unroll
-            for (int r = 0; r < MV_ROWS; ++r) sub[r] = 0.0;
-            if (jj > 0) {   // the deleted block's own contribution
-                const float *Gb = G + (size_t)(jj - 1) * mat;
-                for (int c = lane * 4; c < ldg; c += 128) {
-                    const double2 va = *reinterpret_cast<const double2 *>(V + (size_t)jj * ldg + c);
-                    const double2 vb = *reinterpret_cast<const double2 *>(V + (size_t)jj * ldg + c + 2);
-#pragma unroll
-                    for (int r = 0; r < MV_ROWS; ++r) {
-                        const float4 g = *reinterpret_cast<const float4 *>(Gb + (size_t)rr[r] * ldg + c);
-                        sub[r] += (double)g.x * va.x + (double)g.y * va.y + (double)g.z * vb.x + (double)g.w * vb.y;
-                    }
+                for (int r = 0; r < MV_ROWS; ++r) {
+                    const double sum = warp_sum(acc[r][j]);
+                    if (lane == 0 && r0 + r < ldg) WA[(size_t)(j0 + j) * ldg + r0 + r] = sum;
                 }
-            }
-#pragma unroll
-            for (int r = 0; r < MV_ROWS; ++r) {
-                const double s = warp_sum(acc[r][j] - sub[r]);
-                if (lane == 0 && r0 + r < ldg) W[(size_t)jj * ldg + r0 + r] = s;
             }
         }
     }
@@ -464,26 +529,32 @@ __global__ void __launch_bounds__(256) pca_init_kernel(const long long *__restri
     for (int c = threadIdx.x; c < ldg; c += blockDim.x) v[c] = v[c] / n2;
 }
 
-// stats[j] = { Rayleigh quotient V.W (|V| = 1), |V_new - V|^2 };  V <- W / |W| when normalise != 0.
-__global__ void __launch_bounds__(256) pca_update_kernel(double *__restrict__ V, const double *__restrict__ W, double *__restrict__ stats,
-                                                         int ldg, int normalise)
+// W_j = WA_j - WB_j;  stats[j] = { Rayleigh quotient V.W (|V| = 1), |V_new - V|^2 };  V <- W / |W|.
+__global__ void __launch_bounds__(256) pca_update_kernel(double *__restrict__ V, const double *__restrict__ WA,
+                                                         const double *__restrict__ WB, double *__restrict__ stats, int ldg,
+                                                         int nj, double tol2, IterState *state, int slot)
 {
     __shared__ double scratch[8];
+    if (iter_finished(state, slot, nj)) {
+        if (threadIdx.x == 0) state->done = 1;
+        return;
+    }
     const int j = blockIdx.x;
     double *v = V + (size_t)j * ldg;
-    const double *w = W + (size_t)j * ldg;
+    const double *wa = WA + (size_t)j * ldg, *wb = WB + (size_t)j * ldg;
     double vw = 0.0, ww = 0.0;
     for (int c = threadIdx.x; c < ldg; c += blockDim.x) {
-        vw += v[c] * w[c];
-        ww += w[c] * w[c];
+        const double w = j ? wa[c] - wb[c] : wa[c];
+        vw += v[c] * w;
+        ww += w * w;
     }
     vw = block_sum(vw, scratch);
     ww = block_sum(ww, scratch);
     double diff = 0.0;
-    if (normalise && ww > 0.0) {
+    if (ww > 0.0) {
         const double inv = 1.0 / sqrt(ww);
         for (int c = threadIdx.x; c < ldg; c += blockDim.x) {
-            const double x = w[c] * inv, dx = x - v[c];
+            const double x = (j ? wa[c] - wb[c] : wa[c]) * inv, dx = x - v[c];
             diff += dx * dx;
             v[c] = x;
         }
@@ -492,6 +563,8 @@ __global__ void __launch_bounds__(256) pca_update_kernel(double *__restrict__ V,
     if (threadIdx.x == 0) {
         stats[2 * j] = vw;
         stats[2 * j + 1] = diff;
+        if (diff <= tol2) atomicAdd(&state->cnt[slot], 1);
+        if (j == 0) state->iters += 1;
     }
 }
 
@@ -516,8 +589,8 @@ __global__ void __launch_bounds__(256) pca_finish_kernel(const double *__restric
     vs = block_sum(vs, scratch);
     const double n = (double)(p.cfg0[p.nb] - (j > 0 ? p.cfg0[j] - p.cfg0[j - 1] : 0));
     if (threadIdx.x == 0) {
-        const double m = sv / n;
-        explained[j] = stats[2 * j] / n - m * m;
+        const double m = n > 0.0 ? sv / n : 0.0;
+        explained[j] = n > 0.0 ? stats[2 * j] / n - m * m : 0.0;   // num_blocks = 1: the delete-one set is empty
         if (sigma2) sigma2[j] = stats[2 * j];
     }
     if (j == 0 && component) {   // sign convention: the component sums to a positive number
@@ -549,6 +622,40 @@ EncodeTiledFn encode_tiled()
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Optional stage timing (worm_pca_timing): CUDA events on the caller's stream around each stage.
+std::atomic<int> g_timing{0};
+thread_local double g_ms[PCA_TIMING_SLOTS] = {0, 0, 0, 0, 0};
+
+struct StageTimer {
+    cudaStream_t st;
+    bool on;
+    cudaEvent_t ev[PCA_TIMING_SLOTS + 1];
+    int n = 0;
+    explicit StageTimer(cudaStream_t s) : st(s), on(g_timing.load() != 0)
+    {
+        if (on)
+            for (auto &e : ev) cudaEventCreate(&e);
+    }
+    void mark()
+    {
+        if (on && n <= PCA_TIMING_SLOTS) cudaEventRecord(ev[n++], st);
+    }
+    void finish()   // after a stream synchronise
+    {
+        if (!on) return;
+        for (int i = 0; i < PCA_TIMING_SLOTS; ++i) {
+            float ms = 0.f;
+            if (i + 1 < n) cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            g_ms[i] = ms;
+        }
+    }
+    ~StageTimer()
+    {
+        if (on)
+            for (auto &e : ev) cudaEventDestroy(e);
+    }
+};
+
 void make_pack_plan(int d, int64_t n, int nb, PackPlan &p)
 {
     p.d = d;
@@ -568,7 +675,7 @@ void make_pack_plan(int d, int64_t n, int nb, PackPlan &p)
 }
 
 struct Layout {
-    size_t xt, colsum, maxabs, gram, v, w, stats, total;
+    size_t xt, colsum, maxabs, gram, v, w, wb, stats, state, total;
     int ldg;
 };
 
@@ -585,18 +692,21 @@ Layout make_layout(int d, const PackPlan &p, bool with_iteration)
         off = align_up(off + (size_t)(p.nb + 1) * l.ldg * l.ldg * 4, 256);
         l.v = off;      off = align_up(off + (size_t)(p.nb + 1) * l.ldg * 8, 256);
         l.w = off;      off = align_up(off + (size_t)(p.nb + 1) * l.ldg * 8, 256);
+        l.wb = off;     off = align_up(off + (size_t)(p.nb + 1) * l.ldg * 8, 256);
         l.stats = off;  off = align_up(off + (size_t)(p.nb + 1) * 16, 256);
+        l.state = off;  off = align_up(off + sizeof(IterState), 256);
     } else {
-        l.v = l.w = l.stats = off;
+        l.v = l.w = l.wb = l.stats = l.state = off;
     }
     l.total = off;
     return l;
 }
 
 cudaError_t run_pack_and_gram(int d, int64_t n, const int32_t *d_img, const PackPlan &pp, const Layout &lay, uint8_t *ws,
-                              float *d_gram, int sm_count, cudaStream_t st, const char **why)
+                              float *d_gram, int sm_count, cudaStream_t st, const char **why, StageTimer &tm)
 {
     cudaError_t e;
+    tm.mark();
     auto *xt = reinterpret_cast<__nv_bfloat16 *>(ws + lay.xt);
     auto *colsum = reinterpret_cast<long long *>(ws + lay.colsum);
     int *maxabs = reinterpret_cast<int *>(ws + lay.maxabs);
@@ -606,6 +716,7 @@ cudaError_t run_pack_and_gram(int d, int64_t n, const int32_t *d_img, const Pack
         pca_pack_kernel<<<grid, 256, 0, st>>>(d_img, xt, colsum, maxabs, pp);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
+    tm.mark();
     // exactness gate: every partial sum of products must stay below 2^24 (fp32 integers) and every value
     // must be a bf16 integer (|v| <= 256)
     int h_max = 0;
@@ -649,7 +760,9 @@ cudaError_t run_pack_and_gram(int d, int64_t n, const int32_t *d_img, const Pack
     });
     if (attr_err != cudaSuccess) return attr_err;
     const int total = gp.nb * gp.tiles_per_block;
+    tm.mark();
     gram_kernel<<<std::min(total, sm_count), GRAM_THREADS, GRAM_SMEM, st>>>(tmap, gp);
+    tm.mark();
     return cudaGetLastError();
 }
 
@@ -670,7 +783,20 @@ cudaError_t launch_pca_gram(int d, int64_t n, const int32_t *d_img, int nb, floa
     PackPlan pp;
     make_pack_plan(d, n, nb, pp);
     const Layout lay = make_layout(d, pp, false);
-    return run_pack_and_gram(d, n, d_img, pp, lay, static_cast<uint8_t *>(d_ws), d_gram, sm_count, st, why);
+    StageTimer tm(st);
+    cudaError_t e = run_pack_and_gram(d, n, d_img, pp, lay, static_cast<uint8_t *>(d_ws), d_gram, sm_count, st, why, tm);
+    if (e == cudaSuccess && tm.on) {
+        e = cudaStreamSynchronize(st);
+        tm.finish();
+    }
+    return e;
+}
+
+void pca_timing(int enable) { g_timing.store(enable); }
+
+void pca_last_timing(double *ms)
+{
+    for (int i = 0; i < PCA_TIMING_SLOTS; ++i) ms[i] = g_ms[i];
 }
 
 cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_iters, double tol, double *d_explained,
@@ -682,7 +808,8 @@ cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_i
     const Layout lay = make_layout(d, pp, true);
     uint8_t *ws = static_cast<uint8_t *>(d_ws);
     float *G = reinterpret_cast<float *>(ws + lay.gram);
-    cudaError_t e = run_pack_and_gram(d, n, d_img, pp, lay, ws, G, sm_count, st, why);
+    StageTimer tm(st);
+    cudaError_t e = run_pack_and_gram(d, n, d_img, pp, lay, ws, G, sm_count, st, why, tm);
     if (e != cudaSuccess) return e;
     const int ldg = lay.ldg, nj = nb + 1;
     const size_t quads = (size_t)ldg * ldg / 4;
@@ -696,29 +823,42 @@ cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_i
     pca_init_kernel<<<nj, 256, 0, st>>>(colsum, V, d, ldg, nb);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
-    const int mv_blocks = (ldg + MV_ROWS * MV_WARPS - 1) / (MV_ROWS * MV_WARPS);
+    double *WB = reinterpret_cast<double *>(ws + lay.wb);
+    IterState *state = reinterpret_cast<IterState *>(ws + lay.state);
+    if ((e = cudaMemsetAsync(state, 0, sizeof(IterState), st)) != cudaSuccess) return e;
+    const unsigned mv_rows = (unsigned)((ldg + MV_ROWS * MV_WARPS - 1) / (MV_ROWS * MV_WARPS));
     std::vector<double> h_stats(2 * (size_t)nj);
+    IterState h_state{};
     int iters = 0;
     double worst = 0.0;
-    constexpr int CHECK_EVERY = 4;
+    // Batches of MV_BATCH iterations are queued without host round trips; once every problem has
+    // converged (device-side count) the remaining launches of the batch return immediately.
     while (iters < max_iters) {
-        for (int i = 0; i < CHECK_EVERY && iters < max_iters; ++i, ++iters) {
-            pca_matvec_kernel<<<mv_blocks, MV_WARPS * 32, 0, st>>>(G, V, W, ldg, nb);
-            pca_update_kernel<<<nj, 256, 0, st>>>(V, W, stats, ldg, 1);
+        const int batch = std::min(MV_BATCH, max_iters - iters);
+        if ((e = cudaMemsetAsync(state->cnt, 0, sizeof(state->cnt), st)) != cudaSuccess) return e;
+        for (int i = 0; i < batch; ++i) {
+            pca_matvec_block_kernel<<<dim3(mv_rows, (unsigned)nb), MV_WARPS * 32, 0, st>>>(G, V, WB, ldg, nb, state, i);
+            pca_matvec_full_kernel<<<mv_rows, MV_WARPS * 32, 0, st>>>(G, V, W, ldg, nb, state, i);
+            pca_update_kernel<<<nj, 256, 0, st>>>(V, W, WB, stats, ldg, nj, tol * tol, state, i);
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if ((e = cudaMemcpyAsync(h_stats.data(), stats, h_stats.size() * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(&h_state, state, sizeof(IterState), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+        iters = h_state.iters;
         worst = 0.0;
         for (int j = 0; j < nj; ++j) worst = std::max(worst, h_stats[2 * j + 1]);
-        if (worst <= tol * tol) break;
+        bool conv = h_state.done != 0;
+        for (int i = 0; i < batch; ++i) conv = conv || h_state.cnt[i] == nj;
+        if (conv) break;
     }
-    // Rayleigh quotient of the final vectors, then the explained variances
-    pca_matvec_kernel<<<mv_blocks, MV_WARPS * 32, 0, st>>>(G, V, W, ldg, nb);
-    pca_update_kernel<<<nj, 256, 0, st>>>(V, W, stats, ldg, 0);
+    // stats[2j] is the Rayleigh quotient of the vector BEFORE the last normalisation; at convergence it
+    // differs from that of V by O(tol^2).
     pca_finish_kernel<<<nj, 256, 0, st>>>(V, stats, colsum, pp, ldg, d_explained, d_sigma2, d_component);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    tm.mark();
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    tm.finish();
     if (h_iters) *h_iters = iters;
     if (h_residual) *h_residual = std::sqrt(worst);
     return cudaSuccess;

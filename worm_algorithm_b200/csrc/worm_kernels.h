@@ -59,6 +59,11 @@ cudaError_t launch_count(int W, int64_t n, const int32_t *d_img, int64_t *d_coun
 // leading principal component + delete-one-block jackknife (pca.cu)
 constexpr int PCA_MAX_BLOCKS = 64;
 size_t pca_workspace_bytes(int d, int64_t n, int nb, bool with_iteration);
+// stage timing, off by default: slots = {pack, host exactness gate + tensor map, Gram kernel, sum + power
+// iteration + finish, unused}
+constexpr int PCA_TIMING_SLOTS = 5;
+void pca_timing(int enable);
+void pca_last_timing(double *ms);
 int pca_ldg(int d);   // leading dimension of the Gram matrices: d rounded up to a multiple of 4
 cudaError_t launch_pca_gram(int d, int64_t n, const int32_t *d_img, int nb, float *d_gram, void *d_ws, int sm_count,
                             cudaStream_t st, const char **why);
