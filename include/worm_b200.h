@@ -162,8 +162,9 @@ int worm_count(int W, int64_t n, const int32_t *d_img, int64_t *d_count, void *s
  * [n][d] matrix, i.e. the variance of the projection on the leading right singular vector;
  * utils.py:90-104 block_resampling = the num_blocks KFold training sets; utils.py:123-135).
  *
- * d_images      int32 [n][d], small integers (|v| <= 256 and max|v|^2 * ceil(n/num_blocks) < 2^24, so
- *               that the tensor-core Gram matrices are exact; anything else returns WORM_E_ARG)
+ * d_images      int32 [n][d], small integers (|v| <= 127 and max|v|^2 * n < 2^31: the tensor cores work
+ *               on int8 with int32 accumulators, so the Gram matrices are exact; anything else
+ *               returns WORM_E_ARG)
  * num_blocks    1 .. 64 (1 = no resampling); n >= num_blocks
  * d_explained   f64 [1 + num_blocks]: [0] the full data set, [1 + b] with block b deleted
  * d_sigma2      f64 [1 + num_blocks] or NULL: leading eigenvalue of X^T X (sigma_1^2) of each set
@@ -171,8 +172,8 @@ int worm_count(int W, int64_t n, const int32_t *d_img, int64_t *d_count, void *s
  * h_iters, h_residual   host outputs (may be NULL): power iterations used, last max_j |dv_j|
  * Synchronises the stream (convergence is checked on the host every few iterations).
  *
- * worm_pca_gram is the tensor-core stage alone: d_gram f32 [num_blocks][ldg][ldg], ldg = (d + 3) & ~3,
- * G_b = X_b^T X_b (exact integers), rows / columns >= d zero.  Workspace: worm_pca_workspace_bytes
+ * worm_pca_gram is the tensor-core stage alone: d_gram int32 [num_blocks][ldg][ldg], ldg = (d + 3) & ~3,
+ * G_b = X_b^T X_b, rows / columns >= d zero.  Workspace: worm_pca_workspace_bytes
  * with gram_only = 1.
  * worm_pca_timing(1) makes the following worm_pca / worm_pca_gram calls record CUDA events around
  * their stages (and worm_pca_gram synchronise); worm_pca_last_timing returns, for the calling thread's
@@ -184,7 +185,7 @@ void worm_pca_last_timing(double *ms4);
 int worm_pca(int d, int64_t n, const int32_t *d_images, int num_blocks, int max_iters, double tol,
              double *d_explained, double *d_sigma2, double *d_component, int32_t *h_iters,
              double *h_residual, void *d_workspace, size_t workspace_bytes, void *stream);
-int worm_pca_gram(int d, int64_t n, const int32_t *d_images, int num_blocks, float *d_gram,
+int worm_pca_gram(int d, int64_t n, const int32_t *d_images, int num_blocks, int32_t *d_gram,
                   void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------

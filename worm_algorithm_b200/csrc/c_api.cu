@@ -323,7 +323,7 @@ void worm_pca_last_timing(double *ms4)
         for (int i = 0; i < 4; ++i) ms4[i] = ms[i];
 }
 
-int worm_pca_gram(int d, int64_t n, const int32_t *d_images, int num_blocks, float *d_gram,
+int worm_pca_gram(int d, int64_t n, const int32_t *d_images, int num_blocks, int32_t *d_gram,
                   void *d_workspace, size_t workspace_bytes, void *stream)
 {
     if (int rc = pca_check(d, n, num_blocks)) return rc;

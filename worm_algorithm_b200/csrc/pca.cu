@@ -4,21 +4,19 @@
 // = KFold(num_blocks) training sets; utils.py:123-135 jackknife_err).
 //
 // Device pipeline (everything stays in HBM):
-//   1. pca_pack_kernel   int32 images [n, d] -> bf16 Xt [d, Ktot], pixel-major, each jackknife block in its
-//                        own zero-padded run of 64-wide k tiles; per-block column sums; max |value|.
+//   1. pca_pack_kernel   int32 images [n, d] -> int8 Xt [d, Ktot], pixel-major, each jackknife block in its
+//                        own zero-padded run of 128-wide k tiles; per-block column sums; max |value|.
 //   2. gram_kernel       per-block Gram matrices G_b = X_b^T X_b on the 5th-generation tensor cores
-//                        (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM; TMA 128B-swizzled operand
+//                        (tcgen05.mma kind::i8, s8 x s8 -> s32 in TMEM; TMA 128B-swizzled operand
 //                        tiles; only the lower triangle of 128x256 tiles is computed and mirrored on the
-//                        way out).  Pixel values are small integers, so every product and partial sum
-//                        is an integer below 2^24: the fp32 result is EXACT (checked on the host from
-//                        max|value| and the block length; larger inputs are refused, not rounded).
+//                        way out).  Integer in, integer out: the result is EXACT as long as it fits
+//                        int32 (checked on the host from max|value| and n; larger inputs are refused).
 //   3. gram_sum_kernel   G_full = sum_b G_b.
 //   4. power iteration   for the 1 + num_blocks problems at once (full data and each delete-one
-//                        set, A_j = G_full - G_{j-1}): fp64 matrix-vector products on the exact fp32
+//                        set, A_j = G_full - G_{j-1}): fp64 matrix-vector products on the exact int32
 //                        Gram matrices, HBM-bound.
 //   5. explained variance lambda_j / n_j - (s_j . v_j / n_j)^2.
 #include <cuda.h>   // CUtensorMap and its enums only; cuTensorMapEncodeTiled is fetched through the runtime
-#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -40,10 +38,10 @@ struct PackPlan {
     int d, nb;
     int64_t ktot;
     int cfg0[PCA_MAX_BLOCKS + 1];   // first configuration of jackknife block b (cfg0[nb] = n)
-    int kt0[PCA_MAX_BLOCKS + 1];    // first 64-wide k tile of block b in Xt (kt0[nb] = Ktot / 64)
+    int kt0[PCA_MAX_BLOCKS + 1];    // first 64-configuration group of block b in Xt (kt0[nb] = Ktot / 64); always even
 };
 
-__global__ void __launch_bounds__(256) pca_pack_kernel(const int32_t *__restrict__ img, __nv_bfloat16 *__restrict__ xt,
+__global__ void __launch_bounds__(256) pca_pack_kernel(const int32_t *__restrict__ img, int8_t *__restrict__ xt,
                                                        long long *__restrict__ colsum, int *__restrict__ maxabs,
                                                        const PackPlan p)
 {
@@ -68,15 +66,14 @@ __global__ void __launch_bounds__(256) pca_pack_kernel(const int32_t *__restrict
     if ((t & 31) == 0 && mx) atomicMax(maxabs, mx);
     __syncthreads();
     {
-        const int k2 = t & 31;
+        const int k4 = t & 15;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int cl = (t >> 5) + 8 * i, c = c0 + cl;
+        for (int i = 0; i < 4; ++i) {
+            const int cl = (t >> 4) + 16 * i, c = c0 + cl;
             if (c < p.d) {
-                __nv_bfloat162 w;
-                w.x = __int2bfloat16_rn(tile[2 * k2][cl]);
-                w.y = __int2bfloat16_rn(tile[2 * k2 + 1][cl]);
-                *reinterpret_cast<__nv_bfloat162 *>(xt + (size_t)c * p.ktot + (size_t)kt * 64 + 2 * k2) = w;
+                const uint32_t w = (uint32_t)(tile[4 * k4][cl] & 0xff) | ((uint32_t)(tile[4 * k4 + 1][cl] & 0xff) << 8) |
+                                   ((uint32_t)(tile[4 * k4 + 2][cl] & 0xff) << 16) | ((uint32_t)(tile[4 * k4 + 3][cl] & 0xff) << 24);
+                *reinterpret_cast<uint32_t *>(xt + (size_t)c * p.ktot + (size_t)kt * 64 + 4 * k4) = w;
             }
         }
     }
@@ -91,16 +88,16 @@ __global__ void __launch_bounds__(256) pca_pack_kernel(const int32_t *__restrict
 // ---------------------------------------------------------------------------------------------------
 // 2. Gram matrices on tcgen05
 // ---------------------------------------------------------------------------------------------------
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2, B_HALF_BYTES = 128 * BK * 2, STAGE_BYTES = A_BYTES + 2 * B_HALF_BYTES;
+constexpr int BM = 128, BN = 256, BK = 128, STAGES = 4;   // BK int8 elements = one 128-byte swizzle row
+constexpr int A_BYTES = BM * BK, B_HALF_BYTES = 128 * BK, STAGE_BYTES = A_BYTES + 2 * B_HALF_BYTES;
 constexpr int GRAM_THREADS = 256;
 constexpr int GRAM_SMEM = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 constexpr int TMEM_COLS = 512;   // two 256-column accumulators: the epilogue of tile i overlaps the MMAs of tile i+1
 
 struct GramPlan {
     int d, ldg, nb, tm_count, tiles_per_block;
-    int kt0[PCA_MAX_BLOCKS + 1];
-    float *G;   // [nb][ldg][ldg]
+    int kt0[PCA_MAX_BLOCKS + 1];   // first BK-wide k block of jackknife block b
+    int32_t *G;   // [nb][ldg][ldg]
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,12 +139,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
                  : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -164,10 +161,10 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr)
 {
     return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16 instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 128, N = n.
-__device__ __forceinline__ uint32_t idesc_bf16(int n)
+// kind::i8 instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t idesc_i8(int n)
 {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 struct Tile {
@@ -236,7 +233,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const __grid_cons
                 if (lane == 0) {
                     mbar_wait(empty(stage), phase ^ 1);
                     const uint32_t a = base + stage * STAGE_BYTES, bsm = a + A_BYTES;
-                    mbar_expect_tx(full(stage), A_BYTES + tl.ncols * BK * 2);
+                    mbar_expect_tx(full(stage), A_BYTES + tl.ncols * BK);
                     tma_load_2d(a, &tmap, full(stage), (k0 + kb) * BK, tl.tm * BM);
                     tma_load_2d(bsm, &tmap, full(stage), (k0 + kb) * BK, tl.tn * BN);
                     if (tl.ncols > 128) tma_load_2d(bsm + B_HALF_BYTES, &tmap, full(stage), (k0 + kb) * BK, tl.tn * BN + 128);
@@ -252,7 +249,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const __grid_cons
             const Tile tl = decode_tile(t, p);
             const int nk = p.kt0[tl.b + 1] - p.kt0[tl.b];
             const int as = it & 1, aphase = (it >> 1) & 1;
-            const uint32_t idesc = idesc_bf16(tl.ncols);
+            const uint32_t idesc = idesc_i8(tl.ncols);
             if (lane == 0) {
                 mbar_wait(tempty(as), aphase ^ 1);
                 tc_fence_after();
@@ -265,8 +262,8 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const __grid_cons
                     const uint32_t a = base + stage * STAGE_BYTES;
                     const uint64_t adesc = smem_desc_sw128(a), bdesc = smem_desc_sw128(a + A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16(tmem + as * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < BK / 32; ++k)   // one instruction consumes K = 32 bytes
+                        umma_i8(tmem + as * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                     umma_commit(empty(stage));
                     if (kb == nk - 1) umma_commit(tfull(as));
                 }
@@ -283,7 +280,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const __grid_cons
             const int as = it & 1, aphase = (it >> 1) & 1;
             mbar_wait(tfull(as), aphase);
             tc_fence_after();
-            float *Gb = p.G + (size_t)tl.b * p.ldg * p.ldg;
+            int32_t *Gb = p.G + (size_t)tl.b * p.ldg * p.ldg;
             const int row = tl.tm * BM + 32 * w + lane;
             for (int c0 = 0; c0 < tl.ncols; c0 += 32) {
                 uint32_t v[32];
@@ -301,18 +298,16 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const __grid_cons
                     : "memory");
                 const int col0 = tl.tn * BN + c0;
                 if (row < p.ldg) {
-                    float *dst = Gb + (size_t)row * p.ldg + col0;
+                    int32_t *dst = Gb + (size_t)row * p.ldg + col0;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
-                        if (col0 + j < p.ldg)
-                            *reinterpret_cast<float4 *>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        if (col0 + j < p.ldg) *reinterpret_cast<uint4 *>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
                 // columns inside the diagonal 128 x 128 block are already written symmetrically above
                 if (col0 < tl.tm * BM && row < p.ldg) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (col0 + j < p.ldg) Gb[(size_t)(col0 + j) * p.ldg + row] = __uint_as_float(v[j]);
+                        if (col0 + j < p.ldg) Gb[(size_t)(col0 + j) * p.ldg + row] = (int32_t)v[j];
                 }
             }
             tc_fence_before();
@@ -332,12 +327,12 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const __grid_cons
 // ---------------------------------------------------------------------------------------------------
 // 3. G_full = sum_b G_b
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gram_sum_kernel(const float4 *__restrict__ G, float4 *__restrict__ out, size_t quads, int nb)
+__global__ void __launch_bounds__(256) gram_sum_kernel(const int4 *__restrict__ G, int4 *__restrict__ out, size_t quads, int nb)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < quads; i += (size_t)gridDim.x * blockDim.x) {
-        float4 s = G[i];
+        int4 s = __ldcs(G + i);
         for (int b = 1; b < nb; ++b) {
-            const float4 g = G[(size_t)b * quads + i];
+            const int4 g = __ldcs(G + (size_t)b * quads + i);
             s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
         }
         out[i] = s;
@@ -367,112 +362,127 @@ __device__ __forceinline__ bool iter_finished(const IterState *s, int slot, int 
     return s->done || (slot > 0 && s->cnt[slot - 1] == nj);
 }
 
-__device__ __forceinline__ double dot4(const float4 g, const double2 va, const double2 vb)
+// int32 -> double through the mantissa of 2^52 (exact for |g| < 2^31): one fp64 add instead of a
+// conversion instruction.
+__device__ __forceinline__ double int_to_double(int g)
 {
-    return (double)g.x * va.x + (double)g.y * va.y + (double)g.z * vb.x + (double)g.w * vb.y;
+    return __hiloint2double(0x43300000, g ^ 0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
+}
+
+__device__ __forceinline__ double dot4(const int4 g, const double2 va, const double2 vb)
+{
+    return int_to_double(g.x) * va.x + int_to_double(g.y) * va.y + int_to_double(g.z) * vb.x + int_to_double(g.w) * vb.y;
 }
 
 // One iteration's matrix-vector products, two kernels.  pca_matvec_block_kernel, blockIdx.y = b:
 // WB_{b+1} = G_b V_{b+1}, the deleted block's own part;  pca_matvec_full_kernel: WA_j = G_full V_j for all nj
-// problems (A_j V_j = WA_j - WB_j).  One warp per MV_ROWS rows, several independent 16-byte loads in flight
-// per lane; the matrices are exact integers in fp32, the vectors and all accumulation fp64.
-// G: [nb + 1][ldg][ldg] (full matrix last), V / WA / WB: [nj][ldg].
-__global__ void __launch_bounds__(MV_WARPS * 32, 4) pca_matvec_block_kernel(const float *__restrict__ G, const double *__restrict__ V,
+// problems (A_j V_j = WA_j - WB_j).  One warp per MV_ROWS rows; the matrices are exact int32, the vectors and
+// all accumulation fp64.  G: [nb + 1][ldg][ldg] (full matrix last), V / WA / WB: [nj][ldg].
+template <int U>
+__device__ __forceinline__ void rows_times_vector(const int32_t *__restrict__ r0, const int32_t *__restrict__ r1,
+                                                  const double *__restrict__ v, int c, double &a0, double &a1)
+{
+    int4 g0[U], g1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        g0[u] = __ldcs(reinterpret_cast<const int4 *>(r0 + c + 128 * u));
+        g1[u] = __ldcs(reinterpret_cast<const int4 *>(r1 + c + 128 * u));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const double2 va = *reinterpret_cast<const double2 *>(v + c + 128 * u);
+        const double2 vb = *reinterpret_cast<const double2 *>(v + c + 128 * u + 2);
+        a0 += dot4(g0[u], va, vb);
+        a1 += dot4(g1[u], va, vb);
+    }
+}
+
+__global__ void __launch_bounds__(MV_WARPS * 32, 3) pca_matvec_block_kernel(const int32_t *__restrict__ G, const double *__restrict__ V,
                                                                              double *__restrict__ WB, int ldg, int nb,
                                                                              const IterState *state, int slot)
 {
+    static_assert(MV_ROWS == 2, "two rows per warp");
     if (iter_finished(state, slot, nb + 1)) return;
     const int lane = threadIdx.x & 31;
     const int r0 = (blockIdx.x * MV_WARPS + (threadIdx.x >> 5)) * MV_ROWS;
     if (r0 >= ldg) return;
     const int m = blockIdx.y;
-    const float *M = G + (size_t)m * ldg * ldg;
-    const float *row[MV_ROWS];
-#pragma unroll
-    for (int r = 0; r < MV_ROWS; ++r) row[r] = M + (size_t)min(r0 + r, ldg - 1) * ldg;
-    {
-        constexpr int U = 4;
-        const double *v = V + (size_t)(m + 1) * ldg;
-        double acc[MV_ROWS];
-#pragma unroll
-        for (int r = 0; r < MV_ROWS; ++r) acc[r] = 0.0;
-        for (int c = lane * 4; c < ldg; c += 128 * U) {
-            float4 g[U][MV_ROWS];
-            double2 va[U], vb[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int cc = c + 128 * u;
-                const bool ok = cc < ldg;
-                const int cl = ok ? cc : 0;
-#pragma unroll
-                for (int r = 0; r < MV_ROWS; ++r)
-                    g[u][r] = ok ? __ldcs(reinterpret_cast<const float4 *>(row[r] + cl)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                va[u] = *reinterpret_cast<const double2 *>(v + cl);
-                vb[u] = *reinterpret_cast<const double2 *>(v + cl + 2);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int r = 0; r < MV_ROWS; ++r) acc[r] += dot4(g[u][r], va[u], vb[u]);
-        }
-#pragma unroll
-        for (int r = 0; r < MV_ROWS; ++r) {
-            const double sum = warp_sum(acc[r]);
-            if (lane == 0 && r0 + r < ldg) WB[(size_t)(m + 1) * ldg + r0 + r] = sum;
-        }
+    const int32_t *M = G + (size_t)m * ldg * ldg;
+    const int32_t *row0 = M + (size_t)r0 * ldg, *row1 = M + (size_t)min(r0 + 1, ldg - 1) * ldg;
+    const double *v = V + (size_t)(m + 1) * ldg;
+    constexpr int U = 4;
+    double a0 = 0.0, a1 = 0.0;
+    int c = lane * 4;
+    for (; c + 128 * (U - 1) < ldg; c += 128 * U) rows_times_vector<U>(row0, row1, v, c, a0, a1);
+    for (; c < ldg; c += 128) rows_times_vector<1>(row0, row1, v, c, a0, a1);
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    if (lane == 0) {
+        WB[(size_t)(m + 1) * ldg + r0] = a0;
+        if (r0 + 1 < ldg) WB[(size_t)(m + 1) * ldg + r0 + 1] = a1;
     }
 }
 
-__global__ void __launch_bounds__(MV_WARPS * 32, 2) pca_matvec_full_kernel(const float *__restrict__ G, const double *__restrict__ V,
+// The full matrix meets all nj vectors: the vectors of one 256-column chunk are staged in shared memory
+// once per block (16 rows) instead of being fetched through L1 by every warp.
+constexpr int MV_CHUNK = 256;
+
+__global__ void __launch_bounds__(MV_WARPS * 32, 2) pca_matvec_full_kernel(const int32_t *__restrict__ G, const double *__restrict__ V,
                                                                             double *__restrict__ WA, int ldg, int nb,
                                                                             const IterState *state, int slot)
 {
+    __shared__ __align__(16) double vs[MV_JC][MV_CHUNK];
     const int nj = nb + 1;
     if (iter_finished(state, slot, nj)) return;
     const int lane = threadIdx.x & 31;
     const int r0 = (blockIdx.x * MV_WARPS + (threadIdx.x >> 5)) * MV_ROWS;
-    if (r0 >= ldg) return;
-    const float *M = G + (size_t)nb * ldg * ldg;
-    const float *row[MV_ROWS];
+    const int32_t *M = G + (size_t)nb * ldg * ldg;
+    const int32_t *row[MV_ROWS];
 #pragma unroll
     for (int r = 0; r < MV_ROWS; ++r) row[r] = M + (size_t)min(r0 + r, ldg - 1) * ldg;
 
-    constexpr int U = 2;
     for (int j0 = 0; j0 < nj; j0 += MV_JC) {
+        const int jn = min(MV_JC, nj - j0);
         double acc[MV_ROWS][MV_JC];
 #pragma unroll
         for (int r = 0; r < MV_ROWS; ++r)
 #pragma unroll
             for (int j = 0; j < MV_JC; ++j) acc[r][j] = 0.0;
-        for (int c = lane * 4; c < ldg; c += 128 * U) {
-            float4 g[U][MV_ROWS];
-            int cl[U];
+        for (int c0 = 0; c0 < ldg; c0 += MV_CHUNK) {
+            int4 g[2][MV_ROWS];
+            bool ok[2];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int cc = c + 128 * u;
-                const bool ok = cc < ldg;
-                cl[u] = ok ? cc : 0;
+            for (int h = 0; h < 2; ++h) {   // issue the matrix loads before waiting at the barrier
+                const int c = c0 + 128 * h + lane * 4;
+                ok[h] = c < ldg && r0 < ldg;
 #pragma unroll
                 for (int r = 0; r < MV_ROWS; ++r)
-                    g[u][r] = ok ? __ldcs(reinterpret_cast<const float4 *>(row[r] + cl[u])) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    g[h][r] = ok[h] ? __ldcs(reinterpret_cast<const int4 *>(row[r] + c)) : make_int4(0, 0, 0, 0);
             }
+            __syncthreads();
+            for (int i = threadIdx.x; i < jn * (MV_CHUNK / 2); i += MV_WARPS * 32) {
+                const int j = i / (MV_CHUNK / 2), cc = (i % (MV_CHUNK / 2)) * 2;
+                double2 x = make_double2(0.0, 0.0);
+                if (c0 + cc < ldg) x = *reinterpret_cast<const double2 *>(V + (size_t)(j0 + j) * ldg + c0 + cc);
+                *reinterpret_cast<double2 *>(&vs[j][cc]) = x;
+            }
+            __syncthreads();
 #pragma unroll
             for (int j = 0; j < MV_JC; ++j) {
-                if (j0 + j < nj) {
-                    const double *v = V + (size_t)(j0 + j) * ldg;
+                if (j < jn) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const double2 va = *reinterpret_cast<const double2 *>(v + cl[u]);
-                        const double2 vb = *reinterpret_cast<const double2 *>(v + cl[u] + 2);
+                    for (int h = 0; h < 2; ++h) {
+                        const double2 va = *reinterpret_cast<const double2 *>(&vs[j][128 * h + lane * 4]);
+                        const double2 vb = *reinterpret_cast<const double2 *>(&vs[j][128 * h + lane * 4 + 2]);
 #pragma unroll
-                        for (int r = 0; r < MV_ROWS; ++r) acc[r][j] += dot4(g[u][r], va, vb);
+                        for (int r = 0; r < MV_ROWS; ++r) acc[r][j] += dot4(g[h][r], va, vb);
                     }
                 }
             }
         }
 #pragma unroll
         for (int j = 0; j < MV_JC; ++j) {
-            if (j0 + j < nj) {
+            if (j < jn) {
 #pragma unroll
                 for (int r = 0; r < MV_ROWS; ++r) {
                     const double sum = warp_sum(acc[r][j]);
@@ -497,7 +507,17 @@ __device__ double block_sum(double x, double *scratch)
 
 // start vectors: the normalised column sums of the included configurations (for images, close to the
 // leading singular vector already) plus a small fixed pattern so that no start is exactly zero.
-__global__ void __launch_bounds__(256) pca_init_kernel(const long long *__restrict__ colsum, double *__restrict__ V, int d, int ldg, int nb)
+__global__ void __launch_bounds__(256) pca_coltot_kernel(const long long *__restrict__ colsum, long long *__restrict__ coltot, int d, int nb)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d) return;
+    long long s = 0;
+    for (int b = 0; b < nb; ++b) s += colsum[(size_t)b * d + c];
+    coltot[c] = s;
+}
+
+__global__ void __launch_bounds__(256) pca_init_kernel(const long long *__restrict__ colsum, const long long *__restrict__ coltot,
+                                                       double *__restrict__ V, int d, int ldg)
 {
     __shared__ double scratch[8];
     const int j = blockIdx.x;
@@ -505,12 +525,7 @@ __global__ void __launch_bounds__(256) pca_init_kernel(const long long *__restri
     double ss = 0.0;
     for (int c = threadIdx.x; c < ldg; c += blockDim.x) {
         double x = 0.0;
-        if (c < d) {
-            long long s = 0;
-            for (int b = 0; b < nb; ++b)
-                if (b != j - 1) s += colsum[(size_t)b * d + c];
-            x = (double)s;
-        }
+        if (c < d) x = (double)(coltot[c] - (j ? colsum[(size_t)(j - 1) * d + c] : 0ll));
         v[c] = x;
         ss += x * x;
     }
@@ -570,7 +585,8 @@ __global__ void __launch_bounds__(256) pca_update_kernel(double *__restrict__ V,
 
 // explained variance of the projection on v_j: mean((X v)^2) - mean(X v)^2 over the included configurations
 __global__ void __launch_bounds__(256) pca_finish_kernel(const double *__restrict__ V, const double *__restrict__ stats,
-                                                         const long long *__restrict__ colsum, const PackPlan p, int ldg,
+                                                         const long long *__restrict__ colsum, const long long *__restrict__ coltot,
+                                                         const PackPlan p, int ldg,
                                                          double *__restrict__ explained, double *__restrict__ sigma2,
                                                          double *__restrict__ component)
 {
@@ -579,9 +595,7 @@ __global__ void __launch_bounds__(256) pca_finish_kernel(const double *__restric
     const double *v = V + (size_t)j * ldg;
     double sv = 0.0, vs = 0.0;
     for (int c = threadIdx.x; c < p.d; c += blockDim.x) {
-        long long s = 0;
-        for (int b = 0; b < p.nb; ++b)
-            if (b != j - 1) s += colsum[(size_t)b * p.d + c];
+        const long long s = coltot[c] - (j ? colsum[(size_t)(j - 1) * p.d + c] : 0ll);
         sv += (double)s * v[c];
         vs += v[c];
     }
@@ -667,15 +681,15 @@ void make_pack_plan(int d, int64_t n, int nb, PackPlan &p)
         p.cfg0[b] = cfg;
         p.kt0[b] = kt;
         cfg += len;
-        kt += (len + BK - 1) / BK;
+        kt += 2 * ((len + BK - 1) / BK);   // 64-configuration groups, padded to whole BK = 128 k blocks
     }
     p.cfg0[nb] = cfg;
     p.kt0[nb] = kt;
-    p.ktot = (int64_t)kt * BK;
+    p.ktot = (int64_t)kt * 64;
 }
 
 struct Layout {
-    size_t xt, colsum, maxabs, gram, v, w, wb, stats, state, total;
+    size_t xt, colsum, maxabs, gram, v, w, wb, stats, state, coltot, total;
     int ldg;
 };
 
@@ -684,7 +698,7 @@ Layout make_layout(int d, const PackPlan &p, bool with_iteration)
     Layout l;
     l.ldg = (d + 3) & ~3;
     size_t off = 0;
-    l.xt = off;      off = align_up(off + (size_t)d * p.ktot * 2, 1024);
+    l.xt = off;      off = align_up(off + (size_t)d * p.ktot, 1024);
     l.colsum = off;  off = align_up(off + (size_t)p.nb * d * 8, 256);
     l.maxabs = off;  off = align_up(off + 256, 256);
     l.gram = off;
@@ -695,19 +709,20 @@ Layout make_layout(int d, const PackPlan &p, bool with_iteration)
         l.wb = off;     off = align_up(off + (size_t)(p.nb + 1) * l.ldg * 8, 256);
         l.stats = off;  off = align_up(off + (size_t)(p.nb + 1) * 16, 256);
         l.state = off;  off = align_up(off + sizeof(IterState), 256);
+        l.coltot = off; off = align_up(off + (size_t)d * 8, 256);
     } else {
-        l.v = l.w = l.wb = l.stats = l.state = off;
+        l.v = l.w = l.wb = l.stats = l.state = l.coltot = off;
     }
     l.total = off;
     return l;
 }
 
 cudaError_t run_pack_and_gram(int d, int64_t n, const int32_t *d_img, const PackPlan &pp, const Layout &lay, uint8_t *ws,
-                              float *d_gram, int sm_count, cudaStream_t st, const char **why, StageTimer &tm)
+                              int32_t *d_gram, int sm_count, cudaStream_t st, const char **why, StageTimer &tm)
 {
     cudaError_t e;
     tm.mark();
-    auto *xt = reinterpret_cast<__nv_bfloat16 *>(ws + lay.xt);
+    auto *xt = reinterpret_cast<int8_t *>(ws + lay.xt);
     auto *colsum = reinterpret_cast<long long *>(ws + lay.colsum);
     int *maxabs = reinterpret_cast<int *>(ws + lay.maxabs);
     if ((e = cudaMemsetAsync(ws + lay.colsum, 0, (lay.maxabs + 256) - lay.colsum, st)) != cudaSuccess) return e;
@@ -717,15 +732,12 @@ cudaError_t run_pack_and_gram(int d, int64_t n, const int32_t *d_img, const Pack
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     tm.mark();
-    // exactness gate: every partial sum of products must stay below 2^24 (fp32 integers) and every value
-    // must be a bf16 integer (|v| <= 256)
+    // exactness gate: every value must fit int8 and every entry of the full Gram matrix int32
     int h_max = 0;
     if ((e = cudaMemcpyAsync(&h_max, maxabs, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-    int64_t longest = 0;
-    for (int b = 0; b < pp.nb; ++b) longest = std::max<int64_t>(longest, pp.cfg0[b + 1] - pp.cfg0[b]);
-    if (h_max > 256 || (int64_t)h_max * h_max * longest >= (1ll << 24)) {
-        *why = "pixel values too large for an exact bf16 x bf16 -> fp32 Gram matrix (need max|v| <= 256 and max|v|^2 * block length < 2^24)";
+    if (h_max > 127 || (int64_t)h_max * h_max * n >= (1ll << 31)) {
+        *why = "pixel values too large for an exact s8 x s8 -> s32 Gram matrix (need max|v| <= 127 and max|v|^2 * n < 2^31)";
         return cudaErrorInvalidValue;
     }
 
@@ -736,10 +748,10 @@ cudaError_t run_pack_and_gram(int d, int64_t n, const int32_t *d_img, const Pack
     }
     CUtensorMap tmap;
     const cuuint64_t gdim[2] = {(cuuint64_t)pp.ktot, (cuuint64_t)d};
-    const cuuint64_t gstride[1] = {(cuuint64_t)pp.ktot * 2};
+    const cuuint64_t gstride[1] = {(cuuint64_t)pp.ktot};
     const cuuint32_t box[2] = {BK, 128};
     const cuuint32_t estr[2] = {1, 1};
-    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, xt, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, xt, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
         *why = "cuTensorMapEncodeTiled failed";
         return cudaErrorInvalidValue;
@@ -751,7 +763,7 @@ cudaError_t run_pack_and_gram(int d, int64_t n, const int32_t *d_img, const Pack
     gp.tm_count = (lay.ldg + BM - 1) / BM;
     gp.tiles_per_block = 0;
     for (int tm = 0; tm < gp.tm_count; ++tm) gp.tiles_per_block += tm / 2 + 1;
-    for (int b = 0; b <= pp.nb; ++b) gp.kt0[b] = pp.kt0[b];
+    for (int b = 0; b <= pp.nb; ++b) gp.kt0[b] = pp.kt0[b] / 2;
     gp.G = d_gram;
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
@@ -777,7 +789,7 @@ size_t pca_workspace_bytes(int d, int64_t n, int nb, bool with_iteration)
 
 int pca_ldg(int d) { return (d + 3) & ~3; }
 
-cudaError_t launch_pca_gram(int d, int64_t n, const int32_t *d_img, int nb, float *d_gram, void *d_ws, int sm_count,
+cudaError_t launch_pca_gram(int d, int64_t n, const int32_t *d_img, int nb, int32_t *d_gram, void *d_ws, int sm_count,
                             cudaStream_t st, const char **why)
 {
     PackPlan pp;
@@ -807,20 +819,22 @@ cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_i
     make_pack_plan(d, n, nb, pp);
     const Layout lay = make_layout(d, pp, true);
     uint8_t *ws = static_cast<uint8_t *>(d_ws);
-    float *G = reinterpret_cast<float *>(ws + lay.gram);
+    int32_t *G = reinterpret_cast<int32_t *>(ws + lay.gram);
     StageTimer tm(st);
     cudaError_t e = run_pack_and_gram(d, n, d_img, pp, lay, ws, G, sm_count, st, why, tm);
     if (e != cudaSuccess) return e;
     const int ldg = lay.ldg, nj = nb + 1;
     const size_t quads = (size_t)ldg * ldg / 4;
     gram_sum_kernel<<<(unsigned)std::min<size_t>((quads + 255) / 256, (size_t)sm_count * 8), 256, 0, st>>>(
-        reinterpret_cast<const float4 *>(G), reinterpret_cast<float4 *>(G + (size_t)nb * ldg * ldg), quads, nb);
+        reinterpret_cast<const int4 *>(G), reinterpret_cast<int4 *>(G + (size_t)nb * ldg * ldg), quads, nb);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
     auto *colsum = reinterpret_cast<const long long *>(ws + lay.colsum);
     double *V = reinterpret_cast<double *>(ws + lay.v), *W = reinterpret_cast<double *>(ws + lay.w);
     double *stats = reinterpret_cast<double *>(ws + lay.stats);
-    pca_init_kernel<<<nj, 256, 0, st>>>(colsum, V, d, ldg, nb);
+    long long *coltot = reinterpret_cast<long long *>(ws + lay.coltot);
+    pca_coltot_kernel<<<(d + 255) / 256, 256, 0, st>>>(colsum, coltot, d, nb);
+    pca_init_kernel<<<nj, 256, 0, st>>>(colsum, coltot, V, d, ldg);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
     double *WB = reinterpret_cast<double *>(ws + lay.wb);
@@ -854,7 +868,7 @@ cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_i
     }
     // stats[2j] is the Rayleigh quotient of the vector BEFORE the last normalisation; at convergence it
     // differs from that of V by O(tol^2).
-    pca_finish_kernel<<<nj, 256, 0, st>>>(V, stats, colsum, pp, ldg, d_explained, d_sigma2, d_component);
+    pca_finish_kernel<<<nj, 256, 0, st>>>(V, stats, colsum, coltot, pp, ldg, d_explained, d_sigma2, d_component);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     tm.mark();
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;

@@ -65,7 +65,7 @@ constexpr int PCA_TIMING_SLOTS = 5;
 void pca_timing(int enable);
 void pca_last_timing(double *ms);
 int pca_ldg(int d);   // leading dimension of the Gram matrices: d rounded up to a multiple of 4
-cudaError_t launch_pca_gram(int d, int64_t n, const int32_t *d_img, int nb, float *d_gram, void *d_ws, int sm_count,
+cudaError_t launch_pca_gram(int d, int64_t n, const int32_t *d_img, int nb, int32_t *d_gram, void *d_ws, int sm_count,
                             cudaStream_t st, const char **why);
 cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_iters, double tol, double *d_explained,
                        double *d_sigma2, double *d_component, int *h_iters, double *h_residual, void *d_ws, int sm_count,

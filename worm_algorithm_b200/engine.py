@@ -256,7 +256,7 @@ def pca(images: torch.Tensor, num_blocks: int = 10, max_iters: int = 2000, tol: 
 
 
 def pca_gram(images: torch.Tensor, num_blocks: int = 1) -> torch.Tensor:
-    """The tensor-core stage of `pca` alone: f32 [num_blocks, d, d], G_b = X_b^T X_b, exact integers."""
+    """The tensor-core stage of `pca` alone: int32 [num_blocks, d, d], G_b = X_b^T X_b."""
     dev = _dev(images.device)
     a, n, d = _flat_images(images)
     nb = int(num_blocks)
@@ -264,7 +264,7 @@ def pca_gram(images: torch.Tensor, num_blocks: int = 1) -> torch.Tensor:
     with torch.cuda.device(dev):
         wsb = lib().worm_pca_workspace_bytes(d, n, nb, 1)
         ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=dev)
-        g = torch.empty((nb, ldg, ldg), dtype=torch.float32, device=dev)
+        g = torch.empty((nb, ldg, ldg), dtype=torch.int32, device=dev)
         check(lib().worm_pca_gram(d, n, _ptr(a), nb, _ptr(g), _ptr(ws), wsb, _stream_ptr(dev)))
         torch.cuda.current_stream(dev).synchronize()     # the workspace must outlive the kernels
     return g[:, :d, :d]
