@@ -37,10 +37,10 @@ def gpu_case(L, n, nb, reps, peak_tf, peak_gbs):
     best.update(L=L, d=d, n=n, num_blocks=nb,
                 gram_tflops=flops / (best["gram_ms"] * 1e-3) / 1e12,
                 gram_frac=flops / (best["gram_ms"] * 1e-3) / 1e12 / peak_tf,
-                gram_out_gbs=nb * ldg * ldg * 4 / (best["gram_ms"] * 1e-3) / 1e9,
+                gram_out_gbs=ldg * ldg * 4 / (best["gram_ms"] * 1e-3) / 1e9,
                 pack_gbs=(n * d * 4 + n * d * 2) / (best["pack_ms"] * 1e-3) / 1e9,
                 pack_frac=(n * d * 4 + n * d * 2) / (best["pack_ms"] * 1e-3) / 1e9 / peak_gbs,
-                iter_gbs=(best["iters"] + 1) * (nb + 1) * ldg * ldg * 4 / (best["iter_ms"] * 1e-3) / 1e9,
+                iter_ms_per_iteration=best["iter_ms"] / max(best["iters"], 1),
                 configs_per_s=n / (best["wall_ms"] * 1e-3), explained=float(res.explained[0]))
     return best, x
 

@@ -11,11 +11,15 @@
 //                        tiles; only the lower triangle of 128x256 tiles is computed and mirrored on the
 //                        way out).  Integer in, integer out: the result is EXACT as long as it fits
 //                        int32 (checked on the host from max|value| and n; larger inputs are refused).
-//   3. gram_sum_kernel   G_full = sum_b G_b.
-//   4. power iteration   for the 1 + num_blocks problems at once (full data and each delete-one
-//                        set, A_j = G_full - G_{j-1}): fp64 matrix-vector products on the exact int32
-//                        Gram matrices, HBM-bound.
-//   5. explained variance lambda_j / n_j - (s_j . v_j / n_j)^2.
+//                        worm_pca needs only the Gram matrix of ALL configurations (one "block" spanning
+//                        the whole packed matrix); worm_pca_gram exposes the per-block matrices.
+//   3. power iteration   for the 1 + num_blocks problems at once (full data and each delete-one
+//                        set): A_j v_j = G_full v_j - X_b^T (X_b v_j), b = j - 1.  G_full meets all
+//                        vectors in one pass (pca_matvec_full_kernel); the deleted block's part goes
+//                        through the int8 configurations themselves (pca_xv_kernel, pca_xty_kernel:
+//                        two passes over 1 byte per pixel instead of a d x d matrix per block).
+//                        Matrices are exact integers, vectors and accumulation fp64.
+//   4. explained variance lambda_j / n_j - (s_j . v_j / n_j)^2.
 #include <cuda.h>   // CUtensorMap and its enums only; cuTensorMapEncodeTiled is fetched through the runtime
 #include <cuda_runtime.h>
 
@@ -38,7 +42,7 @@ struct PackPlan {
     int d, nb;
     int64_t ktot;
     int cfg0[PCA_MAX_BLOCKS + 1];   // first configuration of jackknife block b (cfg0[nb] = n)
-    int kt0[PCA_MAX_BLOCKS + 1];    // first 64-configuration group of block b in Xt (kt0[nb] = Ktot / 64); always even
+    int kt0[PCA_MAX_BLOCKS + 1];    // first 64-configuration group of block b in Xt (kt0[nb] = Ktot / 64); multiples of 8
 };
 
 __global__ void __launch_bounds__(256) pca_pack_kernel(const int32_t *__restrict__ img, int8_t *__restrict__ xt,
@@ -325,22 +329,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------------
-// 3. G_full = sum_b G_b
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gram_sum_kernel(const int4 *__restrict__ G, int4 *__restrict__ out, size_t quads, int nb)
-{
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < quads; i += (size_t)gridDim.x * blockDim.x) {
-        int4 s = __ldcs(G + i);
-        for (int b = 1; b < nb; ++b) {
-            const int4 g = __ldcs(G + (size_t)b * quads + i);
-            s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
-        }
-        out[i] = s;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// 4. power iteration on the nj = 1 + nb problems A_0 = G_full, A_j = G_full - G_{j-1}
+// 3. power iteration on the nj = 1 + nb problems A_0 = G_full, A_j = G_full - X_{j-1}^T X_{j-1}
 // ---------------------------------------------------------------------------------------------------
 constexpr int MV_ROWS = 2, MV_JC = 12, MV_WARPS = 8, MV_BATCH = 8;
 
@@ -374,97 +363,183 @@ __device__ __forceinline__ double dot4(const int4 g, const double2 va, const dou
     return int_to_double(g.x) * va.x + int_to_double(g.y) * va.y + int_to_double(g.z) * vb.x + int_to_double(g.w) * vb.y;
 }
 
-// One iteration's matrix-vector products, two kernels.  pca_matvec_block_kernel, blockIdx.y = b:
-// WB_{b+1} = G_b V_{b+1}, the deleted block's own part;  pca_matvec_full_kernel: WA_j = G_full V_j for all nj
-// problems (A_j V_j = WA_j - WB_j).  One warp per MV_ROWS rows; the matrices are exact int32, the vectors and
-// all accumulation fp64.  G: [nb + 1][ldg][ldg] (full matrix last), V / WA / WB: [nj][ldg].
-template <int U>
-__device__ __forceinline__ void rows_times_vector(const int32_t *__restrict__ r0, const int32_t *__restrict__ r1,
-                                                  const double *__restrict__ v, int c, double &a0, double &a1)
+// signed byte B of a 32-bit word -> double, exactly (sign extension, then the 2^52 trick)
+template <int B>
+__device__ __forceinline__ double s8_to_double(uint32_t w)
 {
-    int4 g0[U], g1[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        g0[u] = __ldcs(reinterpret_cast<const int4 *>(r0 + c + 128 * u));
-        g1[u] = __ldcs(reinterpret_cast<const int4 *>(r1 + c + 128 * u));
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const double2 va = *reinterpret_cast<const double2 *>(v + c + 128 * u);
-        const double2 vb = *reinterpret_cast<const double2 *>(v + c + 128 * u + 2);
-        a0 += dot4(g0[u], va, vb);
-        a1 += dot4(g1[u], va, vb);
-    }
+    return int_to_double((int)(signed char)(w >> (8 * B)));
 }
 
-__global__ void __launch_bounds__(MV_WARPS * 32, 3) pca_matvec_block_kernel(const int32_t *__restrict__ G, const double *__restrict__ V,
-                                                                             double *__restrict__ WB, int ldg, int nb,
-                                                                             const IterState *state, int slot)
+// first 512-configuration step of each jackknife block in the packed matrix
+struct StepPlan {
+    int nb;
+    int st0[PCA_MAX_BLOCKS + 1];
+};
+
+constexpr int XV_SLICES = 8;   // pixel-row slices per 512-configuration step (grid.y of pca_xv_kernel)
+
+// y = X_b v_{b+1} for every block b at once: y[k] = sum_c Xt[c][k] * V_{b(k)+1}[c].
+// blockIdx.x = 512-configuration step (one jackknife block per step), blockIdx.y = slice of pixel rows;
+// a warp reads 512 contiguous bytes of a pixel row, lane l owning configurations 16 l .. 16 l + 15.
+// The result is accumulated (fp64 atomics across the XV_SLICES slices) in the lane-major order
+// ysw[((step * 8 + i) * 32 + l) * 2 + e] = y[step * 512 + 16 l + 2 i + e], which pca_xty_kernel reads back
+// with coalesced 16-byte loads.
+__global__ void __launch_bounds__(256) pca_xv_kernel(const int8_t *__restrict__ xt, const double *__restrict__ V,
+                                                     double *__restrict__ ysw, int d, int ldg, long long ktot,
+                                                     const StepPlan sp, const IterState *state, int slot)
 {
-    static_assert(MV_ROWS == 2, "two rows per warp");
-    if (iter_finished(state, slot, nb + 1)) return;
-    const int lane = threadIdx.x & 31;
-    const int r0 = (blockIdx.x * MV_WARPS + (threadIdx.x >> 5)) * MV_ROWS;
-    if (r0 >= ldg) return;
-    const int m = blockIdx.y;
-    const int32_t *M = G + (size_t)m * ldg * ldg;
-    const int32_t *row0 = M + (size_t)r0 * ldg, *row1 = M + (size_t)min(r0 + 1, ldg - 1) * ldg;
-    const double *v = V + (size_t)(m + 1) * ldg;
+    __shared__ double red[8][16][32];
+    if (iter_finished(state, slot, sp.nb + 1)) return;
+    const int step = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int b = 0;
+    while (step >= sp.st0[b + 1]) ++b;
+    const double *v = V + (size_t)(b + 1) * ldg;
+    const int rps = (d + XV_SLICES - 1) / XV_SLICES;
+    const int c_begin = blockIdx.y * rps, c_end = min(d, c_begin + rps);
+    const int8_t *col = xt + (size_t)step * 512 + lane * 16;
+    double acc[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] = 0.0;
     constexpr int U = 4;
-    double a0 = 0.0, a1 = 0.0;
-    int c = lane * 4;
-    for (; c + 128 * (U - 1) < ldg; c += 128 * U) rows_times_vector<U>(row0, row1, v, c, a0, a1);
-    for (; c < ldg; c += 128) rows_times_vector<1>(row0, row1, v, c, a0, a1);
-    a0 = warp_sum(a0);
-    a1 = warp_sum(a1);
-    if (lane == 0) {
-        WB[(size_t)(m + 1) * ldg + r0] = a0;
-        if (r0 + 1 < ldg) WB[(size_t)(m + 1) * ldg + r0 + 1] = a1;
+    for (int c = c_begin + warp; c < c_end; c += 8 * U) {
+        uint4 x[U];
+        double vc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int cc = c + 8 * u;
+            const bool ok = cc < c_end;
+            x[u] = ok ? *reinterpret_cast<const uint4 *>(col + (size_t)cc * ktot) : make_uint4(0u, 0u, 0u, 0u);
+            vc[u] = ok ? v[cc] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                acc[4 * q + 0] += s8_to_double<0>(w[q]) * vc[u];
+                acc[4 * q + 1] += s8_to_double<1>(w[q]) * vc[u];
+                acc[4 * q + 2] += s8_to_double<2>(w[q]) * vc[u];
+                acc[4 * q + 3] += s8_to_double<3>(w[q]) * vc[u];
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) red[warp][e][lane] = acc[e];
+    __syncthreads();
+    {
+        const int l = threadIdx.x >> 3, i = threadIdx.x & 7;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            s0 += red[w][2 * i][l];
+            s1 += red[w][2 * i + 1][l];
+        }
+        double *dst = ysw + ((size_t)(step * 8 + i) * 32 + l) * 2;
+        atomicAdd(dst, s0);
+        atomicAdd(dst + 1, s1);
     }
 }
 
-// The full matrix meets all nj vectors: the vectors of one 256-column chunk are staged in shared memory
-// once per block (16 rows) instead of being fetched through L1 by every warp.
+// WB_{b+1} = X_b^T y_b: WB[(b+1)][c] = sum_{k in block b} Xt[c][k] * y[k].  blockIdx.x = 32 pixel rows
+// (4 per warp), blockIdx.y = jackknife block.
+__global__ void __launch_bounds__(256) pca_xty_kernel(const int8_t *__restrict__ xt, const double *__restrict__ ysw,
+                                                      double *__restrict__ WB, int d, int ldg, long long ktot,
+                                                      const StepPlan sp, const IterState *state, int slot)
+{
+    if (iter_finished(state, slot, sp.nb + 1)) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, c0 = blockIdx.x * 32 + warp * 4;
+    if (c0 >= ldg) return;
+    const double2 *y2 = reinterpret_cast<const double2 *>(ysw);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int step = sp.st0[b]; step < sp.st0[b + 1]; ++step) {
+        double2 y[8];
+        uint4 x[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = y2[(size_t)(step * 8 + i) * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            x[r] = c0 + r < d ? *reinterpret_cast<const uint4 *>(xt + (size_t)(c0 + r) * ktot + (size_t)step * 512 + lane * 16)
+                              : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t w[4] = {x[r].x, x[r].y, x[r].z, x[r].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                acc[r] += s8_to_double<0>(w[q]) * y[2 * q].x + s8_to_double<1>(w[q]) * y[2 * q].y +
+                          s8_to_double<2>(w[q]) * y[2 * q + 1].x + s8_to_double<3>(w[q]) * y[2 * q + 1].y;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const double sum = warp_sum(acc[r]);
+        if (lane == 0 && c0 + r < ldg) WB[(size_t)(b + 1) * ldg + c0 + r] = sum;
+    }
+}
+
+// WA_j = G_full V_j for all nj problems.  One warp per MV_ROWS rows; the vectors of a 256-column chunk are
+// staged in shared memory once per block (cp.async, double buffered) and the matrix words of the next
+// chunk are in flight while the current one is consumed.
 constexpr int MV_CHUNK = 256;
+constexpr int MV_FULL_SMEM = 2 * MV_JC * MV_CHUNK * 8;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 
 __global__ void __launch_bounds__(MV_WARPS * 32, 2) pca_matvec_full_kernel(const int32_t *__restrict__ G, const double *__restrict__ V,
-                                                                            double *__restrict__ WA, int ldg, int nb,
+                                                                            double *__restrict__ WA, int ldg, int nj,
                                                                             const IterState *state, int slot)
 {
-    __shared__ __align__(16) double vs[MV_JC][MV_CHUNK];
-    const int nj = nb + 1;
+    extern __shared__ __align__(16) uint8_t mv_smem[];
+    double (*vs)[MV_JC][MV_CHUNK] = reinterpret_cast<double (*)[MV_JC][MV_CHUNK]>(mv_smem);
     if (iter_finished(state, slot, nj)) return;
     const int lane = threadIdx.x & 31;
     const int r0 = (blockIdx.x * MV_WARPS + (threadIdx.x >> 5)) * MV_ROWS;
-    const int32_t *M = G + (size_t)nb * ldg * ldg;
     const int32_t *row[MV_ROWS];
 #pragma unroll
-    for (int r = 0; r < MV_ROWS; ++r) row[r] = M + (size_t)min(r0 + r, ldg - 1) * ldg;
+    for (int r = 0; r < MV_ROWS; ++r) row[r] = G + (size_t)min(r0 + r, ldg - 1) * ldg;
+    const int nch = (ldg + MV_CHUNK - 1) / MV_CHUNK;
+    const uint32_t vs_base = (uint32_t)__cvta_generic_to_shared(mv_smem);
 
     for (int j0 = 0; j0 < nj; j0 += MV_JC) {
         const int jn = min(MV_JC, nj - j0);
+        auto fill = [&](int buf, int c0) {
+            for (int i = threadIdx.x; i < jn * (MV_CHUNK / 2); i += MV_WARPS * 32) {
+                const int j = i / (MV_CHUNK / 2), cc = (i % (MV_CHUNK / 2)) * 2;
+                const bool ok = c0 + cc < ldg;
+                cp_async16(vs_base + (uint32_t)(((buf * MV_JC + j) * MV_CHUNK + cc) * 8),
+                           ok ? V + (size_t)(j0 + j) * ldg + c0 + cc : V, ok ? 16u : 0u);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto load_g = [&](int4 (&g)[2][MV_ROWS], int c0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = c0 + 128 * h + lane * 4;
+                const bool ok = c < ldg && r0 < ldg;
+#pragma unroll
+                for (int r = 0; r < MV_ROWS; ++r)
+                    g[h][r] = ok ? __ldcs(reinterpret_cast<const int4 *>(row[r] + c)) : make_int4(0, 0, 0, 0);
+            }
+        };
         double acc[MV_ROWS][MV_JC];
 #pragma unroll
         for (int r = 0; r < MV_ROWS; ++r)
 #pragma unroll
             for (int j = 0; j < MV_JC; ++j) acc[r][j] = 0.0;
-        for (int c0 = 0; c0 < ldg; c0 += MV_CHUNK) {
-            int4 g[2][MV_ROWS];
-            bool ok[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {   // issue the matrix loads before waiting at the barrier
-                const int c = c0 + 128 * h + lane * 4;
-                ok[h] = c < ldg && r0 < ldg;
-#pragma unroll
-                for (int r = 0; r < MV_ROWS; ++r)
-                    g[h][r] = ok[h] ? __ldcs(reinterpret_cast<const int4 *>(row[r] + c)) : make_int4(0, 0, 0, 0);
-            }
-            __syncthreads();
-            for (int i = threadIdx.x; i < jn * (MV_CHUNK / 2); i += MV_WARPS * 32) {
-                const int j = i / (MV_CHUNK / 2), cc = (i % (MV_CHUNK / 2)) * 2;
-                double2 x = make_double2(0.0, 0.0);
-                if (c0 + cc < ldg) x = *reinterpret_cast<const double2 *>(V + (size_t)(j0 + j) * ldg + c0 + cc);
-                *reinterpret_cast<double2 *>(&vs[j][cc]) = x;
+        int4 gcur[2][MV_ROWS], gnext[2][MV_ROWS];
+        fill(0, 0);
+        load_g(gcur, 0);
+        for (int ci = 0; ci < nch; ++ci) {
+            const int buf = ci & 1;
+            if (ci + 1 < nch) {
+                fill(buf ^ 1, (ci + 1) * MV_CHUNK);
+                load_g(gnext, (ci + 1) * MV_CHUNK);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
             __syncthreads();
 #pragma unroll
@@ -472,13 +547,18 @@ __global__ void __launch_bounds__(MV_WARPS * 32, 2) pca_matvec_full_kernel(const
                 if (j < jn) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const double2 va = *reinterpret_cast<const double2 *>(&vs[j][128 * h + lane * 4]);
-                        const double2 vb = *reinterpret_cast<const double2 *>(&vs[j][128 * h + lane * 4 + 2]);
+                        const double2 va = *reinterpret_cast<const double2 *>(&vs[buf][j][128 * h + lane * 4]);
+                        const double2 vb = *reinterpret_cast<const double2 *>(&vs[buf][j][128 * h + lane * 4 + 2]);
 #pragma unroll
-                        for (int r = 0; r < MV_ROWS; ++r) acc[r][j] += dot4(g[h][r], va, vb);
+                        for (int r = 0; r < MV_ROWS; ++r) acc[r][j] += dot4(gcur[h][r], va, vb);
                     }
                 }
             }
+            __syncthreads();   // buffer `buf` is refilled two chunks ahead
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int r = 0; r < MV_ROWS; ++r) gcur[h][r] = gnext[h][r];
         }
 #pragma unroll
         for (int j = 0; j < MV_JC; ++j) {
@@ -681,7 +761,7 @@ void make_pack_plan(int d, int64_t n, int nb, PackPlan &p)
         p.cfg0[b] = cfg;
         p.kt0[b] = kt;
         cfg += len;
-        kt += 2 * ((len + BK - 1) / BK);   // 64-configuration groups, padded to whole BK = 128 k blocks
+        kt += 8 * ((len + 511) / 512);   // 64-configuration groups; every block is padded to whole 512-configuration steps
     }
     p.cfg0[nb] = cfg;
     p.kt0[nb] = kt;
@@ -689,7 +769,7 @@ void make_pack_plan(int d, int64_t n, int nb, PackPlan &p)
 }
 
 struct Layout {
-    size_t xt, colsum, maxabs, gram, v, w, wb, stats, state, coltot, total;
+    size_t xt, colsum, maxabs, gram, v, w, wb, ysw, stats, state, coltot, total;
     int ldg;
 };
 
@@ -703,22 +783,23 @@ Layout make_layout(int d, const PackPlan &p, bool with_iteration)
     l.maxabs = off;  off = align_up(off + 256, 256);
     l.gram = off;
     if (with_iteration) {
-        off = align_up(off + (size_t)(p.nb + 1) * l.ldg * l.ldg * 4, 256);
+        off = align_up(off + (size_t)l.ldg * l.ldg * 4, 256);   // the Gram matrix of all configurations
         l.v = off;      off = align_up(off + (size_t)(p.nb + 1) * l.ldg * 8, 256);
         l.w = off;      off = align_up(off + (size_t)(p.nb + 1) * l.ldg * 8, 256);
         l.wb = off;     off = align_up(off + (size_t)(p.nb + 1) * l.ldg * 8, 256);
+        l.ysw = off;    off = align_up(off + (size_t)p.ktot * 8, 256);
         l.stats = off;  off = align_up(off + (size_t)(p.nb + 1) * 16, 256);
         l.state = off;  off = align_up(off + sizeof(IterState), 256);
         l.coltot = off; off = align_up(off + (size_t)d * 8, 256);
     } else {
-        l.v = l.w = l.wb = l.stats = l.state = l.coltot = off;
+        l.v = l.w = l.wb = l.ysw = l.stats = l.state = l.coltot = off;
     }
     l.total = off;
     return l;
 }
 
 cudaError_t run_pack_and_gram(int d, int64_t n, const int32_t *d_img, const PackPlan &pp, const Layout &lay, uint8_t *ws,
-                              int32_t *d_gram, int sm_count, cudaStream_t st, const char **why, StageTimer &tm)
+                              int32_t *d_gram, bool all_in_one, int sm_count, cudaStream_t st, const char **why, StageTimer &tm)
 {
     cudaError_t e;
     tm.mark();
@@ -759,11 +840,12 @@ cudaError_t run_pack_and_gram(int d, int64_t n, const int32_t *d_img, const Pack
     GramPlan gp;
     gp.d = d;
     gp.ldg = lay.ldg;
-    gp.nb = pp.nb;
+    gp.nb = all_in_one ? 1 : pp.nb;   // all_in_one: one Gram matrix over the whole packed matrix (the padding is zeros)
     gp.tm_count = (lay.ldg + BM - 1) / BM;
     gp.tiles_per_block = 0;
     for (int tm = 0; tm < gp.tm_count; ++tm) gp.tiles_per_block += tm / 2 + 1;
     for (int b = 0; b <= pp.nb; ++b) gp.kt0[b] = pp.kt0[b] / 2;
+    if (all_in_one) gp.kt0[1] = pp.kt0[pp.nb] / 2;
     gp.G = d_gram;
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
@@ -796,7 +878,7 @@ cudaError_t launch_pca_gram(int d, int64_t n, const int32_t *d_img, int nb, int3
     make_pack_plan(d, n, nb, pp);
     const Layout lay = make_layout(d, pp, false);
     StageTimer tm(st);
-    cudaError_t e = run_pack_and_gram(d, n, d_img, pp, lay, static_cast<uint8_t *>(d_ws), d_gram, sm_count, st, why, tm);
+    cudaError_t e = run_pack_and_gram(d, n, d_img, pp, lay, static_cast<uint8_t *>(d_ws), d_gram, false, sm_count, st, why, tm);
     if (e == cudaSuccess && tm.on) {
         e = cudaStreamSynchronize(st);
         tm.finish();
@@ -821,14 +903,9 @@ cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_i
     uint8_t *ws = static_cast<uint8_t *>(d_ws);
     int32_t *G = reinterpret_cast<int32_t *>(ws + lay.gram);
     StageTimer tm(st);
-    cudaError_t e = run_pack_and_gram(d, n, d_img, pp, lay, ws, G, sm_count, st, why, tm);
+    cudaError_t e = run_pack_and_gram(d, n, d_img, pp, lay, ws, G, true, sm_count, st, why, tm);
     if (e != cudaSuccess) return e;
     const int ldg = lay.ldg, nj = nb + 1;
-    const size_t quads = (size_t)ldg * ldg / 4;
-    gram_sum_kernel<<<(unsigned)std::min<size_t>((quads + 255) / 256, (size_t)sm_count * 8), 256, 0, st>>>(
-        reinterpret_cast<const int4 *>(G), reinterpret_cast<int4 *>(G + (size_t)nb * ldg * ldg), quads, nb);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-
     auto *colsum = reinterpret_cast<const long long *>(ws + lay.colsum);
     double *V = reinterpret_cast<double *>(ws + lay.v), *W = reinterpret_cast<double *>(ws + lay.w);
     double *stats = reinterpret_cast<double *>(ws + lay.stats);
@@ -841,6 +918,17 @@ cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_i
     IterState *state = reinterpret_cast<IterState *>(ws + lay.state);
     if ((e = cudaMemsetAsync(state, 0, sizeof(IterState), st)) != cudaSuccess) return e;
     const unsigned mv_rows = (unsigned)((ldg + MV_ROWS * MV_WARPS - 1) / (MV_ROWS * MV_WARPS));
+    const int8_t *xt = reinterpret_cast<const int8_t *>(ws + lay.xt);
+    double *ysw = reinterpret_cast<double *>(ws + lay.ysw);
+    StepPlan sp;
+    sp.nb = nb;
+    for (int b = 0; b <= nb; ++b) sp.st0[b] = pp.kt0[b] / 8;
+    static std::once_flag mv_once;
+    static cudaError_t mv_err = cudaSuccess;
+    std::call_once(mv_once, [] {
+        mv_err = cudaFuncSetAttribute(pca_matvec_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MV_FULL_SMEM);
+    });
+    if (mv_err != cudaSuccess) return mv_err;
     std::vector<double> h_stats(2 * (size_t)nj);
     IterState h_state{};
     int iters = 0;
@@ -851,8 +939,10 @@ cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_i
         const int batch = std::min(MV_BATCH, max_iters - iters);
         if ((e = cudaMemsetAsync(state->cnt, 0, sizeof(state->cnt), st)) != cudaSuccess) return e;
         for (int i = 0; i < batch; ++i) {
-            pca_matvec_block_kernel<<<dim3(mv_rows, (unsigned)nb), MV_WARPS * 32, 0, st>>>(G, V, WB, ldg, nb, state, i);
-            pca_matvec_full_kernel<<<mv_rows, MV_WARPS * 32, 0, st>>>(G, V, W, ldg, nb, state, i);
+            if ((e = cudaMemsetAsync(ysw, 0, (size_t)pp.ktot * 8, st)) != cudaSuccess) return e;
+            pca_xv_kernel<<<dim3((unsigned)sp.st0[nb], XV_SLICES), 256, 0, st>>>(xt, V, ysw, d, ldg, pp.ktot, sp, state, i);
+            pca_xty_kernel<<<dim3((unsigned)((ldg + 31) / 32), (unsigned)nb), 256, 0, st>>>(xt, ysw, WB, d, ldg, pp.ktot, sp, state, i);
+            pca_matvec_full_kernel<<<mv_rows, MV_WARPS * 32, MV_FULL_SMEM, st>>>(G, V, W, ldg, nj, state, i);
             pca_update_kernel<<<nj, 256, 0, st>>>(V, W, WB, stats, ldg, nj, tol * tol, state, i);
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
