@@ -20,6 +20,7 @@ Numbers:
          reduced sums are all inside the timed region (wall clock around a synchronised call).
   roofline        SM integer-issue roofline of the worm kernel (64 thread-instr/step).
   roofline_blocking  HBM roofline of the RG blocking kernel (20 L^2 bytes per config per level).
+  roofline_pca    tensor roofline of the PCA Gram kernel (int8 tcgen05) + stage times + sklearn CPU baseline.
   cpu_baseline    the UNMODIFIED reference executable (oracle/_ref) on all host cores, bounded sample.
 """
 from __future__ import annotations
@@ -327,6 +328,7 @@ def run_b200_arm(a) -> None:
                 "peak_source": "148 SM x 128 lanes x sm_max_mhz (MEASURED_PEAKS.json)" if peaks else "fallback 1965 MHz",
                 "cycles_per_step_per_chain": f_max * n / kern_rate}
     roofline_blocking = bench_blocking(torch, engine, dev, peaks)
+    roofline_pca = bench_pca(torch, engine, dev, peaks, cpu=(world == 1 and not a.no_cpu))
     cpu = None
     if world == 1 and not a.no_cpu:
         cores = host_cores()
@@ -347,6 +349,7 @@ def run_b200_arm(a) -> None:
         "clocks": clocks,
         "roofline": roofline,
         "roofline_blocking": roofline_blocking,
+        "roofline_pca": roofline_pca,
         "cpu_baseline": cpu,
         "check": {"E_T1.5": float(E[0]), "E_T3.5": float(E[-1]), "e2e_E_T1.5": float(e2e_E[0]),
                   "kaufman_E_T1.5": -1.9511165659, "kaufman_E_T3.5": -0.6601217470},
@@ -354,6 +357,55 @@ def run_b200_arm(a) -> None:
     print(json.dumps(line), flush=True)
     if world > 1:
         td.destroy_process_group()
+
+
+def bench_pca(torch, engine, dev, peaks, cpu: bool) -> dict:
+    """PCA row (pca.py:97-147) at L=32: 20480 images of 4096 pixels, 10 jackknife blocks.
+    Tensor roofline of the Gram kernel (int8 tcgen05: algorithmic ops = 2 x n x d(d+1)/2), stage times from
+    CUDA events inside the library, and the reference's CPU algorithm (sklearn TruncatedSVD) beside it."""
+    import ctypes as C
+    L, n, nb = 32, 20480, 10
+    d = 4 * L * L
+    gen = torch.Generator(device=dev).manual_seed(32)
+    x = (torch.rand((n, d), device=dev, generator=gen) < 0.2).to(torch.int32)
+    lib = engine.lib()
+    lib.worm_pca_timing(1)
+    ms = (C.c_double * 4)()
+    best, wall_best, res = None, None, None
+    for _ in range(5):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        res = engine.pca(x, nb)
+        torch.cuda.synchronize(dev)
+        wall = time.perf_counter() - t0
+        lib.worm_pca_last_timing(ms)
+        if best is None or ms[2] < best[2]:
+            best = [ms[0], ms[1], ms[2], ms[3]]
+        wall_best = wall if wall_best is None else min(wall_best, wall)
+    lib.worm_pca_timing(0)
+    ops = float(n) * d * (d + 1)
+    peak = 2.0 * float(peaks.get("bf16_tflops", 1627.0))
+    out = {"bound": "tensor", "kernel": "gram_kernel", "achieved": ops / (best[2] * 1e-3) / 1e12, "peak": peak,
+           "unit": "Top/s (int8)", "frac": ops / (best[2] * 1e-3) / 1e12 / peak, "traffic": None,
+           "peak_source": "2 x bf16_tflops of MEASURED_PEAKS.json (no measured int8 figure; int8 dense is 2x bf16 nominally)",
+           "alg_ops": "2 x n x d(d+1)/2, n = %d images, d = %d pixels" % (n, d),
+           "stage_ms": {"pack": best[0], "gate": best[1], "gram": best[2], "iterate": best[3]},
+           "iterations": res.iters, "ms_per_call": wall_best * 1e3, "images_per_s": n / wall_best,
+           "explained_variance": float(res.explained[0])}
+    if cpu:
+        from sklearn.decomposition import TruncatedSVD
+        data = x.cpu().numpy().astype(np.float64)
+        t0 = time.perf_counter()
+        svd = TruncatedSVD(n_components=1)
+        svd.fit(data)
+        TruncatedSVD(n_components=1).fit(data[n // nb:])           # one of the nb delete-one-block fits
+        w = time.perf_counter() - t0
+        est = w * (1 + nb) / 2
+        out["cpu_baseline"] = {"value": n / est, "unit": "images/s", "kind": "port", "cores": host_cores(),
+                               "sample": "sklearn TruncatedSVD(1): full fit + 1 of %d jackknife fits on the same images, %.1f s; extrapolated to 1 + %d fits" % (nb, w, nb),
+                               "explained_variance": float(svd.explained_variance_[0])}
+    del x
+    return out
 
 
 def bench_blocking(torch, engine, dev, peaks) -> dict:

@@ -156,6 +156,16 @@ int worm_block(int W, int64_t n, const int32_t *d_in, int32_t *d_out,
                int double_bonds_value, int variant, void *stream);
 int worm_count(int W, int64_t n, const int32_t *d_img, int64_t *d_count, void *stream);
 
+/* worm_boundaries  boundaries between the black and white regions of thresholded grey images
+ *              (image_analysis/image.py:46-80, Image._cutoff + Image.get_boundaries), all images x all
+ *              cutoffs in one launch: d_img f64 [n][Nx][Ny] (the class's `_image`, 1 - bytes/255),
+ *              d_cutoffs f64 [m], d_links int32 [n][m][2Nx][2Ny] in the bond-image convention of
+ *              worm_image (sites at even-even, links at odd-parity pixels), so worm_block / worm_count
+ *              apply to it unchanged.  The comparison `pixel < cutoff` is done in f64 as the reference
+ *              does. */
+int worm_boundaries(int Nx, int Ny, int64_t n, const double *d_img, int m, const double *d_cutoffs,
+                    int32_t *d_links, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Leading principal component of a stack of images, with the reference's delete-one-block jackknife
  * (pca.py:97-147: TruncatedSVD(n_components=1).fit(data).explained_variance_[0] of the un-centred
@@ -202,6 +212,8 @@ int worm_image_host(int L, int64_t n, const uint8_t *h_bonds, int32_t *h_img);
 int worm_block_host(int W, int64_t n, const int32_t *h_in, int32_t *h_out,
                     int double_bonds_value, int variant);
 int worm_count_host(int W, int64_t n, const int32_t *h_img, int64_t *h_count);
+int worm_boundaries_host(int Nx, int Ny, int64_t n, const double *h_img, int m, const double *h_cutoffs,
+                         int32_t *h_links);
 /* h_explained f64 [1 + num_blocks]; h_component f64 [d] or NULL */
 int worm_pca_host(int d, int64_t n, const int32_t *h_images, int num_blocks, int max_iters, double tol,
                   double *h_explained, double *h_component, int32_t *h_iters, double *h_residual);

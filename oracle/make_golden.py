@@ -257,6 +257,44 @@ def gen_pca():
     print("pca.npz:", len(g), "arrays")
 
 
+def gen_boundaries():
+    """image_analysis/image.py's own Image class (unmodified) on synthetic grey images.  scipy.misc.bytescale /
+    imread no longer exist: the module is imported with a stub scipy.misc whose bytescale is the restated
+    scipy 1.1 algorithm (oracle/image_oracle.py); _cutoff and get_boundaries are the reference's code."""
+    import_reference()
+    from oracle import image_oracle as io
+    import scipy
+    stub = types.ModuleType("scipy.misc")
+    stub.bytescale = io.bytescale
+    stub.imread = None
+    sys.modules["scipy.misc"] = stub
+    scipy.misc = stub
+    sys.path.insert(0, os.path.join(os.path.dirname(REF.rstrip("/")), "image_analysis"))
+    import image as ref_image               # noqa
+    rng = np.random.default_rng(4242)
+    g = {}
+    yy, xx = np.mgrid[0:28, 0:28]
+    blob = np.exp(-((xx - 9.0) ** 2 + (yy - 12.0) ** 2) / 30.0) + 0.7 * np.exp(-((xx - 20.0) ** 2 + (yy - 18.0) ** 2) / 12.0)
+    cases = {"rand8": rng.random((8, 8)), "rand12x10": rng.random((12, 10)) * 300.0 - 20.0,
+             "blob28": blob + 0.05 * rng.random((28, 28)), "bytes6": rng.integers(0, 256, (6, 6)).astype(np.uint8),
+             "flat5": np.full((5, 5), 3.0)}
+    for name, img in cases.items():
+        ri = ref_image.Image(img)
+        cutoffs = np.array([0.0, 0.1, 0.35, 0.5, 0.8, 1.0, 1.1])
+        g["bdy_%s_in" % name] = img
+        g["bdy_%s_prepared" % name] = np.asarray(ri._image, dtype=np.float64)
+        g["bdy_%s_cutoffs" % name] = cutoffs
+        outs, bws = [], []
+        for c in cutoffs:
+            outs.append(np.asarray(ri.get_boundaries(c)).astype(np.int8))
+            bws.append(np.asarray(ri._image_bw).astype(np.int8))
+            assert (io.get_boundaries(io.prepare(img), c) == outs[-1]).all(), (name, c)
+        g["bdy_%s_links" % name] = np.stack(outs)
+        g["bdy_%s_bw" % name] = np.stack(bws)
+    np.savez_compressed(os.path.join(GOLD, "boundaries.npz"), **g)
+    print("boundaries.npz:", len(g), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -266,3 +304,5 @@ if __name__ == "__main__":
         gen_post()
     if what in ("all", "pca"):
         gen_pca()
+    if what in ("all", "boundaries"):
+        gen_boundaries()

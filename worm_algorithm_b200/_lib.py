@@ -50,6 +50,8 @@ SIGNATURES = {
     "worm_image_host": (C.c_int, [C.c_int, _i64, _vp, _vp]),
     "worm_block_host": (C.c_int, [C.c_int, _i64, _vp, _vp, C.c_int, C.c_int]),
     "worm_count_host": (C.c_int, [C.c_int, _i64, _vp, _vp]),
+    "worm_boundaries": (C.c_int, [C.c_int, C.c_int, _i64, _vp, C.c_int, _vp, _vp, _vp]),
+    "worm_boundaries_host": (C.c_int, [C.c_int, C.c_int, _i64, _vp, C.c_int, _vp, _vp]),
     "worm_pca_workspace_bytes": (_sz, [C.c_int, _i64, C.c_int, C.c_int]),
     "worm_pca_timing": (None, [C.c_int]),
     "worm_pca_last_timing": (None, [_pd]),

@@ -299,6 +299,18 @@ int worm_count(int W, int64_t n, const int32_t *d_img, int64_t *d_count, void *s
     return WORM_OK;
 }
 
+int worm_boundaries(int Nx, int Ny, int64_t n, const double *d_img, int m, const double *d_cutoffs,
+                    int32_t *d_links, void *stream)
+{
+    if (Nx < 1 || Ny < 1 || Nx > 32768 || Ny > 32768) return fail(WORM_E_ARG, "image size %d x %d out of range", Nx, Ny);
+    if (n < 0 || m < 0 || ((n > 0 && m > 0) && (!d_img || !d_cutoffs || !d_links))) return fail(WORM_E_ARG, "bad n / m / null pointer");
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    cudaError_t e = worm::launch_boundaries(Nx, Ny, n, m, d_img, d_cutoffs, d_links, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "boundaries_kernel launch");
+    return WORM_OK;
+}
+
 static int pca_check(int d, int64_t n, int num_blocks)
 {
     if (d < 1 || d > (1 << 20)) return fail(WORM_E_ARG, "d = %d out of range", d);
@@ -458,6 +470,26 @@ int worm_count_host(int W, int64_t n, const int32_t *h_img, int64_t *h_count)
     if ((e = cudaMemcpy(in.p, h_img, (size_t)n * W * W * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "copy in");
     if (int rc = worm_count(W, n, (const int32_t *)in.p, (int64_t *)out.p, nullptr)) return rc;
     if ((e = cudaMemcpy(h_count, out.p, (size_t)n * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "copy out");
+    return WORM_OK;
+}
+
+int worm_boundaries_host(int Nx, int Ny, int64_t n, const double *h_img, int m, const double *h_cutoffs,
+                         int32_t *h_links)
+{
+    if (n <= 0 || m <= 0 || !h_img || !h_cutoffs || !h_links) return fail(WORM_E_ARG, "bad n / m / null pointer");
+    if (Nx < 1 || Ny < 1 || Nx > 32768 || Ny > 32768) return fail(WORM_E_ARG, "image size %d x %d out of range", Nx, Ny);
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    DevBuf in, cut, out;
+    cudaError_t e;
+    const size_t sites = (size_t)Nx * Ny;
+    if ((e = in.alloc(n * sites * 8)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cut.alloc((size_t)m * 8)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = out.alloc((size_t)n * m * sites * 16)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMemcpy(in.p, h_img, n * sites * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "copy in");
+    if ((e = cudaMemcpy(cut.p, h_cutoffs, (size_t)m * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "copy in");
+    if (int rc = worm_boundaries(Nx, Ny, n, (const double *)in.p, m, (const double *)cut.p, (int32_t *)out.p, nullptr)) return rc;
+    if ((e = cudaMemcpy(h_links, out.p, (size_t)n * m * sites * 16, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "copy out");
     return WORM_OK;
 }
 

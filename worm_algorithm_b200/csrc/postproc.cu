@@ -358,6 +358,43 @@ cudaError_t launch_block(int W, int64_t n, const int32_t *d_in, int32_t *d_out, 
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Boundaries between the black and white regions of thresholded grey images (image_analysis/image.py:46-80)
+// ---------------------------------------------------------------------------------------------------
+// bw(x, y) = image(x, y) >= cutoff.  link0(x, y) = bw(x, y) ^ bw(x, y-1), link1(x, y) = bw(x, y) ^ bw(x-1, y)
+// (periodic).  Output [2Nx][2Ny]: (2x+1, 2y) = link0, (2x, 2y+1) = link1, (2x, 2y) = any of link0(x, y),
+// link1(x, y), link0(x-1, y), link1(x, y-1); (2x+1, 2y+1) = 0.  One thread per site, one launch for all
+// images x cutoffs; each thread writes two 8-byte pairs, consecutive threads consecutive y.
+__global__ void __launch_bounds__(256) boundaries_kernel(int Nx, int Ny, int64_t n, int m, const double *__restrict__ img,
+                                                         const double *__restrict__ cutoffs, int32_t *__restrict__ out)
+{
+    const int64_t sites = (int64_t)Nx * Ny, total = n * m * sites;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t im = i / sites;                 // image-major, cutoff-minor: im = image * m + cutoff
+        const int s = (int)(i - im * sites);
+        const int x = s / Ny, y = s - x * Ny;
+        const double cut = cutoffs[im % m];
+        const double *src = img + (im / m) * sites;
+        const int xm = x ? x - 1 : Nx - 1, ym = y ? y - 1 : Ny - 1;
+        const int b = src[(size_t)x * Ny + y] >= cut, bxm = src[(size_t)xm * Ny + y] >= cut;
+        const int bym = src[(size_t)x * Ny + ym] >= cut, bxy = src[(size_t)xm * Ny + ym] >= cut;
+        const int l0 = b ^ bym, l1 = b ^ bxm;
+        const int l0_up = bxm ^ bxy, l1_left = bym ^ bxy;
+        int32_t *dst = out + im * 4 * sites + (size_t)(2 * x) * (2 * Ny) + 2 * y;
+        *reinterpret_cast<int2 *>(dst) = make_int2((l0 | l1 | l0_up | l1_left) ? 1 : 0, l1);
+        *reinterpret_cast<int2 *>(dst + 2 * Ny) = make_int2(l0, 0);
+    }
+}
+
+cudaError_t launch_boundaries(int Nx, int Ny, int64_t n, int m, const double *d_img, const double *d_cutoffs, int32_t *d_out,
+                              cudaStream_t st)
+{
+    const int64_t items = n * m * (int64_t)Nx * Ny;
+    if (items == 0) return cudaSuccess;
+    boundaries_kernel<<<grid_for(items, 256), 256, 0, st>>>(Nx, Ny, n, m, d_img, d_cutoffs, d_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_count(int W, int64_t n, const int32_t *d_img, int64_t *d_count, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;

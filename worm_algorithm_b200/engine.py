@@ -216,6 +216,23 @@ def count(images: torch.Tensor) -> torch.Tensor:
     return out.reshape(lead) if len(lead) else out.reshape(())
 
 
+def boundaries(images: torch.Tensor, cutoffs) -> torch.Tensor:
+    """Black / white boundaries of thresholded grey images (image_analysis/image.py:46-80):
+    f64 [n, Nx, Ny] x cutoffs [m] -> int32 [n, m, 2Nx, 2Ny]."""
+    dev = _dev(images.device)
+    a = images.contiguous()
+    if a.dtype != torch.float64 or a.dim() != 3:
+        raise TypeError("images must be float64 [n, Nx, Ny]")
+    n, Nx, Ny = a.shape
+    with torch.cuda.device(dev):
+        cut = torch.as_tensor(np.asarray(cutoffs, dtype=np.float64).reshape(-1)).to(dev)
+        m = cut.numel()
+        out = torch.empty((n, m, 2 * Nx, 2 * Ny), dtype=torch.int32, device=dev)
+        check(lib().worm_boundaries(Nx, Ny, n, _ptr(a), m, _ptr(cut), _ptr(out), _stream_ptr(dev)))
+        torch.cuda.current_stream(dev).synchronize()     # `cut` must outlive the kernel
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 @dataclass
 class PcaResult:
