@@ -8,7 +8,7 @@
 //                        own zero-padded run of 128-wide k tiles; per-block column sums; max |value|.
 //   2. gram_kernel       per-block Gram matrices G_b = X_b^T X_b on the 5th-generation tensor cores
 //                        (tcgen05.mma kind::i8, s8 x s8 -> s32 in TMEM; TMA 128B-swizzled operand
-//                        tiles; only the lower triangle of 128x256 tiles is computed and mirrored on the
+//                        tiles; only the lower triangle of 256x256 tiles is computed and mirrored on the
 //                        way out).  Integer in, integer out: the result is EXACT as long as it fits
 //                        int32 (checked on the host from max|value| and n; larger inputs are refused).
 //                        worm_pca needs only the Gram matrix of ALL configurations (one "block" spanning
@@ -92,11 +92,16 @@ __global__ void __launch_bounds__(256) pca_pack_kernel(const int32_t *__restrict
 // ---------------------------------------------------------------------------------------------------
 // 2. Gram matrices on tcgen05
 // ---------------------------------------------------------------------------------------------------
-constexpr int BM = 128, BN = 256, BK = 128, STAGES = 4;   // BK int8 elements = one 128-byte swizzle row
-constexpr int A_BYTES = BM * BK, B_HALF_BYTES = 128 * BK, STAGE_BYTES = A_BYTES + 2 * B_HALF_BYTES;
+// CTA tile 256 x 256: two M = 128 accumulators (TMEM columns 0-255 and 256-511) share every B stage, so a
+// stage of 64 KB feeds eight MMAs (1024 tensor cycles).  With three stages in flight that covers ~3000
+// cycles of TMA latency at 64 B/clk/SM of L2 traffic; the 128 x 256 tile of the first version (48 KB per
+// 512 cycles, four stages) left the tensor pipe idle 47 % of the time waiting for operands.
+constexpr int BM = 256, BN = 256, BK = 128, STAGES = 3;   // BK int8 elements = one 128-byte swizzle row
+constexpr int HALF_BYTES = 128 * BK;                        // one TMA box: 128 rows x 128 bytes
+constexpr int STAGE_BYTES = 4 * HALF_BYTES;                 // A rows 0-127, A rows 128-255, B cols 0-127, B cols 128-255
 constexpr int GRAM_THREADS = 256;
 constexpr int GRAM_SMEM = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-constexpr int TMEM_COLS = 512;   // two 256-column accumulators: the epilogue of tile i overlaps the MMAs of tile i+1
+constexpr int TMEM_COLS = 512;
 
 struct GramPlan {
     int d, ldg, nb, tm_count, tiles_per_block;
@@ -168,27 +173,23 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr)
 // kind::i8 instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, M = 128, N = n.
 __device__ __forceinline__ uint32_t idesc_i8(int n)
 {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 struct Tile {
-    int b, tm, tn, ncols;
+    int b, tm, tn, mh, nh;   // mh / nh: 128-row halves of the tile that hold any row / column below ldg
 };
-// Lower-triangle enumeration: row tile tm (128 rows) meets column tiles tn (256 columns) with
-// tn * 256 <= tm * 128 + 127.  A tile whose right half lies wholly above the diagonal is computed 128 wide.
+// Lower-triangle enumeration of 256 x 256 tiles: row tile tm meets column tiles tn <= tm.
 __device__ __forceinline__ Tile decode_tile(int t, const GramPlan &p)
 {
     Tile r;
     r.b = t / p.tiles_per_block;
     int rem = t - r.b * p.tiles_per_block, tm = 0;
-    for (;; ++tm) {
-        const int c = tm / 2 + 1;
-        if (rem < c) break;
-        rem -= c;
-    }
+    for (; rem > tm; ++tm) rem -= tm + 1;
     r.tm = tm;
     r.tn = rem;
-    r.ncols = min(BN, (tm + 1) * BM - rem * BN);
+    r.mh = p.ldg - tm * BM > 128 ? 2 : 1;
+    r.nh = p.ldg - rem * BN > 128 ? 2 : 1;
     return r;
 }
 
@@ -200,9 +201,8 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const __grid_cons
     const uint32_t bars = base + STAGES * STAGE_BYTES;
     auto full = [&](int s) { return bars + 8u * s; };
     auto empty = [&](int s) { return bars + 8u * (STAGES + s); };
-    auto tfull = [&](int a) { return bars + 8u * (2 * STAGES + a); };
-    auto tempty = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
-    const uint32_t slot = bars + 8u * (2 * STAGES + 4);
+    const uint32_t tfull = bars + 8u * (2 * STAGES), tempty = bars + 8u * (2 * STAGES + 1);
+    const uint32_t slot = bars + 8u * (2 * STAGES + 2);
     volatile uint32_t *slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -213,10 +213,8 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const __grid_cons
             mbar_init(full(s), 1);
             mbar_init(empty(s), 1);
         }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(tfull(a), 1);
-            mbar_init(tempty(a), 4);
-        }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(TMEM_COLS) : "memory");
@@ -228,7 +226,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const __grid_cons
     const uint32_t tmem = *slot_ptr;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer (runs ahead into the next tile while the epilogue drains TMEM) =====
         int stage = 0, phase = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const Tile tl = decode_tile(t, p);
@@ -236,11 +234,13 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const __grid_cons
             for (int kb = 0; kb < nk; ++kb) {
                 if (lane == 0) {
                     mbar_wait(empty(stage), phase ^ 1);
-                    const uint32_t a = base + stage * STAGE_BYTES, bsm = a + A_BYTES;
-                    mbar_expect_tx(full(stage), A_BYTES + tl.ncols * BK);
-                    tma_load_2d(a, &tmap, full(stage), (k0 + kb) * BK, tl.tm * BM);
-                    tma_load_2d(bsm, &tmap, full(stage), (k0 + kb) * BK, tl.tn * BN);
-                    if (tl.ncols > 128) tma_load_2d(bsm + B_HALF_BYTES, &tmap, full(stage), (k0 + kb) * BK, tl.tn * BN + 128);
+                    const uint32_t a = base + stage * STAGE_BYTES;
+                    mbar_expect_tx(full(stage), (tl.mh + tl.nh) * HALF_BYTES);
+                    const int kc = (k0 + kb) * BK;
+                    tma_load_2d(a, &tmap, full(stage), kc, tl.tm * BM);
+                    if (tl.mh > 1) tma_load_2d(a + HALF_BYTES, &tmap, full(stage), kc, tl.tm * BM + 128);
+                    tma_load_2d(a + 2 * HALF_BYTES, &tmap, full(stage), kc, tl.tn * BN);
+                    if (tl.nh > 1) tma_load_2d(a + 3 * HALF_BYTES, &tmap, full(stage), kc, tl.tn * BN + 128);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -252,10 +252,9 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const __grid_cons
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
             const Tile tl = decode_tile(t, p);
             const int nk = p.kt0[tl.b + 1] - p.kt0[tl.b];
-            const int as = it & 1, aphase = (it >> 1) & 1;
-            const uint32_t idesc = idesc_i8(tl.ncols);
+            const uint32_t idesc = idesc_i8(128 * tl.nh);
             if (lane == 0) {
-                mbar_wait(tempty(as), aphase ^ 1);
+                mbar_wait(tempty, (it & 1) ^ 1);     // the epilogue of the previous tile has drained both accumulators
                 tc_fence_after();
             }
             __syncwarp();
@@ -264,59 +263,63 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const __grid_cons
                     mbar_wait(full(stage), phase);
                     tc_fence_after();
                     const uint32_t a = base + stage * STAGE_BYTES;
-                    const uint64_t adesc = smem_desc_sw128(a), bdesc = smem_desc_sw128(a + A_BYTES);
+                    const uint64_t a0 = smem_desc_sw128(a), a1 = smem_desc_sw128(a + HALF_BYTES);
+                    const uint64_t bd = smem_desc_sw128(a + 2 * HALF_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 32; ++k)   // one instruction consumes K = 32 bytes
-                        umma_i8(tmem + as * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < BK / 32; ++k) {   // one instruction consumes K = 32 bytes
+                        umma_i8(tmem, a0 + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                        if (tl.mh > 1) umma_i8(tmem + 256, a1 + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                    }
                     umma_commit(empty(stage));
-                    if (kb == nk - 1) umma_commit(tfull(as));
+                    if (kb == nk - 1) umma_commit(tfull);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> G (direct rows, and the mirrored transpose) =====
+        // ===== epilogue: TMEM -> registers -> G (direct rows, and the mirrored transpose below the diagonal) =====
         const int w = warp - 4;
         int it = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
             const Tile tl = decode_tile(t, p);
-            const int as = it & 1, aphase = (it >> 1) & 1;
-            mbar_wait(tfull(as), aphase);
+            mbar_wait(tfull, it & 1);
             tc_fence_after();
             int32_t *Gb = p.G + (size_t)tl.b * p.ldg * p.ldg;
-            const int row = tl.tm * BM + 32 * w + lane;
-            for (int c0 = 0; c0 < tl.ncols; c0 += 32) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem + (uint32_t)(as * BN + c0) + ((uint32_t)(32 * w) << 16);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-                    "tcgen05.wait::ld.sync.aligned;"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr)
-                    : "memory");
-                const int col0 = tl.tn * BN + c0;
-                if (row < p.ldg) {
-                    int32_t *dst = Gb + (size_t)row * p.ldg + col0;
+            const bool mirror = tl.tn < tl.tm;
+            for (int h = 0; h < tl.mh; ++h) {
+                const int row = tl.tm * BM + 128 * h + 32 * w + lane;
+                for (int c0 = 0; c0 < 128 * tl.nh; c0 += 32) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem + (uint32_t)(256 * h + c0) + ((uint32_t)(32 * w) << 16);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+                        "tcgen05.wait::ld.sync.aligned;"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr)
+                        : "memory");
+                    const int col0 = tl.tn * BN + c0;
+                    if (row < p.ldg) {
+                        int32_t *dst = Gb + (size_t)row * p.ldg + col0;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        if (col0 + j < p.ldg) *reinterpret_cast<uint4 *>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
-                // columns inside the diagonal 128 x 128 block are already written symmetrically above
-                if (col0 < tl.tm * BM && row < p.ldg) {
+                        for (int j = 0; j < 32; j += 4)
+                            if (col0 + j < p.ldg) *reinterpret_cast<uint4 *>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        if (mirror) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < p.ldg) Gb[(size_t)(col0 + j) * p.ldg + row] = (int32_t)v[j];
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < p.ldg) Gb[(size_t)(col0 + j) * p.ldg + row] = (int32_t)v[j];
+                        }
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty(as));
+            if (lane == 0) mbar_arrive(tempty);
         }
     }
 
@@ -842,8 +845,7 @@ cudaError_t run_pack_and_gram(int d, int64_t n, const int32_t *d_img, const Pack
     gp.ldg = lay.ldg;
     gp.nb = all_in_one ? 1 : pp.nb;   // all_in_one: one Gram matrix over the whole packed matrix (the padding is zeros)
     gp.tm_count = (lay.ldg + BM - 1) / BM;
-    gp.tiles_per_block = 0;
-    for (int tm = 0; tm < gp.tm_count; ++tm) gp.tiles_per_block += tm / 2 + 1;
+    gp.tiles_per_block = gp.tm_count * (gp.tm_count + 1) / 2;
     for (int b = 0; b <= pp.nb; ++b) gp.kt0[b] = pp.kt0[b] / 2;
     if (all_in_one) gp.kt0[1] = pp.kt0[pp.nb] / 2;
     gp.G = d_gram;
