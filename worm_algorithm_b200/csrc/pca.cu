@@ -50,25 +50,32 @@ __global__ void __launch_bounds__(256) pca_pack_kernel(const int32_t *__restrict
                                                        const PackPlan p)
 {
     __shared__ int tile[64][65];
+    __shared__ int csum[64];
     const int kt = blockIdx.x, c0 = blockIdx.y * 64, t = threadIdx.x;
     int b = 0;
     while (kt >= p.kt0[b + 1]) ++b;
     const int cfg_first = p.cfg0[b] + (kt - p.kt0[b]) * 64, cfg_end = p.cfg0[b + 1];
-    int mx = 0;
+    if (t < 64) csum[t] = 0;
+    int mx = 0, part = 0;
     {
         const int c = c0 + (t & 63);
-#pragma unroll 4
+        int v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {   // sixteen independent loads in flight per thread
+            const int cfg = cfg_first + (t >> 6) + 4 * i;
+            v[i] = (cfg < cfg_end && c < p.d) ? __ldcs(img + (size_t)cfg * p.d + c) : 0;
+        }
+#pragma unroll
         for (int i = 0; i < 16; ++i) {
-            const int k = (t >> 6) + 4 * i, cfg = cfg_first + k;
-            int v = 0;
-            if (cfg < cfg_end && c < p.d) v = img[(size_t)cfg * p.d + c];
-            tile[k][t & 63] = v;
-            mx = max(mx, abs(v));
+            tile[(t >> 6) + 4 * i][t & 63] = v[i];
+            mx = max(mx, abs(v[i]));
+            part += v[i];
         }
     }
     for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((t & 31) == 0 && mx) atomicMax(maxabs, mx);
     __syncthreads();
+    if (part) atomicAdd(&csum[t & 63], part);
     {
         const int k4 = t & 15;
 #pragma unroll
@@ -81,12 +88,9 @@ __global__ void __launch_bounds__(256) pca_pack_kernel(const int32_t *__restrict
             }
         }
     }
-    if (t < 64 && c0 + t < p.d) {
-        long long s = 0;
-#pragma unroll 8
-        for (int k = 0; k < 64; ++k) s += tile[k][t];
-        if (s) atomicAdd(reinterpret_cast<unsigned long long *>(colsum + (size_t)b * p.d + c0 + t), (unsigned long long)s);
-    }
+    __syncthreads();
+    if (t < 64 && c0 + t < p.d && csum[t])
+        atomicAdd(reinterpret_cast<unsigned long long *>(colsum + (size_t)b * p.d + c0 + t), (unsigned long long)(long long)csum[t]);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -373,6 +377,16 @@ __device__ __forceinline__ double s8_to_double(uint32_t w)
     return int_to_double((int)(signed char)(w >> (8 * B)));
 }
 
+// Packed signed bytes meet fp64 vectors without a conversion per element: with wx = word ^ 0x80808080 every
+// byte is u = x + 128 in [0, 255], and ONE byte permute builds the double 1 + u * 2^-12 (u dropped into
+// byte 1 of the high word of 1.0).  Then sum_k x_k y_k = 4096 * (sum_k (1 + u_k 2^-12) y_k - S) - 128 * S with
+// S = sum_k y_k, which costs one extra add per vector element instead of per matrix element.
+template <int B>
+__device__ __forceinline__ double biased_byte(uint32_t wx)
+{
+    return __hiloint2double((int)__byte_perm(wx, 0x3FF00000u, 0x7604u | (B << 4)), 0);
+}
+
 // first 512-configuration step of each jackknife block in the packed matrix
 struct StepPlan {
     int nb;
@@ -400,7 +414,7 @@ __global__ void __launch_bounds__(256) pca_xv_kernel(const int8_t *__restrict__ 
     const int rps = (d + XV_SLICES - 1) / XV_SLICES;
     const int c_begin = blockIdx.y * rps, c_end = min(d, c_begin + rps);
     const int8_t *col = xt + (size_t)step * 512 + lane * 16;
-    double acc[16];
+    double acc[16], vsum = 0.0;
 #pragma unroll
     for (int e = 0; e < 16; ++e) acc[e] = 0.0;
     constexpr int U = 4;
@@ -416,16 +430,19 @@ __global__ void __launch_bounds__(256) pca_xv_kernel(const int8_t *__restrict__ 
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+            const uint32_t w[4] = {x[u].x ^ 0x80808080u, x[u].y ^ 0x80808080u, x[u].z ^ 0x80808080u, x[u].w ^ 0x80808080u};
+            vsum += vc[u];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                acc[4 * q + 0] += s8_to_double<0>(w[q]) * vc[u];
-                acc[4 * q + 1] += s8_to_double<1>(w[q]) * vc[u];
-                acc[4 * q + 2] += s8_to_double<2>(w[q]) * vc[u];
-                acc[4 * q + 3] += s8_to_double<3>(w[q]) * vc[u];
+                acc[4 * q + 0] += biased_byte<0>(w[q]) * vc[u];
+                acc[4 * q + 1] += biased_byte<1>(w[q]) * vc[u];
+                acc[4 * q + 2] += biased_byte<2>(w[q]) * vc[u];
+                acc[4 * q + 3] += biased_byte<3>(w[q]) * vc[u];
             }
         }
     }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] = 4096.0 * (acc[e] - vsum) - 128.0 * vsum;
 #pragma unroll
     for (int e = 0; e < 16; ++e) red[warp][e][lane] = acc[e];
     __syncthreads();
@@ -454,7 +471,7 @@ __global__ void __launch_bounds__(256) pca_xty_kernel(const int8_t *__restrict__
     const int b = blockIdx.y, c0 = blockIdx.x * 32 + warp * 4;
     if (c0 >= ldg) return;
     const double2 *y2 = reinterpret_cast<const double2 *>(ysw);
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double acc[4] = {0.0, 0.0, 0.0, 0.0}, ysum = 0.0;
     for (int step = sp.st0[b]; step < sp.st0[b + 1]; ++step) {
         double2 y[8];
         uint4 x[4];
@@ -465,18 +482,20 @@ __global__ void __launch_bounds__(256) pca_xty_kernel(const int8_t *__restrict__
             x[r] = c0 + r < d ? *reinterpret_cast<const uint4 *>(xt + (size_t)(c0 + r) * ktot + (size_t)step * 512 + lane * 16)
                               : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
+        for (int i = 0; i < 8; ++i) ysum += y[i].x + y[i].y;
+#pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const uint32_t w[4] = {x[r].x, x[r].y, x[r].z, x[r].w};
+            const uint32_t w[4] = {x[r].x ^ 0x80808080u, x[r].y ^ 0x80808080u, x[r].z ^ 0x80808080u, x[r].w ^ 0x80808080u};
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                acc[r] += s8_to_double<0>(w[q]) * y[2 * q].x + s8_to_double<1>(w[q]) * y[2 * q].y +
-                          s8_to_double<2>(w[q]) * y[2 * q + 1].x + s8_to_double<3>(w[q]) * y[2 * q + 1].y;
+                acc[r] += biased_byte<0>(w[q]) * y[2 * q].x + biased_byte<1>(w[q]) * y[2 * q].y +
+                          biased_byte<2>(w[q]) * y[2 * q + 1].x + biased_byte<3>(w[q]) * y[2 * q + 1].y;
         }
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const double sum = warp_sum(acc[r]);
-        if (lane == 0 && c0 + r < ldg) WB[(size_t)(b + 1) * ldg + c0 + r] = sum;
+        const double sum = warp_sum(4096.0 * (acc[r] - ysum) - 128.0 * ysum);
+        if (lane == 0 && c0 + r < ldg) WB[(size_t)(b + 1) * ldg + c0 + r] = c0 + r < d ? sum : 0.0;
     }
 }
 
@@ -512,7 +531,10 @@ __global__ void __launch_bounds__(MV_WARPS * 32, 2) pca_matvec_full_kernel(const
             for (int i = threadIdx.x; i < jn * (MV_CHUNK / 2); i += MV_WARPS * 32) {
                 const int j = i / (MV_CHUNK / 2), cc = (i % (MV_CHUNK / 2)) * 2;
                 const bool ok = c0 + cc < ldg;
-                cp_async16(vs_base + (uint32_t)(((buf * MV_JC + j) * MV_CHUNK + cc) * 8),
+                // lane-major slots: lane l's columns 4l .. 4l+3 of each 128-column half sit in slots
+                // (2h) * 32 + l and (2h + 1) * 32 + l, so the 16-byte shared loads below are conflict free
+                const int slot = ((cc >> 7) * 2 + ((cc & 3) >> 1)) * 32 + ((cc & 127) >> 2);
+                cp_async16(vs_base + (uint32_t)(((buf * MV_JC + j) * MV_CHUNK + 2 * slot) * 8),
                            ok ? V + (size_t)(j0 + j) * ldg + c0 + cc : V, ok ? 16u : 0u);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -550,8 +572,8 @@ __global__ void __launch_bounds__(MV_WARPS * 32, 2) pca_matvec_full_kernel(const
                 if (j < jn) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const double2 va = *reinterpret_cast<const double2 *>(&vs[buf][j][128 * h + lane * 4]);
-                        const double2 vb = *reinterpret_cast<const double2 *>(&vs[buf][j][128 * h + lane * 4 + 2]);
+                        const double2 va = *reinterpret_cast<const double2 *>(&vs[buf][j][2 * ((2 * h) * 32 + lane)]);
+                        const double2 vb = *reinterpret_cast<const double2 *>(&vs[buf][j][2 * ((2 * h + 1) * 32 + lane)]);
 #pragma unroll
                         for (int r = 0; r < MV_ROWS; ++r) acc[r][j] += dot4(gcur[h][r], va, vb);
                     }
