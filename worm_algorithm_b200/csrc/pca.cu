@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(256) pca_pack_kernel(const int32_t *__restrict
         }
     }
     for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((t & 31) == 0 && mx) atomicMax(maxabs, mx);
+    // one address for the whole grid: only touch it when this warp would raise it
+    if ((t & 31) == 0 && mx > *reinterpret_cast<volatile int *>(maxabs)) atomicMax(maxabs, mx);
     __syncthreads();
     if (part) atomicAdd(&csum[t & 63], part);
     {
