@@ -567,6 +567,20 @@ __global__ void __launch_bounds__(MV_WARPS * 32, 2) pca_matvec_full_kernel(const
             } else {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
+            // the matrix words become doubles ONCE per chunk (the asm keeps the compiler from redoing the
+            // conversion inside every vector's branch, which doubled the fp64 work of this kernel)
+            double gd[2][MV_ROWS][4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int r = 0; r < MV_ROWS; ++r) {
+                    gd[h][r][0] = int_to_double(gcur[h][r].x);
+                    gd[h][r][1] = int_to_double(gcur[h][r].y);
+                    gd[h][r][2] = int_to_double(gcur[h][r].z);
+                    gd[h][r][3] = int_to_double(gcur[h][r].w);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) asm volatile("" : "+d"(gd[h][r][e]));
+                }
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < MV_JC; ++j) {
@@ -576,7 +590,14 @@ __global__ void __launch_bounds__(MV_WARPS * 32, 2) pca_matvec_full_kernel(const
                         const double2 va = *reinterpret_cast<const double2 *>(&vs[buf][j][2 * ((2 * h) * 32 + lane)]);
                         const double2 vb = *reinterpret_cast<const double2 *>(&vs[buf][j][2 * ((2 * h + 1) * 32 + lane)]);
 #pragma unroll
-                        for (int r = 0; r < MV_ROWS; ++r) acc[r][j] += dot4(gcur[h][r], va, vb);
+                        for (int r = 0; r < MV_ROWS; ++r) {
+                            double a = acc[r][j];
+                            a = fma(gd[h][r][0], va.x, a);
+                            a = fma(gd[h][r][1], va.y, a);
+                            a = fma(gd[h][r][2], vb.x, a);
+                            a = fma(gd[h][r][3], vb.y, a);
+                            acc[r][j] = a;
+                        }
                     }
                 }
             }
