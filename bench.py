@@ -385,8 +385,14 @@ def bench_pca(torch, engine, dev, peaks, cpu: bool) -> dict:
     lib.worm_pca_timing(0)
     ops = float(n) * d * (d + 1)
     peak = 2.0 * float(peaks.get("bf16_tflops", 1627.0))
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("gram_kernel")
+    except (OSError, ValueError):
+        pass
     out = {"bound": "tensor", "kernel": "gram_kernel", "achieved": ops / (best[2] * 1e-3) / 1e12, "peak": peak,
-           "unit": "Top/s (int8)", "frac": ops / (best[2] * 1e-3) / 1e12 / peak, "traffic": None,
+           "unit": "Top/s (int8)", "frac": ops / (best[2] * 1e-3) / 1e12 / peak, "traffic": traffic,
            "peak_source": "2 x bf16_tflops of MEASURED_PEAKS.json (no measured int8 figure; int8 dense is 2x bf16 nominally)",
            "alg_ops": "2 x n x d(d+1)/2, n = %d images, d = %d pixels" % (n, d),
            "stage_ms": {"pack": best[0], "gate": best[1], "gram": best[2], "iterate": best[3]},
