@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const __grid_cons
 // ---------------------------------------------------------------------------------------------------
 // 3. power iteration on the nj = 1 + nb problems A_0 = G_full, A_j = G_full - X_{j-1}^T X_{j-1}
 // ---------------------------------------------------------------------------------------------------
-constexpr int MV_ROWS = 2, MV_JC = 12, MV_WARPS = 8, MV_BATCH = 8;
+constexpr int MV_ROWS = 2, MV_JC = 12, MV_WARPS = 8, MV_BATCH = 4;
 
 // iteration state shared by the kernels of one worm_pca call
 struct IterState {
@@ -419,9 +419,8 @@ __global__ void __launch_bounds__(256) pca_xv_kernel(const int8_t *__restrict__ 
 #pragma unroll
     for (int e = 0; e < 16; ++e) acc[e] = 0.0;
     constexpr int U = 4;
-    for (int c = c_begin + warp; c < c_end; c += 8 * U) {
-        uint4 x[U];
-        double vc[U];
+    // software pipeline: the loads of the next batch of rows are in flight while this one is consumed
+    auto load = [&](int c, uint4 (&x)[U], double (&vc)[U]) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int cc = c + 8 * u;
@@ -429,6 +428,12 @@ __global__ void __launch_bounds__(256) pca_xv_kernel(const int8_t *__restrict__ 
             x[u] = ok ? *reinterpret_cast<const uint4 *>(col + (size_t)cc * ktot) : make_uint4(0u, 0u, 0u, 0u);
             vc[u] = ok ? v[cc] : 0.0;
         }
+    };
+    uint4 x[U], xn[U];
+    double vc[U], vn[U];
+    load(c_begin + warp, x, vc);
+    for (int c = c_begin + warp; c < c_end; c += 8 * U) {
+        load(c + 8 * U, xn, vn);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t w[4] = {x[u].x ^ 0x80808080u, x[u].y ^ 0x80808080u, x[u].z ^ 0x80808080u, x[u].w ^ 0x80808080u};
@@ -440,6 +445,11 @@ __global__ void __launch_bounds__(256) pca_xv_kernel(const int8_t *__restrict__ 
                 acc[4 * q + 2] += biased_byte<2>(w[q]) * vc[u];
                 acc[4 * q + 3] += biased_byte<3>(w[q]) * vc[u];
             }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            x[u] = xn[u];
+            vc[u] = vn[u];
         }
     }
 #pragma unroll
@@ -473,25 +483,37 @@ __global__ void __launch_bounds__(256) pca_xty_kernel(const int8_t *__restrict__
     if (c0 >= ldg) return;
     const double2 *y2 = reinterpret_cast<const double2 *>(ysw);
     double acc[4] = {0.0, 0.0, 0.0, 0.0}, ysum = 0.0;
-    for (int step = sp.st0[b]; step < sp.st0[b + 1]; ++step) {
-        double2 y[8];
-        uint4 x[4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = y2[(size_t)(step * 8 + i) * 32 + lane];
+    auto load_x = [&](int step, uint4 (&x)[4]) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-            x[r] = c0 + r < d ? *reinterpret_cast<const uint4 *>(xt + (size_t)(c0 + r) * ktot + (size_t)step * 512 + lane * 16)
-                              : make_uint4(0u, 0u, 0u, 0u);
+            x[r] = (c0 + r < d && step < sp.st0[b + 1])
+                       ? *reinterpret_cast<const uint4 *>(xt + (size_t)(c0 + r) * ktot + (size_t)step * 512 + lane * 16)
+                       : make_uint4(0u, 0u, 0u, 0u);
+    };
+    uint4 x[4], xn[4];
+    load_x(sp.st0[b], x);
+    for (int step = sp.st0[b]; step < sp.st0[b + 1]; ++step) {
+        double2 y[8];
+        load_x(step + 1, xn);                                  // in flight while this step is consumed
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = y2[(size_t)(step * 8 + i) * 32 + lane];
 #pragma unroll
         for (int i = 0; i < 8; ++i) ysum += y[i].x + y[i].y;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const uint32_t w[4] = {x[r].x ^ 0x80808080u, x[r].y ^ 0x80808080u, x[r].z ^ 0x80808080u, x[r].w ^ 0x80808080u};
+            double a = acc[r];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                acc[r] += biased_byte<0>(w[q]) * y[2 * q].x + biased_byte<1>(w[q]) * y[2 * q].y +
-                          biased_byte<2>(w[q]) * y[2 * q + 1].x + biased_byte<3>(w[q]) * y[2 * q + 1].y;
+            for (int q = 0; q < 4; ++q) {
+                a = fma(biased_byte<0>(w[q]), y[2 * q].x, a);
+                a = fma(biased_byte<1>(w[q]), y[2 * q].y, a);
+                a = fma(biased_byte<2>(w[q]), y[2 * q + 1].x, a);
+                a = fma(biased_byte<3>(w[q]), y[2 * q + 1].y, a);
+            }
+            acc[r] = a;
         }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) x[r] = xn[r];
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {

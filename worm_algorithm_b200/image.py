@@ -47,18 +47,14 @@ class Image(object):
                 raise FileNotFoundError("Unable to load from {}".format(image))
         else:
             self._image_orig = bytescale(image)
-        image_shape = self._image_orig.shape
-        if len(image_shape) == 1:
-            self._Nx = int(np.sqrt(image_shape[0]))
-            self._Ny = self._Nx
-            self._image_flat = self._image_orig
+        orig = self._image_orig
+        if orig.ndim == 1:                                   # flattened square image (image.py:26-29)
+            self._Nx = self._Ny = int(np.sqrt(orig.shape[0]))
         else:
-            self._Nx, self._Ny = self._image_orig.shape
-            self._image_flat = self._image_orig.flatten()
-        self._image = np.reshape(1 - self._image_flat / 255.0, (self._Nx, self._Ny))
-        self._image_cropped = None
-        self._image_bw = None
-        self._image_links = None
+            self._Nx, self._Ny = orig.shape
+        self._image_flat = orig.reshape(-1)
+        self._image = (1 - self._image_flat / 255.0).reshape(self._Nx, self._Ny)
+        self._image_cropped = self._image_bw = self._image_links = None
 
     def crop(self, x_start, y_start, x_end, y_end):
         """image.py:38-44."""

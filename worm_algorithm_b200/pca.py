@@ -51,34 +51,22 @@ class PrincipalComponent(object):
 
     def __init__(self, L, block_val=None, num_blocks=10, data_dir=None, save_dir=None, save=True, load=False,
                  verbose=False, device=None):
-        self._L = L
-        self._block_val = block_val
-        self._num_blocks = num_blocks
-        self._verbose = verbose
-        self._device = device
+        self._L, self._block_val, self._num_blocks = L, block_val, num_blocks
+        self._verbose, self._device = verbose, device
         self._temps = []
-        self._err = {}
-        self._eig_vals = {}
-        self._eig_vecs = {}
-        self._leading_eig_val = {}
-        if data_dir is None:
-            if block_val is None:
-                self._data_dir = '../data/configs/{}_lattice/separated_data/'.format(L)
-            else:
-                self._data_dir = '../data/blocked_configs/{}_lattice/double_bonds_{}/'.format(L, block_val)
-        else:
+        self._err, self._eig_vals, self._eig_vecs, self._leading_eig_val = {}, {}, {}, {}
+        # default directories of pca.py:50-71: raw configurations, or the blocked ones of a given scheme
+        sub = '' if block_val is None else 'double_bonds_{}/'.format(block_val)
+        if data_dir is not None:
             self._data_dir = data_dir
-        if save_dir is None:
-            if block_val is None:
-                self._save_dir = '../data/pca/{}_lattice/'.format(L)
-            else:
-                self._save_dir = '../data/pca/{}_lattice/double_bonds_{}/'.format(L, block_val)
+        elif block_val is None:
+            self._data_dir = '../data/configs/{}_lattice/separated_data/'.format(L)
         else:
-            self._save_dir = save_dir
-        config_files = os.listdir(self._data_dir)
-        self._config_files = sorted([os.path.join(self._data_dir, i) for i in config_files if i.endswith('.txt')])
-        temp_strings = [i.split('_')[-1].rstrip('.txt') for i in config_files]
-        self._temp_strings = [i.rstrip('0') for i in temp_strings]
+            self._data_dir = '../data/blocked_configs/{}_lattice/'.format(L) + sub
+        self._save_dir = save_dir if save_dir is not None else '../data/pca/{}_lattice/'.format(L) + sub
+        names = [f for f in os.listdir(self._data_dir)]
+        self._config_files = sorted(os.path.join(self._data_dir, f) for f in names if f.endswith('.txt'))
+        self._temp_strings = [f.split('_')[-1].rstrip('.txt').rstrip('0') for f in names]
         if not load:
             self._PCA()
             if save:
