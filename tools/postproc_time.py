@@ -30,3 +30,11 @@ for L, n in ((32, 65536), (64, 16384), (128, 4096)):
     print("blockT L=%3d n=%6d: %.3f ms  %.0f GB/s algorithmic (%.2f)" % (L, n, t * 1e3, b / t / 1e9, b / t / 1e9 / peak))
     t = timeit(lambda: engine.count(img)); b = n * 16 * L * L
     print("count  L=%3d n=%6d: %.3f ms  %.0f GB/s algorithmic (%.2f)" % (L, n, t * 1e3, b / t / 1e9, b / t / 1e9 / peak))
+
+# boundary extraction (image_analysis/image.py:46-80): all images x cutoffs in one launch
+for (n, N, m) in ((4096, 64, 8), (16384, 28, 16)):
+    imgs = torch.rand((n, N, N), device="cuda", dtype=torch.float64)
+    cut = np.linspace(0.05, 0.95, m)
+    t = timeit(lambda: engine.boundaries(imgs, cut), reps=5)
+    b = n * N * N * 8 + n * m * N * N * 16
+    print("bdry   %dx%d n=%6d m=%2d: %.3f ms  %.0f GB/s algorithmic (%.2f)" % (N, N, n, m, t * 1e3, b / t / 1e9, b / t / 1e9 / peak))

@@ -368,30 +368,62 @@ cudaError_t launch_block(int W, int64_t n, const int32_t *d_in, int32_t *d_out, 
 __global__ void __launch_bounds__(256) boundaries_kernel(int Nx, int Ny, int64_t n, int m, const double *__restrict__ img,
                                                          const double *__restrict__ cutoffs, int32_t *__restrict__ out)
 {
-    const int64_t sites = (int64_t)Nx * Ny, total = n * m * sites;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t im = i / sites;                 // image-major, cutoff-minor: im = image * m + cutoff
-        const int s = (int)(i - im * sites);
-        const int x = s / Ny, y = s - x * Ny;
-        const double cut = cutoffs[im % m];
-        const double *src = img + (im / m) * sites;
-        const int xm = x ? x - 1 : Nx - 1, ym = y ? y - 1 : Ny - 1;
-        const int b = src[(size_t)x * Ny + y] >= cut, bxm = src[(size_t)xm * Ny + y] >= cut;
-        const int bym = src[(size_t)x * Ny + ym] >= cut, bxy = src[(size_t)xm * Ny + ym] >= cut;
-        const int l0 = b ^ bym, l1 = b ^ bxm;
-        const int l0_up = bxm ^ bxy, l1_left = bym ^ bxy;
-        int32_t *dst = out + im * 4 * sites + (size_t)(2 * x) * (2 * Ny) + 2 * y;
-        *reinterpret_cast<int2 *>(dst) = make_int2((l0 | l1 | l0_up | l1_left) ? 1 : 0, l1);
-        *reinterpret_cast<int2 *>(dst + 2 * Ny) = make_int2(l0, 0);
-    }
+    // generic shape: one thread per site; blockIdx.x = image * m + cutoff, blockIdx.y = block of sites
+    const int sites = Nx * Ny;
+    const int64_t im = blockIdx.x;
+    const int s = blockIdx.y * blockDim.x + threadIdx.x;
+    if (s >= sites) return;
+    const int x = s / Ny, y = s - x * Ny;
+    const double cut = cutoffs[im % m];
+    const double *src = img + (im / m) * sites;
+    const int xm = x ? x - 1 : Nx - 1, ym = y ? y - 1 : Ny - 1;
+    const int b = src[(size_t)x * Ny + y] >= cut, bxm = src[(size_t)xm * Ny + y] >= cut;
+    const int bym = src[(size_t)x * Ny + ym] >= cut, bxy = src[(size_t)xm * Ny + ym] >= cut;
+    const int l0 = b ^ bym, l1 = b ^ bxm;
+    const int l0_up = bxm ^ bxy, l1_left = bym ^ bxy;
+    int32_t *dst = out + im * 4 * sites + (size_t)(2 * x) * (2 * Ny) + 2 * y;
+    *reinterpret_cast<int2 *>(dst) = make_int2((l0 | l1 | l0_up | l1_left) ? 1 : 0, l1);
+    *reinterpret_cast<int2 *>(dst + 2 * Ny) = make_int2(l0, 0);
+}
+
+// Even Ny: one thread per pair of sites (x, 2k), (x, 2k+1): two 16-byte stores, six pixel reads.
+__global__ void __launch_bounds__(256) boundaries_kernel_pair(int Nx, int Ny, int64_t n, int m, const double *__restrict__ img,
+                                                              const double *__restrict__ cutoffs, int32_t *__restrict__ out)
+{
+    const int hy = Ny >> 1, pairs = Nx * hy;
+    const int64_t im = blockIdx.x;
+    const int s = blockIdx.y * blockDim.x + threadIdx.x;
+    if (s >= pairs) return;
+    const int x = s / hy, y = 2 * (s - x * hy);
+    const double cut = cutoffs[im % m];
+    const double *row = img + (im / m) * (size_t)Nx * Ny + (size_t)x * Ny;
+    const double *rowm = img + (im / m) * (size_t)Nx * Ny + (size_t)(x ? x - 1 : Nx - 1) * Ny;
+    const int ym = y ? y - 1 : Ny - 1;
+    const double2 c = *reinterpret_cast<const double2 *>(row + y), u = *reinterpret_cast<const double2 *>(rowm + y);
+    const int b0 = c.x >= cut, b1 = c.y >= cut, u0 = u.x >= cut, u1 = u.y >= cut;
+    const int bl = row[ym] >= cut, ul = rowm[ym] >= cut;     // left neighbours of the pair
+    // site (x, y): link0 = b0 ^ bl, link1 = b0 ^ u0, link0 of (x-1, y) = u0 ^ ul, link1 of (x, y-1) = bl ^ ul
+    const int l0a = b0 ^ bl, l1a = b0 ^ u0, sa = l0a | l1a | (u0 ^ ul) | (bl ^ ul);
+    // site (x, y+1): left neighbour is (x, y)
+    const int l0b = b1 ^ b0, l1b = b1 ^ u1, sb = l0b | l1b | (u1 ^ u0) | (b0 ^ u0);
+    int32_t *dst = out + im * 4 * (int64_t)Nx * Ny + (size_t)(2 * x) * (2 * Ny) + 2 * y;
+    *reinterpret_cast<int4 *>(dst) = make_int4(sa, l1a, sb, l1b);
+    *reinterpret_cast<int4 *>(dst + 2 * Ny) = make_int4(l0a, 0, l0b, 0);
 }
 
 cudaError_t launch_boundaries(int Nx, int Ny, int64_t n, int m, const double *d_img, const double *d_cutoffs, int32_t *d_out,
                               cudaStream_t st)
 {
-    const int64_t items = n * m * (int64_t)Nx * Ny;
-    if (items == 0) return cudaSuccess;
-    boundaries_kernel<<<grid_for(items, 256), 256, 0, st>>>(Nx, Ny, n, m, d_img, d_cutoffs, d_out);
+    const int64_t ims = n * m;
+    if (ims == 0) return cudaSuccess;
+    if (ims > 0x7fffffffll) return cudaErrorInvalidValue;
+    const bool pair = (Ny & 1) == 0 && ((uintptr_t)d_img & 15) == 0 && ((uintptr_t)d_out & 15) == 0;
+    const int items = pair ? Nx * (Ny / 2) : Nx * Ny;
+    const int nblk = (items + 255) / 256;
+    const int threads = ((items + nblk - 1) / nblk + 31) / 32 * 32;   // even split of an image over its blocks
+    const dim3 grid((unsigned)ims, (unsigned)nblk);
+    if (pair) boundaries_kernel_pair<<<grid, threads, 0, st>>>(Nx, Ny, n, m, d_img, d_cutoffs, d_out);
+    else boundaries_kernel<<<grid, threads, 0, st>>>(Nx, Ny, n, m, d_img, d_cutoffs, d_out);
     return cudaGetLastError();
 }
 
