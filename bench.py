@@ -201,6 +201,7 @@ def run_b200_arm(a) -> None:
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the JSON line only
         td.init_process_group("nccl", device_id=dev)
     _lib.lib()                                                    # fail loudly if the .so is missing
 
