@@ -278,17 +278,19 @@ def run_b200_arm(a) -> None:
                              device=dev, lanes_per_chain=a.lanes, rank=rank, world_size=world)
         return sim
     e2e_pass()
-    barrier()
-    t0 = time.perf_counter()
     sim = None
+    pass_s = []
     for _ in range(a.e2e_steps):
-        sim = e2e_pass()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        barrier()
+        t0 = time.perf_counter()
+        sim = e2e_pass()                       # returns with the result dicts on the host (it synchronises)
+        barrier()
+        pass_s.append(time.perf_counter() - t0)
+    te = torch.tensor(pass_s, dtype=torch.float64, device=dev)
     if world > 1:
-        td.all_reduce(te, op=td.ReduceOp.MAX)
-    e2e_value = steps_per_pass_job * a.e2e_steps / float(te[0])
+        td.all_reduce(te, op=td.ReduceOp.MAX)  # a pass ends when the slowest rank has its results
+    pass_s = [float(x) for x in te]
+    e2e_value = steps_per_pass_job / float(np.median(pass_s))      # median pass: host jitter of one pass is not the metric
     h2d = n * 32 + n * 4                      # PhiloxChain records + group index
     d2h = N_T * 8 * 8                         # reduced per-temperature sums
 
@@ -345,7 +347,8 @@ def run_b200_arm(a) -> None:
         "config": workload_config(a, world),
         "sweeps_per_s": value / (2 * L_BENCH * L_BENCH),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "WormSimulation(L=32, T_arr=64 temps, n_replicas=64/GPU, rng='philox')", "passes": a.e2e_steps},
+                "api": "WormSimulation(L=32, T_arr=64 temps, n_replicas=64/GPU, rng='philox')", "passes": a.e2e_steps,
+                "ms_per_pass": [x * 1e3 for x in pass_s], "timing": "wall clock per pass, barrier + synchronize on both sides, max over ranks, median over passes"},
         "gpu_launches": a.steps * st.launches_per_run,
         "clocks": clocks,
         "roofline": roofline,
@@ -448,7 +451,7 @@ def main() -> None:
     p.add_argument("--num-steps", type=int, default=10_000_000, help="worm steps per chain per pass")
     p.add_argument("--algo", default="taylor", choices=["taylor", "binary"])
     p.add_argument("--lanes", type=int, default=0)
-    p.add_argument("--e2e-steps", type=int, default=2)
+    p.add_argument("--e2e-steps", type=int, default=3)
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--cpu-steps", type=int, default=10_000_000)
     p.add_argument("--cpu-runs-per-core", type=int, default=4)
