@@ -150,3 +150,29 @@ def test_pca_host_entry_point(eng, gold):
     evs, _, c, _ = pca_oracle.pca_leading(x, nb)
     np.testing.assert_allclose(ev, evs, rtol=1e-9)
     np.testing.assert_allclose(comp, c, atol=1e-9)
+
+
+def test_pca_edge_cases(eng):
+    """One block (no resampling), one configuration per block, constant and all-zero images, d not a multiple of 4."""
+    import torch
+    from oracle import pca_oracle
+    rng = np.random.default_rng(77)
+    x = (rng.random((90, 30)) < 0.4).astype(np.int32)
+    res = eng.pca(torch.from_numpy(x).cuda(), 1)                      # num_blocks = 1: explained[1] is the empty set -> 0
+    ev0, _, comp = pca_oracle.leading(x)
+    assert abs(float(res.explained[0]) - ev0) <= 1e-9 * ev0 and float(res.explained[1]) == 0.0
+    np.testing.assert_allclose(res.component.cpu().numpy(), comp, atol=1e-9)
+    x = (rng.random((12, 9)) < 0.5).astype(np.int32)                  # n == num_blocks: every block is one configuration
+    res = eng.pca(torch.from_numpy(x).cuda(), 12)
+    np.testing.assert_allclose(res.explained.cpu().numpy(), pca_oracle.pca_leading(x, 12)[0], rtol=1e-8, atol=1e-12)
+    zeros = torch.zeros((40, 16), dtype=torch.int32, device="cuda")   # nothing to decompose
+    res = eng.pca(zeros, 4)
+    assert np.all(res.explained.cpu().numpy() == 0.0) and res.iters <= 4
+    ones = torch.ones((40, 16), dtype=torch.int32, device="cuda")     # rank one, zero variance along it
+    res = eng.pca(ones, 4)
+    np.testing.assert_allclose(res.explained.cpu().numpy(), 0.0, atol=1e-9)
+    np.testing.assert_allclose(res.sigma2.cpu().numpy()[0], 40 * 16, rtol=1e-12)
+    neg = rng.integers(-3, 4, (200, 21)).astype(np.int32)             # signed values, odd d
+    res = eng.pca(torch.from_numpy(neg).cuda(), 5, max_iters=20000, tol=1e-10)
+    evs = pca_oracle.pca_leading(neg, 5)[0]
+    np.testing.assert_allclose(res.explained.cpu().numpy(), evs, rtol=1e-6)
