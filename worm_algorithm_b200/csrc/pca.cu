@@ -394,7 +394,7 @@ struct StepPlan {
     int st0[PCA_MAX_BLOCKS + 1];
 };
 
-constexpr int XV_SLICES = 8;   // pixel-row slices per 512-configuration step (grid.y of pca_xv_kernel)
+constexpr int XV_SLICES = 16;  // pixel-row slices per 512-configuration step (grid.y of pca_xv_kernel)
 
 // y = X_b v_{b+1} for every block b at once: y[k] = sum_c Xt[c][k] * V_{b(k)+1}[c].
 // blockIdx.x = 512-configuration step (one jackknife block per step), blockIdx.y = slice of pixel rows;
@@ -665,10 +665,10 @@ __global__ void __launch_bounds__(256) pca_coltot_kernel(const long long *__rest
     coltot[c] = s;
 }
 
-__global__ void __launch_bounds__(256) pca_init_kernel(const long long *__restrict__ colsum, const long long *__restrict__ coltot,
+__global__ void __launch_bounds__(1024) pca_init_kernel(const long long *__restrict__ colsum, const long long *__restrict__ coltot,
                                                        double *__restrict__ V, int d, int ldg)
 {
-    __shared__ double scratch[8];
+    __shared__ double scratch[32];
     const int j = blockIdx.x;
     double *v = V + (size_t)j * ldg;
     double ss = 0.0;
@@ -694,11 +694,11 @@ __global__ void __launch_bounds__(256) pca_init_kernel(const long long *__restri
 }
 
 // W_j = WA_j - WB_j;  stats[j] = { Rayleigh quotient V.W (|V| = 1), |V_new - V|^2 };  V <- W / |W|.
-__global__ void __launch_bounds__(256) pca_update_kernel(double *__restrict__ V, const double *__restrict__ WA,
+__global__ void __launch_bounds__(1024) pca_update_kernel(double *__restrict__ V, const double *__restrict__ WA,
                                                          const double *__restrict__ WB, double *__restrict__ stats, int ldg,
                                                          int nj, double tol2, IterState *state, int slot)
 {
-    __shared__ double scratch[8];
+    __shared__ double scratch[32];
     if (iter_finished(state, slot, nj)) {
         if (threadIdx.x == 0) state->done = 1;
         return;
@@ -733,13 +733,13 @@ __global__ void __launch_bounds__(256) pca_update_kernel(double *__restrict__ V,
 }
 
 // explained variance of the projection on v_j: mean((X v)^2) - mean(X v)^2 over the included configurations
-__global__ void __launch_bounds__(256) pca_finish_kernel(const double *__restrict__ V, const double *__restrict__ stats,
+__global__ void __launch_bounds__(1024) pca_finish_kernel(const double *__restrict__ V, const double *__restrict__ stats,
                                                          const long long *__restrict__ colsum, const long long *__restrict__ coltot,
                                                          const PackPlan p, int ldg,
                                                          double *__restrict__ explained, double *__restrict__ sigma2,
                                                          double *__restrict__ component)
 {
-    __shared__ double scratch[8];
+    __shared__ double scratch[32];
     const int j = blockIdx.x;
     const double *v = V + (size_t)j * ldg;
     double sv = 0.0, vs = 0.0;
@@ -979,7 +979,8 @@ cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_i
     double *stats = reinterpret_cast<double *>(ws + lay.stats);
     long long *coltot = reinterpret_cast<long long *>(ws + lay.coltot);
     pca_coltot_kernel<<<(d + 255) / 256, 256, 0, st>>>(colsum, coltot, d, nb);
-    pca_init_kernel<<<nj, 256, 0, st>>>(colsum, coltot, V, d, ldg);
+    const int vt = ldg >= 2048 ? 1024 : 256;   // threads of the per-problem vector kernels (latency bound: one block per problem)
+    pca_init_kernel<<<nj, vt, 0, st>>>(colsum, coltot, V, d, ldg);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
     double *WB = reinterpret_cast<double *>(ws + lay.wb);
@@ -1011,7 +1012,7 @@ cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_i
             pca_xv_kernel<<<dim3((unsigned)sp.st0[nb], XV_SLICES), 256, 0, st>>>(xt, V, ysw, d, ldg, pp.ktot, sp, state, i);
             pca_xty_kernel<<<dim3((unsigned)((ldg + 31) / 32), (unsigned)nb), 256, 0, st>>>(xt, ysw, WB, d, ldg, pp.ktot, sp, state, i);
             pca_matvec_full_kernel<<<mv_rows, MV_WARPS * 32, MV_FULL_SMEM, st>>>(G, V, W, ldg, nj, state, i);
-            pca_update_kernel<<<nj, 256, 0, st>>>(V, W, WB, stats, ldg, nj, tol * tol, state, i);
+            pca_update_kernel<<<nj, vt, 0, st>>>(V, W, WB, stats, ldg, nj, tol * tol, state, i);
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if ((e = cudaMemcpyAsync(h_stats.data(), stats, h_stats.size() * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
@@ -1026,7 +1027,7 @@ cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_i
     }
     // stats[2j] is the Rayleigh quotient of the vector BEFORE the last normalisation; at convergence it
     // differs from that of V by O(tol^2).
-    pca_finish_kernel<<<nj, 256, 0, st>>>(V, stats, colsum, coltot, pp, ldg, d_explained, d_sigma2, d_component);
+    pca_finish_kernel<<<nj, vt, 0, st>>>(V, stats, colsum, coltot, pp, ldg, d_explained, d_sigma2, d_component);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     tm.mark();
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
