@@ -15,7 +15,8 @@
 //                        the whole packed matrix); worm_pca_gram exposes the per-block matrices.
 //   3. power iteration   for the 1 + num_blocks problems at once (full data and each delete-one
 //                        set): A_j v_j = G_full v_j - X_b^T (X_b v_j), b = j - 1.  G_full meets all
-//                        vectors in one pass (pca_matvec_full_kernel); the deleted block's part goes
+//                        vectors in one pass (pca_matvec_sym_kernel: G is symmetric, so a lane owning row r walks the
+//                        coalesced column r of the rows above it); the deleted block's part goes
 //                        through the int8 configurations themselves (pca_xv_kernel, pca_xty_kernel:
 //                        two passes over 1 byte per pixel instead of a d x d matrix per block).
 //                        Matrices are exact integers, vectors and accumulation fp64.
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const __grid_cons
 // ---------------------------------------------------------------------------------------------------
 // 3. power iteration on the nj = 1 + nb problems A_0 = G_full, A_j = G_full - X_{j-1}^T X_{j-1}
 // ---------------------------------------------------------------------------------------------------
-constexpr int MV_ROWS = 2, MV_JC = 12, MV_WARPS = 8, MV_BATCH = 4;
+constexpr int MV_BATCH = 4;   // iterations queued per host round trip
 
 // iteration state shared by the kernels of one worm_pca call
 struct IterState {
@@ -366,26 +367,11 @@ __device__ __forceinline__ double int_to_double(int g)
     return __hiloint2double(0x43300000, g ^ 0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
 }
 
-__device__ __forceinline__ double dot4(const int4 g, const double2 va, const double2 vb)
-{
-    return int_to_double(g.x) * va.x + int_to_double(g.y) * va.y + int_to_double(g.z) * vb.x + int_to_double(g.w) * vb.y;
-}
-
 // signed byte B of a 32-bit word -> double, exactly (sign extension, then the 2^52 trick)
 template <int B>
 __device__ __forceinline__ double s8_to_double(uint32_t w)
 {
     return int_to_double((int)(signed char)(w >> (8 * B)));
-}
-
-// Packed signed bytes meet fp64 vectors without a conversion per element: with wx = word ^ 0x80808080 every
-// byte is u = x + 128 in [0, 255], and ONE byte permute builds the double 1 + u * 2^-12 (u dropped into
-// byte 1 of the high word of 1.0).  Then sum_k x_k y_k = 4096 * (sum_k (1 + u_k 2^-12) y_k - S) - 128 * S with
-// S = sum_k y_k, which costs one extra add per vector element instead of per matrix element.
-template <int B>
-__device__ __forceinline__ double biased_byte(uint32_t wx)
-{
-    return __hiloint2double((int)__byte_perm(wx, 0x3FF00000u, 0x7604u | (B << 4)), 0);
 }
 
 // first 512-configuration step of each jackknife block in the packed matrix
@@ -415,7 +401,7 @@ __global__ void __launch_bounds__(256) pca_xv_kernel(const int8_t *__restrict__ 
     const int rps = (d + XV_SLICES - 1) / XV_SLICES;
     const int c_begin = blockIdx.y * rps, c_end = min(d, c_begin + rps);
     const int8_t *col = xt + (size_t)step * 512 + lane * 16;
-    double acc[16], vsum = 0.0;
+    double acc[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) acc[e] = 0.0;
     constexpr int U = 4;
@@ -436,14 +422,13 @@ __global__ void __launch_bounds__(256) pca_xv_kernel(const int8_t *__restrict__ 
         load(c + 8 * U, xn, vn);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t w[4] = {x[u].x ^ 0x80808080u, x[u].y ^ 0x80808080u, x[u].z ^ 0x80808080u, x[u].w ^ 0x80808080u};
-            vsum += vc[u];
+            const uint32_t w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                acc[4 * q + 0] += biased_byte<0>(w[q]) * vc[u];
-                acc[4 * q + 1] += biased_byte<1>(w[q]) * vc[u];
-                acc[4 * q + 2] += biased_byte<2>(w[q]) * vc[u];
-                acc[4 * q + 3] += biased_byte<3>(w[q]) * vc[u];
+                acc[4 * q + 0] = fma(s8_to_double<0>(w[q]), vc[u], acc[4 * q + 0]);
+                acc[4 * q + 1] = fma(s8_to_double<1>(w[q]), vc[u], acc[4 * q + 1]);
+                acc[4 * q + 2] = fma(s8_to_double<2>(w[q]), vc[u], acc[4 * q + 2]);
+                acc[4 * q + 3] = fma(s8_to_double<3>(w[q]), vc[u], acc[4 * q + 3]);
             }
         }
 #pragma unroll
@@ -452,8 +437,6 @@ __global__ void __launch_bounds__(256) pca_xv_kernel(const int8_t *__restrict__ 
             vc[u] = vn[u];
         }
     }
-#pragma unroll
-    for (int e = 0; e < 16; ++e) acc[e] = 4096.0 * (acc[e] - vsum) - 128.0 * vsum;
 #pragma unroll
     for (int e = 0; e < 16; ++e) red[warp][e][lane] = acc[e];
     __syncthreads();
@@ -482,7 +465,7 @@ __global__ void __launch_bounds__(256) pca_xty_kernel(const int8_t *__restrict__
     const int b = blockIdx.y, c0 = blockIdx.x * 32 + warp * 4;
     if (c0 >= ldg) return;
     const double2 *y2 = reinterpret_cast<const double2 *>(ysw);
-    double acc[4] = {0.0, 0.0, 0.0, 0.0}, ysum = 0.0;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
     auto load_x = [&](int step, uint4 (&x)[4]) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
@@ -498,17 +481,15 @@ __global__ void __launch_bounds__(256) pca_xty_kernel(const int8_t *__restrict__
 #pragma unroll
         for (int i = 0; i < 8; ++i) y[i] = y2[(size_t)(step * 8 + i) * 32 + lane];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ysum += y[i].x + y[i].y;
-#pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const uint32_t w[4] = {x[r].x ^ 0x80808080u, x[r].y ^ 0x80808080u, x[r].z ^ 0x80808080u, x[r].w ^ 0x80808080u};
+            const uint32_t w[4] = {x[r].x, x[r].y, x[r].z, x[r].w};
             double a = acc[r];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                a = fma(biased_byte<0>(w[q]), y[2 * q].x, a);
-                a = fma(biased_byte<1>(w[q]), y[2 * q].y, a);
-                a = fma(biased_byte<2>(w[q]), y[2 * q + 1].x, a);
-                a = fma(biased_byte<3>(w[q]), y[2 * q + 1].y, a);
+                a = fma(s8_to_double<0>(w[q]), y[2 * q].x, a);
+                a = fma(s8_to_double<1>(w[q]), y[2 * q].y, a);
+                a = fma(s8_to_double<2>(w[q]), y[2 * q + 1].x, a);
+                a = fma(s8_to_double<3>(w[q]), y[2 * q + 1].y, a);
             }
             acc[r] = a;
         }
@@ -517,127 +498,73 @@ __global__ void __launch_bounds__(256) pca_xty_kernel(const int8_t *__restrict__
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const double sum = warp_sum(4096.0 * (acc[r] - ysum) - 128.0 * ysum);
+        const double sum = warp_sum(acc[r]);
         if (lane == 0 && c0 + r < ldg) WB[(size_t)(b + 1) * ldg + c0 + r] = c0 + r < d ? sum : 0.0;
     }
 }
 
-// WA_j = G_full V_j for all nj problems.  One warp per MV_ROWS rows; the vectors of a 256-column chunk are
-// staged in shared memory once per block (cp.async, double buffered) and the matrix words of the next
-// chunk are in flight while the current one is consumed.
-constexpr int MV_CHUNK = 256;
-constexpr int MV_FULL_SMEM = 2 * MV_JC * MV_CHUNK * 8;
+// WA_j += G V_j for up to SYM_J problems, using the symmetry of G: lane l of a warp owns rows r0 + l and r0 + 32 + l
+// and walks down COLUMNS of those rows, i.e. along row c of G (G[c][r] = G[r][c]) -- a coalesced 128-byte
+// load per c, while V_j[c] is the same for every lane (one broadcast load of the transposed copy VT[c][j]).
+// No shared-memory staging of the vectors, no cross-lane reduction; the eight warps of a block take
+// interleaved c and are summed through shared memory, the SYM_SPLIT column ranges through fp64 atomics
+// (WA is zeroed before the launch).  fp64 issue (32 lanes/clk/SM) is the bound: nj d^2 FMAs.
+constexpr int SYM_J = 12, SYM_SPLIT = 4;
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes)
+__global__ void __launch_bounds__(256, 2) pca_matvec_sym_kernel(const int32_t *__restrict__ G, const double *__restrict__ VT,
+                                                                 double *__restrict__ WA, int ldg, int nj,
+                                                                 const IterState *state, int slot)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-
-__global__ void __launch_bounds__(MV_WARPS * 32, 2) pca_matvec_full_kernel(const int32_t *__restrict__ G, const double *__restrict__ V,
-                                                                            double *__restrict__ WA, int ldg, int nj,
-                                                                            const IterState *state, int slot)
-{
-    extern __shared__ __align__(16) uint8_t mv_smem[];
-    double (*vs)[MV_JC][MV_CHUNK] = reinterpret_cast<double (*)[MV_JC][MV_CHUNK]>(mv_smem);
+    __shared__ double red[8][2 * SYM_J][32];
     if (iter_finished(state, slot, nj)) return;
-    const int lane = threadIdx.x & 31;
-    const int r0 = (blockIdx.x * MV_WARPS + (threadIdx.x >> 5)) * MV_ROWS;
-    const int32_t *row[MV_ROWS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * 64, ra = r0 + lane, rb = r0 + 32 + lane;
+    const int cw = ((ldg + SYM_SPLIT - 1) / SYM_SPLIT + 7) & ~7;
+    const int cb = blockIdx.y * cw, ce = min(ldg, cb + cw);
+    const int j0 = blockIdx.z * SYM_J, jn = min(SYM_J, nj - j0);
+    const double2 *vt = reinterpret_cast<const double2 *>(VT + (size_t)blockIdx.z * ldg * SYM_J);
+    const bool oka = ra < ldg, okb = rb < ldg;
+    double acc[2][SYM_J];
 #pragma unroll
-    for (int r = 0; r < MV_ROWS; ++r) row[r] = G + (size_t)min(r0 + r, ldg - 1) * ldg;
-    const int nch = (ldg + MV_CHUNK - 1) / MV_CHUNK;
-    const uint32_t vs_base = (uint32_t)__cvta_generic_to_shared(mv_smem);
-
-    for (int j0 = 0; j0 < nj; j0 += MV_JC) {
-        const int jn = min(MV_JC, nj - j0);
-        auto fill = [&](int buf, int c0) {
-            for (int i = threadIdx.x; i < jn * (MV_CHUNK / 2); i += MV_WARPS * 32) {
-                const int j = i / (MV_CHUNK / 2), cc = (i % (MV_CHUNK / 2)) * 2;
-                const bool ok = c0 + cc < ldg;
-                // lane-major slots: lane l's columns 4l .. 4l+3 of each 128-column half sit in slots
-                // (2h) * 32 + l and (2h + 1) * 32 + l, so the 16-byte shared loads below are conflict free
-                const int slot = ((cc >> 7) * 2 + ((cc & 3) >> 1)) * 32 + ((cc & 127) >> 2);
-                cp_async16(vs_base + (uint32_t)(((buf * MV_JC + j) * MV_CHUNK + 2 * slot) * 8),
-                           ok ? V + (size_t)(j0 + j) * ldg + c0 + cc : V, ok ? 16u : 0u);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        auto load_g = [&](int4 (&g)[2][MV_ROWS], int c0) {
+    for (int j = 0; j < SYM_J; ++j) acc[0][j] = acc[1][j] = 0.0;
+    constexpr int U = 4;
+    for (int c = cb + warp; c < ce; c += 8 * U) {
+        int ga[U], gb[U];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = c0 + 128 * h + lane * 4;
-                const bool ok = c < ldg && r0 < ldg;
-#pragma unroll
-                for (int r = 0; r < MV_ROWS; ++r)
-                    g[h][r] = ok ? __ldcs(reinterpret_cast<const int4 *>(row[r] + c)) : make_int4(0, 0, 0, 0);
-            }
-        };
-        double acc[MV_ROWS][MV_JC];
-#pragma unroll
-        for (int r = 0; r < MV_ROWS; ++r)
-#pragma unroll
-            for (int j = 0; j < MV_JC; ++j) acc[r][j] = 0.0;
-        int4 gcur[2][MV_ROWS], gnext[2][MV_ROWS];
-        fill(0, 0);
-        load_g(gcur, 0);
-        for (int ci = 0; ci < nch; ++ci) {
-            const int buf = ci & 1;
-            if (ci + 1 < nch) {
-                fill(buf ^ 1, (ci + 1) * MV_CHUNK);
-                load_g(gnext, (ci + 1) * MV_CHUNK);
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-            } else {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-            }
-            // the matrix words become doubles ONCE per chunk (the asm keeps the compiler from redoing the
-            // conversion inside every vector's branch, which doubled the fp64 work of this kernel)
-            double gd[2][MV_ROWS][4];
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int r = 0; r < MV_ROWS; ++r) {
-                    gd[h][r][0] = int_to_double(gcur[h][r].x);
-                    gd[h][r][1] = int_to_double(gcur[h][r].y);
-                    gd[h][r][2] = int_to_double(gcur[h][r].z);
-                    gd[h][r][3] = int_to_double(gcur[h][r].w);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) asm volatile("" : "+d"(gd[h][r][e]));
-                }
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < MV_JC; ++j) {
-                if (j < jn) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const double2 va = *reinterpret_cast<const double2 *>(&vs[buf][j][2 * ((2 * h) * 32 + lane)]);
-                        const double2 vb = *reinterpret_cast<const double2 *>(&vs[buf][j][2 * ((2 * h + 1) * 32 + lane)]);
-#pragma unroll
-                        for (int r = 0; r < MV_ROWS; ++r) {
-                            double a = acc[r][j];
-                            a = fma(gd[h][r][0], va.x, a);
-                            a = fma(gd[h][r][1], va.y, a);
-                            a = fma(gd[h][r][2], vb.x, a);
-                            a = fma(gd[h][r][3], vb.y, a);
-                            acc[r][j] = a;
-                        }
-                    }
-                }
-            }
-            __syncthreads();   // buffer `buf` is refilled two chunks ahead
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int r = 0; r < MV_ROWS; ++r) gcur[h][r] = gnext[h][r];
+        for (int u = 0; u < U; ++u) {
+            const int cc = c + 8 * u;
+            const bool ok = cc < ce;
+            ga[u] = (ok && oka) ? __ldcs(G + (size_t)cc * ldg + ra) : 0;
+            gb[u] = (ok && okb) ? __ldcs(G + (size_t)cc * ldg + rb) : 0;
         }
 #pragma unroll
-        for (int j = 0; j < MV_JC; ++j) {
-            if (j < jn) {
+        for (int u = 0; u < U; ++u) {
+            const int cc = min(c + 8 * u, ce - 1);
+            const double da = int_to_double(ga[u]), db = int_to_double(gb[u]);
 #pragma unroll
-                for (int r = 0; r < MV_ROWS; ++r) {
-                    const double sum = warp_sum(acc[r][j]);
-                    if (lane == 0 && r0 + r < ldg) WA[(size_t)(j0 + j) * ldg + r0 + r] = sum;
-                }
+            for (int jj = 0; jj < SYM_J / 2; ++jj) {
+                const double2 v = vt[(size_t)cc * (SYM_J / 2) + jj];
+                acc[0][2 * jj] = fma(da, v.x, acc[0][2 * jj]);
+                acc[0][2 * jj + 1] = fma(da, v.y, acc[0][2 * jj + 1]);
+                acc[1][2 * jj] = fma(db, v.x, acc[1][2 * jj]);
+                acc[1][2 * jj + 1] = fma(db, v.y, acc[1][2 * jj + 1]);
             }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < SYM_J; ++j) {
+        red[warp][j][lane] = acc[0][j];
+        red[warp][SYM_J + j][lane] = acc[1][j];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 2 * SYM_J * 32; o += 256) {
+        const int l = o & 31, k = o >> 5;                       // k = half * SYM_J + j
+        const int j = k % SYM_J, row = r0 + (k / SYM_J) * 32 + l;
+        if (j < jn && row < ldg) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sum += red[w][k][l];
+            atomicAdd(WA + (size_t)(j0 + j) * ldg + row, sum);
         }
     }
 }
@@ -666,7 +593,7 @@ __global__ void __launch_bounds__(256) pca_coltot_kernel(const long long *__rest
 }
 
 __global__ void __launch_bounds__(1024) pca_init_kernel(const long long *__restrict__ colsum, const long long *__restrict__ coltot,
-                                                       double *__restrict__ V, int d, int ldg)
+                                                       double *__restrict__ V, double *__restrict__ VT, int d, int ldg)
 {
     __shared__ double scratch[32];
     const int j = blockIdx.x;
@@ -690,11 +617,15 @@ __global__ void __launch_bounds__(1024) pca_init_kernel(const long long *__restr
         s2 += x * x;
     }
     const double n2 = sqrt(block_sum(s2, scratch));
-    for (int c = threadIdx.x; c < ldg; c += blockDim.x) v[c] = v[c] / n2;
+    for (int c = threadIdx.x; c < ldg; c += blockDim.x) {
+        const double x = v[c] / n2;
+        v[c] = x;
+        VT[((size_t)(j / SYM_J) * ldg + c) * SYM_J + j % SYM_J] = x;
+    }
 }
 
 // W_j = WA_j - WB_j;  stats[j] = { Rayleigh quotient V.W (|V| = 1), |V_new - V|^2 };  V <- W / |W|.
-__global__ void __launch_bounds__(1024) pca_update_kernel(double *__restrict__ V, const double *__restrict__ WA,
+__global__ void __launch_bounds__(1024) pca_update_kernel(double *__restrict__ V, double *__restrict__ VT, const double *__restrict__ WA,
                                                          const double *__restrict__ WB, double *__restrict__ stats, int ldg,
                                                          int nj, double tol2, IterState *state, int slot)
 {
@@ -721,6 +652,7 @@ __global__ void __launch_bounds__(1024) pca_update_kernel(double *__restrict__ V
             const double x = (j ? wa[c] - wb[c] : wa[c]) * inv, dx = x - v[c];
             diff += dx * dx;
             v[c] = x;
+            VT[((size_t)(j / SYM_J) * ldg + c) * SYM_J + j % SYM_J] = x;
         }
     }
     diff = block_sum(diff, scratch);
@@ -838,7 +770,7 @@ void make_pack_plan(int d, int64_t n, int nb, PackPlan &p)
 }
 
 struct Layout {
-    size_t xt, colsum, maxabs, gram, v, w, wb, ysw, stats, state, coltot, total;
+    size_t xt, colsum, maxabs, gram, v, vt, w, wb, ysw, stats, state, coltot, total;
     int ldg;
 };
 
@@ -854,6 +786,7 @@ Layout make_layout(int d, const PackPlan &p, bool with_iteration)
     if (with_iteration) {
         off = align_up(off + (size_t)l.ldg * l.ldg * 4, 256);   // the Gram matrix of all configurations
         l.v = off;      off = align_up(off + (size_t)(p.nb + 1) * l.ldg * 8, 256);
+        l.vt = off;     off = align_up(off + (size_t)((p.nb + SYM_J) / SYM_J) * l.ldg * SYM_J * 8, 256);
         l.w = off;      off = align_up(off + (size_t)(p.nb + 1) * l.ldg * 8, 256);
         l.wb = off;     off = align_up(off + (size_t)(p.nb + 1) * l.ldg * 8, 256);
         l.ysw = off;    off = align_up(off + (size_t)p.ktot * 8, 256);
@@ -861,7 +794,7 @@ Layout make_layout(int d, const PackPlan &p, bool with_iteration)
         l.state = off;  off = align_up(off + sizeof(IterState), 256);
         l.coltot = off; off = align_up(off + (size_t)d * 8, 256);
     } else {
-        l.v = l.w = l.wb = l.ysw = l.stats = l.state = l.coltot = off;
+        l.v = l.vt = l.w = l.wb = l.ysw = l.stats = l.state = l.coltot = off;
     }
     l.total = off;
     return l;
@@ -980,24 +913,20 @@ cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_i
     long long *coltot = reinterpret_cast<long long *>(ws + lay.coltot);
     pca_coltot_kernel<<<(d + 255) / 256, 256, 0, st>>>(colsum, coltot, d, nb);
     const int vt = ldg >= 2048 ? 1024 : 256;   // threads of the per-problem vector kernels (latency bound: one block per problem)
-    pca_init_kernel<<<nj, vt, 0, st>>>(colsum, coltot, V, d, ldg);
+    double *VT = reinterpret_cast<double *>(ws + lay.vt);
+    const int njc = (nj + SYM_J - 1) / SYM_J;
+    if ((e = cudaMemsetAsync(VT, 0, (size_t)njc * ldg * SYM_J * 8, st)) != cudaSuccess) return e;   // unused problem slots stay zero
+    pca_init_kernel<<<nj, vt, 0, st>>>(colsum, coltot, V, VT, d, ldg);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
     double *WB = reinterpret_cast<double *>(ws + lay.wb);
     IterState *state = reinterpret_cast<IterState *>(ws + lay.state);
     if ((e = cudaMemsetAsync(state, 0, sizeof(IterState), st)) != cudaSuccess) return e;
-    const unsigned mv_rows = (unsigned)((ldg + MV_ROWS * MV_WARPS - 1) / (MV_ROWS * MV_WARPS));
     const int8_t *xt = reinterpret_cast<const int8_t *>(ws + lay.xt);
     double *ysw = reinterpret_cast<double *>(ws + lay.ysw);
     StepPlan sp;
     sp.nb = nb;
     for (int b = 0; b <= nb; ++b) sp.st0[b] = pp.kt0[b] / 8;
-    static std::once_flag mv_once;
-    static cudaError_t mv_err = cudaSuccess;
-    std::call_once(mv_once, [] {
-        mv_err = cudaFuncSetAttribute(pca_matvec_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MV_FULL_SMEM);
-    });
-    if (mv_err != cudaSuccess) return mv_err;
     std::vector<double> h_stats(2 * (size_t)nj);
     IterState h_state{};
     int iters = 0;
@@ -1011,8 +940,9 @@ cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_i
             if ((e = cudaMemsetAsync(ysw, 0, (size_t)pp.ktot * 8, st)) != cudaSuccess) return e;
             pca_xv_kernel<<<dim3((unsigned)sp.st0[nb], XV_SLICES), 256, 0, st>>>(xt, V, ysw, d, ldg, pp.ktot, sp, state, i);
             pca_xty_kernel<<<dim3((unsigned)((ldg + 31) / 32), (unsigned)nb), 256, 0, st>>>(xt, ysw, WB, d, ldg, pp.ktot, sp, state, i);
-            pca_matvec_full_kernel<<<mv_rows, MV_WARPS * 32, MV_FULL_SMEM, st>>>(G, V, W, ldg, nj, state, i);
-            pca_update_kernel<<<nj, vt, 0, st>>>(V, W, WB, stats, ldg, nj, tol * tol, state, i);
+            if ((e = cudaMemsetAsync(W, 0, (size_t)nj * ldg * 8, st)) != cudaSuccess) return e;
+            pca_matvec_sym_kernel<<<dim3((unsigned)((ldg + 63) / 64), SYM_SPLIT, (unsigned)njc), 256, 0, st>>>(G, VT, W, ldg, nj, state, i);
+            pca_update_kernel<<<nj, vt, 0, st>>>(V, VT, W, WB, stats, ldg, nj, tol * tol, state, i);
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if ((e = cudaMemcpyAsync(h_stats.data(), stats, h_stats.size() * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
