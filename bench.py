@@ -20,6 +20,7 @@ Numbers:
          reduced sums are all inside the timed region (wall clock around a synchronised call).
   roofline        SM integer-issue roofline of the worm kernel (64 thread-instr/step).
   roofline_blocking  HBM roofline of the RG blocking kernel (20 L^2 bytes per config per level).
+  pipeline_c3     images -> blocking chain -> counts of 4096 L=64 dumps on the device (configs/s) + the numpy port.
   roofline_pca    tensor roofline of the PCA Gram kernel (int8 tcgen05) + stage times + sklearn CPU baseline.
   cpu_baseline    the UNMODIFIED reference executable (oracle/_ref) on all host cores, bounded sample.
 """
@@ -332,6 +333,7 @@ def run_b200_arm(a) -> None:
                 "cycles_per_step_per_chain": f_max * n / kern_rate}
     roofline_blocking = bench_blocking(torch, engine, dev, peaks)
     roofline_pca = bench_pca(torch, engine, dev, peaks, cpu=(world == 1 and not a.no_cpu))
+    pipeline_c3 = bench_pipeline(torch, engine, dev, peaks, cpu=(world == 1 and not a.no_cpu))
     cpu = None
     if world == 1 and not a.no_cpu:
         cores = host_cores()
@@ -354,6 +356,7 @@ def run_b200_arm(a) -> None:
         "roofline": roofline,
         "roofline_blocking": roofline_blocking,
         "roofline_pca": roofline_pca,
+        "pipeline_c3": pipeline_c3,
         "cpu_baseline": cpu,
         "check": {"E_T1.5": float(E[0]), "E_T3.5": float(E[-1]), "e2e_E_T1.5": float(e2e_E[0]),
                   "kaufman_E_T1.5": -1.9511165659, "kaufman_E_T3.5": -0.6601217470},
@@ -361,6 +364,55 @@ def run_b200_arm(a) -> None:
     print(json.dumps(line), flush=True)
     if world > 1:
         td.destroy_process_group()
+
+
+def bench_pipeline(torch, engine, dev, peaks, cpu: bool) -> dict:
+    """Rows a3-a5 chained as in SURVEY 8d C3: dumped occupations of an L=64 lattice -> 128x128 bond images ->
+    the blocking chain 64 -> 32 -> ... -> 2 -> parity-bond counts at every level, all on the device."""
+    L, n = 64, 4096
+    gen = torch.Generator(device=dev).manual_seed(64)
+    bonds = (torch.rand((n, 2 * L * L), device=dev, generator=gen) < 0.3).to(torch.uint8)
+
+    def chain():
+        img = engine.image(bonds, L)
+        counts = [engine.count(img)]
+        while img.shape[-1] > 4:
+            img = engine.block(img, 0)
+            counts.append(engine.count(img))
+        return counts
+
+    for _ in range(3):
+        counts = chain()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        counts = chain()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    out = {"workload": "L=64: %d dumps -> images -> blocking chain to L=2 -> counts per level" % n,
+           "configs_per_s": n / (ms * 1e-3), "ms_per_batch": ms, "launches_per_batch": 1 + 6 + 5,
+           "levels": len(counts), "mean_count_level0": float(counts[0].double().mean())}
+    if cpu:
+        from oracle import postproc_oracle as po
+        sample = bonds[:4].cpu().numpy()
+        t0 = time.perf_counter()
+        for b in sample:
+            img = po.image_from_bonds(b, L)
+            lv = L
+            po.bond_counts(img.reshape(1, -1), 2 * lv)
+            while lv > 2:
+                img = po.block_config(img.reshape(-1), 1, 0).reshape(lv, lv)
+                lv //= 2
+                po.bond_counts(img.reshape(1, -1), 2 * lv)
+        w = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": len(sample) / w, "unit": "configs/s", "kind": "port", "cores": 1,
+                               "sample": "%d configs through oracle/postproc_oracle.py (an O(L^2) restatement; the reference's "
+                                         "block_configs.py loop is O(L^4), 0.39 s per L=64 config, SURVEY 8a)" % len(sample)}
+    del bonds
+    return out
 
 
 def bench_pca(torch, engine, dev, peaks, cpu: bool) -> dict:
