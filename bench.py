@@ -27,6 +27,7 @@ Numbers:
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -281,12 +282,15 @@ def run_b200_arm(a) -> None:
     e2e_pass()
     sim = None
     pass_s = []
+    gc.collect()
+    gc.disable()                               # like timeit: a generation-2 collection inside one pass is not the metric
     for _ in range(a.e2e_steps):
         barrier()
         t0 = time.perf_counter()
         sim = e2e_pass()                       # returns with the result dicts on the host (it synchronises)
         barrier()
         pass_s.append(time.perf_counter() - t0)
+    gc.enable()
     te = torch.tensor(pass_s, dtype=torch.float64, device=dev)
     if world > 1:
         td.all_reduce(te, op=td.ReduceOp.MAX)  # a pass ends when the slowest rank has its results
