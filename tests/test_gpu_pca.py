@@ -176,3 +176,28 @@ def test_pca_edge_cases(eng):
     res = eng.pca(torch.from_numpy(neg).cuda(), 5, max_iters=20000, tol=1e-10)
     evs = pca_oracle.pca_leading(neg, 5)[0]
     np.testing.assert_allclose(res.explained.cpu().numpy(), evs, rtol=1e-6)
+
+
+def test_pca_many_blocks_and_skipped_files(eng, tmp_path):
+    """More problems than one pass of the G v kernel holds (1 + 30 > 12), and the reference's rule that a
+    file with fewer samples than features is skipped (pca.py:132-133)."""
+    import torch
+    from oracle import pca_oracle
+    from worm_algorithm_b200.pca import PrincipalComponent
+    rng = np.random.default_rng(31)
+    x = (rng.random((700, 128)) < 0.3).astype(np.int32)
+    x[:, :10] |= (rng.random((700, 1)) < 0.5).astype(np.int32)
+    res = eng.pca(torch.from_numpy(x).cuda(), 30)
+    evs, s2, comp, _ = pca_oracle.pca_leading(x, 30)
+    np.testing.assert_allclose(res.explained.cpu().numpy(), evs, rtol=1e-8)
+    np.testing.assert_allclose(res.sigma2.cpu().numpy(), s2, rtol=1e-11)
+    ddir = tmp_path / "in"
+    ddir.mkdir()
+    for T, rows in ((2.0, x[:200, :16]), (2.5, x[:10, :16])):            # the second file: 10 samples < 16 features
+        with open(ddir / ("2_config_%s.txt" % T), "w") as f:
+            for row in rows:
+                f.write("%s %s\n" % (T, " ".join(str(int(v)) for v in row)))
+    pc = PrincipalComponent(2, num_blocks=5, data_dir=str(ddir) + "/", save_dir=str(tmp_path / "out") + "/", save=False)
+    assert list(pc._eig_vals) == ["2."] and pc._temps == [2.0]
+    lam = pca_oracle.pca_leading(x[:200, :16], 5)[0][0]
+    assert abs(pc._eig_vals["2."][0][0] - lam) <= 1e-9 * lam
