@@ -202,8 +202,10 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
             // the accountants move them to the int64 histogram in HBM every Cfg::FLUSH rounds
             const uint32_t off2 = (SCSH >= 1) ? (f >> (SCSH - 1)) : (f << 1);
             const uint32_t ha = (uint32_t)hist_row + off2;
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
-                         :: "r"(ha & ~3u), "r"(1u << ((ha & 2u) << 3)), "r"(hist_writer) : "memory");
+            // branch-free: every lane adds (0 for a slot that does not write; its row is valid shared memory).
+            // A predicated add made ptxas branch around the address arithmetic, one basic block per step,
+            // and the steps no longer overlapped.
+            asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(ha & ~3u), "r"(hist_writer << ((ha & 2u) << 3)) : "memory");
         } else {
             const uint32_t off8 = (SCSH >= 3) ? (f >> (SCSH - 3)) : (f << (3 - SCSH));
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.global.add.u64 [%0], 1;\n\t}"
@@ -646,9 +648,10 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         unsigned long long hist_row = 0ull;
         uint32_t hist_writer = 0u;
         if constexpr (HIST) {
+            // SH: every slot, live or not, has its own row of bins in shared memory (adds of 0 go there too)
+            if constexpr (SH) hist_row = (unsigned long long)(sbase + (uint32_t)g.hist_off + (uint32_t)(q * g.N * 2));
             if (live && a.hist && a.group_index) {
-                if constexpr (SH) hist_row = (unsigned long long)(sbase + (uint32_t)g.hist_off + (uint32_t)(q * g.N * 2));
-                else hist_row = (unsigned long long)(a.hist + (int64_t)a.group_index[cl] * g.N);
+                if constexpr (!SH) hist_row = (unsigned long long)(a.hist + (int64_t)a.group_index[cl] * g.N);
                 hist_writer = 1u;
             }
         }
