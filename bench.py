@@ -172,7 +172,7 @@ def run_reference_arm(a) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(a, world: int) -> dict:
@@ -203,7 +203,6 @@ def run_b200_arm(a) -> None:
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the JSON line only
         td.init_process_group("nccl", device_id=dev)
     _lib.lib()                                                    # fail loudly if the .so is missing
 
@@ -365,7 +364,7 @@ def run_b200_arm(a) -> None:
         "check": {"E_T1.5": float(E[0]), "E_T3.5": float(E[-1]), "e2e_E_T1.5": float(e2e_E[0]),
                   "kaufman_E_T1.5": -1.9511165659, "kaufman_E_T3.5": -0.6601217470},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         td.destroy_process_group()
 
@@ -498,7 +497,30 @@ def bench_blocking(torch, engine, dev, peaks) -> dict:
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout() -> None:
+    """stdout carries the ONE JSON line and nothing else: everything libraries print to fd 1 (NCCL's version
+    banner, for one) is sent to stderr; emit() writes the line to the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main() -> None:
+    claim_stdout()
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=5)
