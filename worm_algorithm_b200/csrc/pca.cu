@@ -717,6 +717,30 @@ EncodeTiledFn encode_tiled()
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// A second stream + fork / join events, created once per host thread and device (stream creation costs
+// tens of microseconds, a worm_pca call one millisecond) and kept for the life of the thread.
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaError_t init()
+    {
+        if (s) return cudaSuccess;
+        cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+        return e;
+    }
+};
+
+SideStream *side_stream()
+{
+    constexpr int MAX_DEV = 64;
+    thread_local SideStream cache[MAX_DEV];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+    return cache[dev].init() == cudaSuccess ? &cache[dev] : nullptr;
+}
+
 // Optional stage timing (worm_pca_timing): CUDA events on the caller's stream around each stage.
 std::atomic<int> g_timing{0};
 thread_local double g_ms[PCA_TIMING_SLOTS] = {0, 0, 0, 0, 0};
@@ -933,15 +957,27 @@ cudaError_t launch_pca(int d, int64_t n, const int32_t *d_img, int nb, int max_i
     double worst = 0.0;
     // Batches of MV_BATCH iterations are queued without host round trips; once every problem has
     // converged (device-side count) the remaining launches of the batch return immediately.
+    // The two halves of an iteration are independent (G v on one side, the deleted blocks' X^T X v on the
+    // other): the second runs on a side stream, forked and joined with events around every update.
+    SideStream *sidep = side_stream();
+    if (!sidep) {
+        *why = "could not create the side stream";
+        return cudaErrorUnknown;
+    }
+    SideStream &side = *sidep;
     while (iters < max_iters) {
         const int batch = std::min(MV_BATCH, max_iters - iters);
         if ((e = cudaMemsetAsync(state->cnt, 0, sizeof(state->cnt), st)) != cudaSuccess) return e;
         for (int i = 0; i < batch; ++i) {
-            if ((e = cudaMemsetAsync(ysw, 0, (size_t)pp.ktot * 8, st)) != cudaSuccess) return e;
-            pca_xv_kernel<<<dim3((unsigned)sp.st0[nb], XV_SLICES), 256, 0, st>>>(xt, V, ysw, d, ldg, pp.ktot, sp, state, i);
-            pca_xty_kernel<<<dim3((unsigned)((ldg + 31) / 32), (unsigned)nb), 256, 0, st>>>(xt, ysw, WB, d, ldg, pp.ktot, sp, state, i);
+            if ((e = cudaEventRecord(side.fork, st)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(side.s, side.fork, 0)) != cudaSuccess) return e;
+            if ((e = cudaMemsetAsync(ysw, 0, (size_t)pp.ktot * 8, side.s)) != cudaSuccess) return e;
+            pca_xv_kernel<<<dim3((unsigned)sp.st0[nb], XV_SLICES), 256, 0, side.s>>>(xt, V, ysw, d, ldg, pp.ktot, sp, state, i);
+            pca_xty_kernel<<<dim3((unsigned)((ldg + 31) / 32), (unsigned)nb), 256, 0, side.s>>>(xt, ysw, WB, d, ldg, pp.ktot, sp, state, i);
+            if ((e = cudaEventRecord(side.join, side.s)) != cudaSuccess) return e;
             if ((e = cudaMemsetAsync(W, 0, (size_t)nj * ldg * 8, st)) != cudaSuccess) return e;
             pca_matvec_sym_kernel<<<dim3((unsigned)((ldg + 63) / 64), SYM_SPLIT, (unsigned)njc), 256, 0, st>>>(G, VT, W, ldg, nj, state, i);
+            if ((e = cudaStreamWaitEvent(st, side.join, 0)) != cudaSuccess) return e;
             pca_update_kernel<<<nj, vt, 0, st>>>(V, VT, W, WB, stats, ldg, nj, tol * tol, state, i);
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
