@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(256) pca_xty_kernel(const int8_t *__restrict__
     }
 }
 
-// WA_j += G V_j for up to SYM_J problems, using the symmetry of G: lane l of a warp owns rows r0 + l and r0 + 32 + l
+// WA_j += G V_j for up to SYM_J problems, using the symmetry of G: lane l of a warp owns rows r0 + 2l and r0 + 2l + 1
 // and walks down COLUMNS of those rows, i.e. along row c of G (G[c][r] = G[r][c]) -- a coalesced 128-byte
 // load per c, while V_j[c] is the same for every lane (one broadcast load of the transposed copy VT[c][j]).
 // No shared-memory staging of the vectors, no cross-lane reduction; the eight warps of a block take
@@ -518,29 +518,27 @@ __global__ void __launch_bounds__(256, 2) pca_matvec_sym_kernel(const int32_t *_
     __shared__ double red[8][2 * SYM_J][32];
     if (iter_finished(state, slot, nj)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r0 = blockIdx.x * 64, ra = r0 + lane, rb = r0 + 32 + lane;
+    const int r0 = blockIdx.x * 64, ra = r0 + 2 * lane;          // this lane's rows: ra, ra + 1 (one 8-byte load per matrix row)
     const int cw = ((ldg + SYM_SPLIT - 1) / SYM_SPLIT + 7) & ~7;
     const int cb = blockIdx.y * cw, ce = min(ldg, cb + cw);
     const int j0 = blockIdx.z * SYM_J, jn = min(SYM_J, nj - j0);
     const double2 *vt = reinterpret_cast<const double2 *>(VT + (size_t)blockIdx.z * ldg * SYM_J);
-    const bool oka = ra < ldg, okb = rb < ldg;
+    const bool oka = ra < ldg;                                    // ldg is even: ra + 1 < ldg too
     double acc[2][SYM_J];
 #pragma unroll
     for (int j = 0; j < SYM_J; ++j) acc[0][j] = acc[1][j] = 0.0;
-    constexpr int U = 4;
+    constexpr int U = 8;
     for (int c = cb + warp; c < ce; c += 8 * U) {
-        int ga[U], gb[U];
+        int2 g[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int cc = c + 8 * u;
-            const bool ok = cc < ce;
-            ga[u] = (ok && oka) ? __ldcs(G + (size_t)cc * ldg + ra) : 0;
-            gb[u] = (ok && okb) ? __ldcs(G + (size_t)cc * ldg + rb) : 0;
+            g[u] = (cc < ce && oka) ? __ldcs(reinterpret_cast<const int2 *>(G + (size_t)cc * ldg + ra)) : make_int2(0, 0);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int cc = min(c + 8 * u, ce - 1);
-            const double da = int_to_double(ga[u]), db = int_to_double(gb[u]);
+            const double da = int_to_double(g[u].x), db = int_to_double(g[u].y);
 #pragma unroll
             for (int jj = 0; jj < SYM_J / 2; ++jj) {
                 const double2 v = vt[(size_t)cc * (SYM_J / 2) + jj];
@@ -559,7 +557,7 @@ __global__ void __launch_bounds__(256, 2) pca_matvec_sym_kernel(const int32_t *_
     __syncthreads();
     for (int o = threadIdx.x; o < 2 * SYM_J * 32; o += 256) {
         const int l = o & 31, k = o >> 5;                       // k = half * SYM_J + j
-        const int j = k % SYM_J, row = r0 + (k / SYM_J) * 32 + l;
+        const int j = k % SYM_J, row = r0 + 2 * l + k / SYM_J;
         if (j < jn && row < ldg) {
             double sum = 0.0;
 #pragma unroll
