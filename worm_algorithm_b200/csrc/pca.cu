@@ -367,11 +367,13 @@ __device__ __forceinline__ double int_to_double(int g)
     return __hiloint2double(0x43300000, g ^ 0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
 }
 
-// signed byte B of a 32-bit word -> double, exactly (sign extension, then the 2^52 trick)
+// Signed byte B of a packed word -> double, exactly, in three instructions per element (permute, fp64 add,
+// then the FMA that uses it): with wx = word ^ 0x80808080 every byte is u = x + 128 in [0, 255]; the permute
+// drops u into the low word of 2^52 (= 2^52 + u exactly) and the add removes 2^52 + 128.
 template <int B>
-__device__ __forceinline__ double s8_to_double(uint32_t w)
+__device__ __forceinline__ double s8_to_double(uint32_t wx)
 {
-    return int_to_double((int)(signed char)(w >> (8 * B)));
+    return __hiloint2double(0x43300000, (int)__byte_perm(wx, 0u, 0x4440u | B)) - 4503599627370624.0;
 }
 
 // first 512-configuration step of each jackknife block in the packed matrix
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(256) pca_xv_kernel(const int8_t *__restrict__ 
         load(c + 8 * U, xn, vn);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+            const uint32_t w[4] = {x[u].x ^ 0x80808080u, x[u].y ^ 0x80808080u, x[u].z ^ 0x80808080u, x[u].w ^ 0x80808080u};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 acc[4 * q + 0] = fma(s8_to_double<0>(w[q]), vc[u], acc[4 * q + 0]);
@@ -482,7 +484,7 @@ __global__ void __launch_bounds__(256) pca_xty_kernel(const int8_t *__restrict__
         for (int i = 0; i < 8; ++i) y[i] = y2[(size_t)(step * 8 + i) * 32 + lane];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const uint32_t w[4] = {x[r].x, x[r].y, x[r].z, x[r].w};
+            const uint32_t w[4] = {x[r].x ^ 0x80808080u, x[r].y ^ 0x80808080u, x[r].z ^ 0x80808080u, x[r].w ^ 0x80808080u};
             double a = acc[r];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
