@@ -291,6 +291,32 @@ def gen_boundaries():
             assert (io.get_boundaries(io.prepare(img), c) == outs[-1]).all(), (name, c)
         g["bdy_%s_links" % name] = np.stack(outs)
         g["bdy_%s_bw" % name] = np.stack(bws)
+    # ---- the notebook's chain on a small image set: boundaries -> block_image -> CountBonds per cutoff ----
+    # (image_analysis/utils is a package named `utils`, like worm_algorithm/utils.py: swap the module in and out)
+    stub.toimage = None
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "utils" or k.startswith("utils.")}
+    saved_path = list(sys.path)
+    sys.path[:] = [q for q in sys.path if os.path.abspath(q) != os.path.abspath(REF)]   # a namespace package loses to utils.py
+    try:
+        from utils.block_images import block_image          # noqa
+        from utils.count_bonds import CountBonds as IACountBonds   # noqa
+        imgs = rng.random((7, 8, 8))
+        cutoffs = np.array([0.3, 0.5, 0.7])
+        bdy = np.array([[np.asarray(ref_image.Image(im).get_boundaries(c)) for c in cutoffs] for im in imgs])   # get_bdy_images
+        blk = np.array([[block_image(b).reshape(8, 8) for b in row] for row in bdy])                            # block_images
+        per_cut = np.transpose(bdy, (1, 0, 2, 3))
+        per_cut_blk = np.transpose(blk, (1, 0, 2, 3))
+        g["chain_in"] = imgs
+        g["chain_cutoffs"] = cutoffs
+        g["chain_bdy"] = bdy.astype(np.int8)
+        g["chain_blocked"] = blk.astype(np.int8)
+        g["chain_stats"] = np.array([IACountBonds(s_, 3).count_bonds() for s_ in per_cut], dtype=np.float64)
+        g["chain_stats_blocked"] = np.array([IACountBonds(s_, 3).count_bonds() for s_ in per_cut_blk], dtype=np.float64)
+    finally:
+        sys.path[:] = saved_path
+        for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
     np.savez_compressed(os.path.join(GOLD, "boundaries.npz"), **g)
     print("boundaries.npz:", len(g), "arrays")
 

@@ -23,7 +23,7 @@ def gold(golden_dir):
 
 
 def _names(gold):
-    return sorted(k[4:-3] for k in gold if k.endswith("_in"))
+    return sorted(k[4:-3] for k in gold if k.startswith("bdy_") and k.endswith("_in"))
 
 
 def test_boundaries_match_reference_class_golden(eng, gold):
@@ -90,3 +90,16 @@ def test_boundaries_host_entry_point(eng, gold):
                                         cutoffs.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
     assert rc == 0
     assert np.array_equal(out, gold["bdy_%s_links" % name].astype(np.int32))
+
+
+def test_notebook_chain_matches_reference_helpers(eng, gold):
+    """get_bdy_images -> block_images -> count_bonds_helper of image_analysis.ipynb against the reference's own
+    Image / block_image / CountBonds on the same images (oracle/make_golden.py gen_boundaries)."""
+    from worm_algorithm_b200 import image as im
+    imgs, cutoffs = gold["chain_in"], gold["chain_cutoffs"]
+    bdy = im.get_bdy_images(cutoffs, imgs)
+    assert np.array_equal(bdy, gold["chain_bdy"])
+    blk = im.block_images(bdy)
+    assert np.array_equal(blk, gold["chain_blocked"])
+    np.testing.assert_allclose(im.count_bonds_helper(bdy, 3), gold["chain_stats"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(im.count_bonds_helper(blk, 3), gold["chain_stats_blocked"], rtol=1e-12, atol=1e-12)

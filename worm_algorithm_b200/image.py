@@ -84,3 +84,41 @@ class Image(object):
         image_links = self.boundaries_for_cutoffs([cutoff], image)[0]
         self._image_links = image_links
         return image_links
+
+
+# ---------------------------------------------------------------------------------------------
+# The three helper functions of image_analysis.ipynb (cells 2-4), each one batched launch here.
+# ---------------------------------------------------------------------------------------------
+def get_bdy_images(cutoffs, images, device=None):
+    """[n_images, n_cutoffs, 2Nx, 2Ny] boundary images (notebook cell 2: `Image(image).get_boundaries(cutoff)`
+    for every image and cutoff)."""
+    import torch
+    prepared = np.stack([Image(im)._image for im in images])           # per-image bytescale, as Image.__init__ does
+    dev = engine._dev(device)
+    return engine.boundaries(torch.from_numpy(np.ascontiguousarray(prepared)).to(dev), cutoffs).cpu().numpy().astype(int)
+
+
+def block_images(images, device=None):
+    """One blocking step on every image of an [n_images, n_cutoffs, W, W] set (notebook cell 3;
+    image_analysis/utils/block_images.py:4-53 is the "1+1=0" scheme of block_configs.py)."""
+    import torch
+    a = np.ascontiguousarray(np.asarray(images).astype(np.int32))
+    out = engine.block(torch.from_numpy(a).to(engine._dev(device)), 0)
+    return out.cpu().numpy().astype(int)
+
+
+def count_bonds_helper(images, num_blocks=20, device=None):
+    """[n_cutoffs, 4] rows (<Nb>, err, <Nb^2> - <Nb>^2, err) over the images of each cutoff (notebook cell 4 with
+    image_analysis/utils/count_bonds.py:CountBonds.count_bonds)."""
+    import torch
+    from .count_bonds import count_stats_with_err
+    a = np.asarray(images)
+    if a.ndim != 4:
+        raise ValueError("Images have the wrong shape.")
+    t = torch.from_numpy(np.ascontiguousarray(np.transpose(a, (1, 0, 2, 3)).astype(np.int32))).to(engine._dev(device))
+    counts = engine.count(t).cpu().numpy()                             # [n_cutoffs, n_images]
+    rows = []
+    for bc in counts:
+        val, err = count_stats_with_err(bc, num_blocks)
+        rows.append([val[0], err[0], val[1], err[1]])
+    return np.array(rows)
