@@ -872,12 +872,8 @@ cudaError_t run_pack_and_gram(int d, int64_t n, const int32_t *d_img, const Pack
     for (int b = 0; b <= pp.nb; ++b) gp.kt0[b] = pp.kt0[b] / 2;
     if (all_in_one) gp.kt0[1] = pp.kt0[pp.nb] / 2;
     gp.G = d_gram;
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM);
-    });
-    if (attr_err != cudaSuccess) return attr_err;
+    // per device (the attribute lives in the device's context), so set on every call: it costs microseconds
+    if ((e = cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM)) != cudaSuccess) return e;
     const int total = gp.nb * gp.tiles_per_block;
     tm.mark();
     gram_kernel<<<std::min(total, sm_count), GRAM_THREADS, GRAM_SMEM, st>>>(tmap, gp);
