@@ -119,6 +119,29 @@ def test_lat_and_wide_kernels_agree_at_scale(eng):
     assert int(a.group_acc[:, 5].sum()) == n * 2700
 
 
+@pytest.mark.parametrize("L", [4, 16, 32])
+def test_solo_histogram_bins_survive_their_flushes(eng, L):
+    """Solo latency mode keeps 16-bit G(r) bins per chain in shared memory and sweeps them into the
+    int64 histogram every 32768 steps: a run across several sweeps (resumed once, so that the chains
+    start open) gives the histogram of the thread-per-chain kernel bit for bit."""
+    nT, reps = 5, 20
+    T = np.tile(np.linspace(1.5, 3.5, nT), reps)
+    n = T.size                                  # 100 chains: three full walkers and a ragged one
+    gi = np.tile(np.arange(nT), reps)
+    seeds = (np.arange(n) // nT + 7).astype(np.uint64)
+    runs = []
+    for lanes in (1, 2):
+        st = eng.PhiloxState(L, T, seeds, algo=0, group_index=gi, n_groups=nT, hist=True)
+        st.run(1001, therm_steps=100, lanes_per_chain=lanes)
+        st.run(80000, therm_steps=100, lanes_per_chain=lanes)
+        runs.append(st)
+    a, b = runs
+    assert (a.hist == b.hist).all() and (a.acc == b.acc).all() and (a.bonds == b.bonds).all()
+    h = b.hist.cpu().numpy()
+    assert h.sum() == n * 80901
+    assert (h[:, 0] == b.group_acc[:, 0].cpu().numpy()).all()        # G(0) = Z
+
+
 # ------------------------------------------------------------------------------------------------
 # host-side mirrors of the reference's post-processing classes
 # ------------------------------------------------------------------------------------------------

@@ -52,6 +52,7 @@ struct LatGeo {
     int rec_off;         // byte offset of the record rings inside dynamic shared memory
     int log_off;         // byte offset of the step logs
     int hist_off;        // byte offset of the 16-bit G(r) bins (solo mode with histograms)
+    int HXF, HYF;        // x / y bit fields of a displacement in bin-address format (solo mode with histograms)
     int lowt;            // some chain has T < 1 (general record builder)
     int zero;            // 0 (a value the compiler cannot see through)
 };
@@ -66,14 +67,15 @@ template <int CH, bool SH = false> struct LatCfg {
     static constexpr int R = 64 * NP / CH;            // steps per chain per round
     static constexpr int BUF = R * CH * 16;           // bytes of one buffer of A (or B) records
     static constexpr int REC_B = 2 * BUF;             // byte offset of the B records (two buffers of A first)
-    static constexpr int RECW = 4 * BUF;              // record bytes per walker warp
+    static constexpr int REC_C = 4 * BUF;             // SH: byte offset of the C records (displacement update)
+    static constexpr int RECW = (SH ? 6 : 4) * BUF;   // record bytes per walker warp
     static constexpr int LSTR = R + 4;                // pitch of a chain's log row (5 words: 32 lanes hit 32 banks)
     static constexpr int LOGH = LSTR * CH;            // bytes of one accept (or closed) log of a round
     static constexpr int LOGB = 2 * LOGH;             // one round's log: accept bytes, then closed bytes
     static constexpr int LOGW = 3 * LOGB;             // three rounds in flight per walker warp
     static constexpr int PARTS = 32 / ACH;            // accountant lanes per chain
     static constexpr int SP = R / PARTS;              // steps per accountant lane per round
-    static constexpr int FLUSH = 4096;                // SH: rounds between flushes of the 16-bit bins (FLUSH * R < 65536)
+    static constexpr int FLUSH = 4096;                // SH: rounds between the walker's flushes of the 16-bit bins (FLUSH * R < 65536)
 };
 
 // ---- shared memory by absolute 32-bit shared-window address.  All hot-loop accesses are volatile
@@ -83,6 +85,16 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
@@ -110,6 +122,7 @@ __device__ __forceinline__ void group_barrier(int id)
 struct LatState {
     int head, tail;      // scaled site indices (site * SC)
     uint32_t closed;     // 0 / 1.  When 1, head already holds the (folded) kick of the coming step.
+    uint32_t dh;         // solo mode with histograms: head - tail in bin-address format (0 iff closed)
 };
 
 // Observables are NOT accumulated by the walker (every instruction of its dependent chain costs
@@ -130,10 +143,15 @@ struct Account {
 //        compact: p = addneg, q = address of bond byte (y bit) of site 0: the bond is owned by
 //                 own = (head & keep) | ((head + addneg) & ~keep) and lives at own + q
 //   rb = {kick, thr, flip, logbits}:  accept iff (nb < thr) xor (flip != 0);  Taylor: nb += 1 | flip
+//   rc = {addh, keeph, gaph, -} (solo mode with histograms): the same move applied to the displacement
+//        head - tail kept in bin-address format,  dh' = (dh & keeph) | (((dh | gaph) + addh) & ~keeph).
+//        Bin s = dy * L + dx of a chain lives at (s >> 1) * 128 + (s & 1) * 2 of the chain's bank, so
+//        the x field is bit 1 plus bits 7.. : a +x move fills the gap (bits 2..6) with ones so that the
+//        carry out of bit 1 reaches bit 7; a -x move borrows through the gap's zeros.
 // numf = float(kfix - 1) * (1 + 2^-18), rounded up (see the threshold computation below)
-template <int ALGO, bool DUAL>
+template <int ALGO, bool DUAL, bool SH>
 __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &prm, const float numf, uint32_t a,
-                                            uint32_t b, uint32_t chain_abs, uint4 &ra, uint4 &rb)
+                                            uint32_t b, uint32_t chain_abs, uint4 &ra, uint4 &rb, uint4 &rc)
 {
     const uint32_t d = b >> 30;                                  // :137
     const bool ym = d & 1u, neg = d & 2u;
@@ -147,6 +165,13 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
     } else {
         ra.z = neg ? (uint32_t)add : 0u;
         ra.w = chain_abs + (uint32_t)ym;
+    }
+    if constexpr (SH) {
+        const int hstep = ym ? g.L * 64 : 2;
+        rc.x = (uint32_t)(neg ? -hstep : hstep);
+        rc.y = ym ? ~(uint32_t)g.HYF : ~(uint32_t)g.HXF;
+        rc.z = (!ym && !neg) ? 0x7cu : 0u;
+        rc.w = 0u;
     }
     rb.x = (uint32_t)g.SC * __umulhi(b << 3, (uint32_t)g.N);     // kick site :128
     if constexpr (ALGO == ALGO_TAYLOR) {
@@ -185,32 +210,21 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
 // alog / clog: shared addresses of this step's accept / closed log bytes.
 template <int ALGO, bool DUAL, int SCSH, bool HIST, bool SH, bool MEAS>
 __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long hist_row, uint32_t hist_writer,
-                                         LatState &c, const uint4 ra, const uint4 rb, const int kick_next,
+                                         LatState &c, const uint4 ra, const uint4 rb, const uint4 rc, const int kick_next,
                                          const uint32_t alog, const uint32_t clog)
 {
     const int add = (int)ra.x, keep = (int)ra.y;
     const int kick = (int)rb.x;
     const uint32_t thr = rb.y, flip = rb.z, logbits = rb.w;
     const bool closed = c.closed != 0u;
-    if constexpr (MEAS && HIST) {
+    if constexpr (MEAS && HIST && !SH) {
         // G(r) bin of (head - tail) before the kick; a closed worm is bin 0
         const int t1 = c.head - c.tail;
         const int t2 = (c.head | g.XM | (g.SC - 1)) - (c.tail & g.YM);          // y fields, no borrow from x
         const uint32_t f = closed ? 0u : (uint32_t)((t1 & g.XM) | (t2 & g.YM)); // site difference * SC
-        if constexpr (SH) {
-            // 16-bit bins of this chain in shared memory, two per word (hist_row = their shared address);
-            // the accountants move them to the int64 histogram in HBM every Cfg::FLUSH rounds
-            const uint32_t off2 = (SCSH >= 1) ? (f >> (SCSH - 1)) : (f << 1);
-            const uint32_t ha = (uint32_t)hist_row + off2;
-            // branch-free: every lane adds (0 for a slot that does not write; its row is valid shared memory).
-            // A predicated add made ptxas branch around the address arithmetic, one basic block per step,
-            // and the steps no longer overlapped.
-            asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(ha & ~3u), "r"(hist_writer << ((ha & 2u) << 3)) : "memory");
-        } else {
-            const uint32_t off8 = (SCSH >= 3) ? (f >> (SCSH - 3)) : (f << (3 - SCSH));
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.global.add.u64 [%0], 1;\n\t}"
-                         :: "l"(hist_row + off8), "r"(hist_writer) : "memory");
-        }
+        const uint32_t off8 = (SCSH >= 3) ? (f >> (SCSH - 3)) : (f << (3 - SCSH));
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.global.add.u64 [%0], 1;\n\t}"
+                     :: "l"(hist_row + off8), "r"(hist_writer) : "memory");
     }
     const int tail = closed ? kick : c.tail;                    // kick :128-129 (head has it already)
     c.tail = tail;
@@ -227,6 +241,18 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
         addr = (uint32_t)own + ra.w;
     }
     const uint32_t nb = lds_u8(addr);                           // :139
+    // Solo mode with histograms: G(r) bin of (head - tail) before the move; a closed worm is bin 0
+    // (dh == 0).  The chain's 16-bit bins live in its own bank and only this lane touches them between
+    // the walker's flushes, so the count is a plain load / add / store (a shared-memory atomic costs
+    // the LSU ~2 cycles per lane); every lane stores (a slot that does not write adds 0).  The load
+    // rides in the bond load's shadow, the add and the store follow the accept block.
+    uint32_t hv = 0u, ha = 0u, dnew = 0u;
+    if constexpr (HIST && SH) {
+        ha = (uint32_t)hist_row + c.dh;
+        if constexpr (MEAS) hv = lds_u16(ha);
+        const uint32_t th = (c.dh | rc.z) + rc.x;
+        dnew = (c.dh & rc.y) | (th & ~rc.y);
+    }
     // closed iteration (worm_ising_2d.cpp:130-132): logged, measured by the accountant.  After the
     // load in program order: a store ahead of it would sit on the load's issue path (the compiler
     // cannot reorder shared-memory accesses that may alias).
@@ -238,7 +264,7 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
     // thr | 0, written so that the compiler has to finish A, B and the second store address before
     // the first consumer of nb: the warp issues in order and stalls at that consumer, so everything
     // that does not depend on the load must sit in front of it (in the load's shadow), not behind
-    const uint32_t thrx = thr | ((uint32_t)(A ^ B ^ (int)addr2) & (uint32_t)g.zero);
+    const uint32_t thrx = thr | ((uint32_t)(A ^ B ^ (int)addr2 ^ (int)dnew) & (uint32_t)g.zero);
     const uint32_t nn = (ALGO == ALGO_TAYLOR) ? nb + (1u | flip) : (nb ^ 1u);
     const uint32_t lg = (nb & 1u) | logbits;
     // accept test (:151), head select, bond stores (:152-154) and the accept-log byte in one opaque
@@ -273,6 +299,10 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
     }
     c.head = head_new;
     c.closed = acc_i ? pc : c.closed;
+    if constexpr (HIST && SH) {
+        c.dh = acc_i ? dnew : c.dh;
+        if constexpr (MEAS) sts_u16(ha, hv + hist_writer);
+    }
 }
 
 // Replay of one round's log by the producer warp: lane (q, part) owns steps [part*SP, part*SP+SP) of
@@ -486,12 +516,13 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 uint64_t pair = (bt.s0 >> 1) + (uint64_t)p_of;
                 for (uint32_t kk = 0; kk < bt.n; ++kk, pair += R / 2) {
                     const uint4 r = philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), c2, c3, keys);
-                    uint4 ra0, rb0, ra1, rb1;
-                    make_record<ALGO, DUAL>(g, prm, numf, r.x, r.y, chain_abs, ra0, rb0);
-                    make_record<ALGO, DUAL>(g, prm, numf, r.z, r.w, chain_abs, ra1, rb1);
+                    uint4 ra0, rb0, rc0, ra1, rb1, rc1;
+                    make_record<ALGO, DUAL, SH>(g, prm, numf, r.x, r.y, chain_abs, ra0, rb0, rc0);
+                    make_record<ALGO, DUAL, SH>(g, prm, numf, r.z, r.w, chain_abs, ra1, rb1, rc1);
                     const uint32_t p0 = rec_q + buf;
                     sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0);
                     sts_v4(p0 + CH * 16, ra1); sts_v4(p0 + CH * 16 + Cfg::REC_B, rb1);
+                    if constexpr (SH) { sts_v4(p0 + Cfg::REC_C, rc0); sts_v4(p0 + CH * 16 + Cfg::REC_C, rc1); }
                     group_barrier<Cfg::GW>(bar_id);
                     buf ^= (uint32_t)Cfg::BUF;
                 }
@@ -566,28 +597,6 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             lbuf_acc = (lbuf_acc == 2u * Cfg::LOGB) ? 0u : lbuf_acc + (uint32_t)Cfg::LOGB;
         };
 
-        // SH: the group's accountant lanes sweep the block's 16-bit G(r) bins into the HBM histogram
-        auto flush_hist = [&]() {
-            if constexpr (SH) {
-                const int wpc = g.N / 2;                              // words per chain
-                for (int i = u * 32 + lane; i < CH * wpc; i += NA * 32) {
-                    uint32_t v;
-                    asm volatile("atom.shared.exch.b32 %0, [%1], %2;"
-                                 : "=r"(v) : "r"(sbase + (uint32_t)g.hist_off + (uint32_t)i * 4u), "r"(0u) : "memory");
-                    if (v) {
-                        const int qc = i / wpc, wv = i - qc * wpc;
-                        const int64_t cg = chain0 + qc;
-                        if (cg < a.n_chains && a.hist && a.group_index) {
-                            unsigned long long *row =
-                                reinterpret_cast<unsigned long long *>(a.hist + (int64_t)a.group_index[cg] * g.N);
-                            if (v & 0xffffu) atomicAdd(row + 2 * wv, (unsigned long long)(v & 0xffffu));
-                            if (v >> 16) atomicAdd(row + 2 * wv + 1, (unsigned long long)(v >> 16));
-                        }
-                    }
-                }
-            }
-        };
-        int flush_ctr = 0;
         uint64_t s = a.step_begin;
         while (s < a.step_end) {
             bool meas, dump_first;
@@ -604,9 +613,6 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     pend[1] = Pending{sr, kk ? 0 : bt.jb, meas, dump_first && seg_first, true};
                     seg_first = false;
                     sr = bt.s0 + (uint64_t)(kk + 1) * (uint64_t)R;
-                    if constexpr (SH) {
-                        if (++flush_ctr == Cfg::FLUSH) { flush_hist(); flush_ctr = 0; }
-                    }
                 }
                 s = bt.s_next;
             }
@@ -615,7 +621,6 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         group_barrier<Cfg::GW>(bar_id);                            // the walker has finished its last step
         if (pend[0].valid) account(pend[0]);
         if (pend[1].valid) account(pend[1]);
-        flush_hist();
         // reduce the parts' shares and write the chain's record
 #pragma unroll
         for (int o = ACH; o < 32; o <<= 1) {
@@ -646,20 +651,55 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         uint32_t log_q = log_w + (uint32_t)(q * Cfg::LSTR);
         asm volatile("" : "+r"(rec_q), "+r"(log_q));                     // keep them in registers
         unsigned long long hist_row = 0ull;
+        unsigned long long *hist_out = nullptr;         // SH: this chain's row of the int64 histogram in HBM
         uint32_t hist_writer = 0u;
         if constexpr (HIST) {
-            // SH: every slot, live or not, has its own row of bins in shared memory (adds of 0 go there too)
-            if constexpr (SH) hist_row = (unsigned long long)(sbase + (uint32_t)g.hist_off + (uint32_t)(q * g.N * 2));
+            // SH: every slot, live or not, has its own bank of bins in shared memory (adds of 0 go there too):
+            // bins 2i, 2i+1 of slot q are the halves of word i * 32 + q
+            if constexpr (SH) hist_row = (unsigned long long)(sbase + (uint32_t)g.hist_off + (uint32_t)(q * 4));
             if (live && a.hist && a.group_index) {
-                if constexpr (!SH) hist_row = (unsigned long long)(a.hist + (int64_t)a.group_index[cl] * g.N);
+                unsigned long long *row = reinterpret_cast<unsigned long long *>(a.hist + (int64_t)a.group_index[cl] * g.N);
+                if constexpr (SH) hist_out = row;
+                else hist_row = (unsigned long long)row;
                 hist_writer = 1u;
             }
         }
+        // SH: the walker sweeps its chains' 16-bit bins into the int64 histogram every Cfg::FLUSH rounds
+        // and at the end (lane q owns bank q: no conflicts, no atomics in shared memory)
+        auto flush_hist = [&]() {
+            if constexpr (SH) {
+                const uint32_t base = (uint32_t)hist_row;
+                for (int i0 = 0; i0 < g.N / 2; i0 += 4) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] = lds_u32(base + (uint32_t)((i0 + e) * 128));
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (v[e]) {
+                            asm volatile("st.shared.u32 [%0], %1;" :: "r"(base + (uint32_t)((i0 + e) * 128)), "r"(0u) : "memory");
+                            if (hist_out) {
+                                if (v[e] & 0xffffu) atomicAdd(hist_out + 2 * (i0 + e), (unsigned long long)(v[e] & 0xffffu));
+                                if (v[e] >> 16) atomicAdd(hist_out + 2 * (i0 + e) + 1, (unsigned long long)(v[e] >> 16));
+                            }
+                        }
+                    }
+                }
+            }
+        };
+        int flush_ctr = 0;
 
         LatState c;
         c.head = SC * a.head[cl];
         c.tail = SC * a.tail[cl];
         c.closed = (c.head == c.tail) ? 1u : 0u;
+        c.dh = 0u;
+        if constexpr (SH) {
+            const int hs = a.head[cl], ts = a.tail[cl];
+            const int dx = (hs - ts) & (g.L - 1);
+            const int dy = (hs / g.L - ts / g.L) & (g.L - 1);
+            const int sd = dy * g.L + dx;
+            c.dh = (uint32_t)((sd >> 1) * 128 + (sd & 1) * 2);
+        }
         int32_t nd = (a.n_dumps && live) ? a.n_dumps[cl] : 0;
 
         auto rec_addr = [&](uint32_t buf, int j) { return rec_q + buf + (uint32_t)(j * CH * 16); };
@@ -669,6 +709,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         // step j+2, which for the last two steps lives in the other buffer (complete once the pair
         // barrier has been passed).  On exit they hold the records of steps 0 / 1 of the next round.
         uint4 p0a, p0b, p1a, p1b;
+        uint4 p0c = make_uint4(0, 0, 0, 0), p1c = make_uint4(0, 0, 0, 0);      // SH only
         auto full_round = [&](auto meas_tag, uint32_t cur, uint32_t nxt, uint32_t lg) {
             constexpr bool MEAS = decltype(meas_tag)::value;
 #pragma unroll
@@ -676,9 +717,12 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 if (j == R - 2) group_barrier<Cfg::GW>(bar_id);
                 const uint32_t nrec = (j < R - 2) ? rec_addr(cur, j + 2) : rec_addr(nxt, j + 2 - R);
                 const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
-                lat_step<ALGO, DUAL, SCSH, HIST, SH, MEAS>(g, hist_row, hist_writer, c, p0a, p0b, (int)p1b.x,
+                uint4 fc = make_uint4(0, 0, 0, 0);
+                if constexpr (SH) fc = lds_v4(nrec + Cfg::REC_C);
+                lat_step<ALGO, DUAL, SCSH, HIST, SH, MEAS>(g, hist_row, hist_writer, c, p0a, p0b, p0c, (int)p1b.x,
                                                        lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j));
                 p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
+                if constexpr (SH) { p0c = p1c; p1c = fc; }
             }
         };
         // Any other round (segment edges): steps [jb, je), records straight from shared memory.  The
@@ -691,7 +735,9 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 uint32_t nrec = rec_addr(cur, j + 1);
                 if (j == je - 1) { group_barrier<Cfg::GW>(bar_id); nrec = rec_addr(nxt, jbn); }
                 const uint4 nb_ = lds_v4(nrec + Cfg::REC_B);
-                lat_step<ALGO, DUAL, SCSH, HIST, SH, MEAS>(g, hist_row, hist_writer, c, xa, xb, (int)nb_.x,
+                uint4 xc = make_uint4(0, 0, 0, 0);
+                if constexpr (SH) xc = lds_v4(rec + Cfg::REC_C);
+                lat_step<ALGO, DUAL, SCSH, HIST, SH, MEAS>(g, hist_row, hist_writer, c, xa, xb, xc, (int)nb_.x,
                                                        lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j));
             }
         };
@@ -738,6 +784,9 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     if (!piped) {
                         p0a = lds_v4(rec_addr(cur, 0)); p0b = lds_v4(rec_addr(cur, 0) + Cfg::REC_B);
                         p1a = lds_v4(rec_addr(cur, 1)); p1b = lds_v4(rec_addr(cur, 1) + Cfg::REC_B);
+                        if constexpr (SH) {
+                            p0c = lds_v4(rec_addr(cur, 0) + Cfg::REC_C); p1c = lds_v4(rec_addr(cur, 1) + Cfg::REC_C);
+                        }
                     }
                     for (uint32_t kk = 0; kk < bt.n; ++kk) {
                         const uint32_t nxt = cur ^ (uint32_t)Cfg::BUF;
@@ -745,6 +794,9 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                         else full_round(std::false_type{}, cur, nxt, log_q + lbuf);
                         cur = nxt;
                         lbuf = (lbuf == 2u * Cfg::LOGB) ? 0u : lbuf + (uint32_t)Cfg::LOGB;
+                        if constexpr (SH) {
+                            if (++flush_ctr == Cfg::FLUSH) { flush_hist(); flush_ctr = 0; }
+                        }
                     }
                     piped = true;
                 } else {
@@ -754,6 +806,9 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     cur = nxt;
                     lbuf = (lbuf == 2u * Cfg::LOGB) ? 0u : lbuf + (uint32_t)Cfg::LOGB;
                     piped = false;
+                    if constexpr (SH) {
+                        if (++flush_ctr == Cfg::FLUSH) { flush_hist(); flush_ctr = 0; }
+                    }
                 }
                 s = bt.s_next;
             }
@@ -761,6 +816,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
 
         if (first) group_barrier<Cfg::GW>(bar_id);                             // empty step range: meet the producer once
         group_barrier<Cfg::GW>(bar_id);                                        // every step is logged: the accountant may finish
+        flush_hist();
         if (live) {
             // a closed worm sits on its tail (head holds the folded kick of the step after the last)
             a.head[cl] = (c.closed ? c.tail : c.head) / SC;
@@ -817,7 +873,7 @@ LatPlan lat_plan(int L, int CH, bool hist, int smem_optin)
     const int NP = (CH == 32) ? (sh ? 4 : 8) : (CH == 8) ? 2 : 1;
     const int R = 64 * NP / CH;
     const size_t histb = sh ? (size_t)CH * N * 2 : 0;
-    const size_t recw = (size_t)4 * R * CH * 16;
+    const size_t recw = (size_t)(sh ? 6 : 4) * R * CH * 16;
     const size_t logw = (size_t)3 * 2 * (R + 4) * CH;
     for (int dual = 1; dual >= 0; --dual) {
         if (!dual && CH != 1) continue;
@@ -836,6 +892,8 @@ LatPlan lat_plan(int L, int CH, bool hist, int smem_optin)
             p.g.rec_off = (int)(nw * region);
             p.g.log_off = (int)(nw * (region + recw));
             p.g.hist_off = (int)((nw * (region + recw + logw) + 15) / 16 * 16);
+            p.g.HXF = 2 | ((L / 2 - 1) << 7);
+            p.g.HYF = (L - 1) * L * 64;
             p.g.lowt = 0;
             p.g.zero = 0;
             return p;
