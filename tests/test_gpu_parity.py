@@ -329,12 +329,14 @@ def test_philox_segment_edges_match_oracle(eng, lanes):
         assert (st.hist.cpu().numpy() == hist).all(), (lanes, chunks)
 
 
-@pytest.mark.parametrize("L,lanes", [(64, 32), (128, 32), (256, 32), (64, 0), (128, 0), (256, 0)])
+@pytest.mark.parametrize("L,lanes", [(64, 32), (128, 32), (256, 32), (64, 0), (128, 0), (256, 0), (64, 8), (64, 4)])
 def test_philox_large_lattices_match_oracle(eng, L, lanes):
-    """L = 64 / 128 (one chain per walker, dual layout) and L = 256 (compact layout, one chain per block)."""
+    """L = 64 (one chain per walker in the dual layout; three walkers of 4 chains or one of 8 for big
+    batches), L = 128 (compact layout, four walkers of one chain) and L = 256 (compact, one chain per block).
+    14 chains: more than a block of any variant, with ragged last blocks."""
     from oracle import worm_oracle as wo
-    n = 5
-    T = np.array([2.269, 1.2, 3.0, 2.0, 2.5])
+    n = 14
+    T = np.array([2.269, 1.2, 3.0, 2.0, 2.5, 2.269, 1.5, 3.5, 2.1, 2.4, 2.269, 1.0, 2.8, 2.2])
     seeds = np.arange(n, dtype=np.uint64) + 3
     st = eng.PhiloxState(L, T, seeds, algo=0, max_dumps=4).run(20000, therm_steps=1000, dump_every=50, lanes_per_chain=lanes)
     acc, bonds = st.acc.cpu().numpy(), st.bonds.cpu().numpy()

@@ -35,6 +35,7 @@
 //
 // Algorithm and random stream: oracle/worm_oracle.c:worm_oracle_philox_run (bit-for-bit), i.e. the
 // reference loop worm_ising_2d.cpp:111-157 on a Philox4x32-10 stream.
+#include <cstdlib>
 #include <type_traits>
 
 #include "worm_run.cuh"
@@ -875,14 +876,21 @@ LatPlan lat_plan(int L, int CH, bool hist, int smem_optin)
     const size_t histb = sh ? (size_t)CH * N * 2 : 0;
     const size_t recw = (size_t)(sh ? 6 : 4) * R * CH * 16;
     const size_t logw = (size_t)3 * 2 * (R + 4) * CH;
+    // Throughput = (chains in flight) / (cycles per step): of the (layout, walkers per block) pairs that
+    // fit, take the one with the most chains per block; the dual layout wins ties (fewer instructions in
+    // front of the bond load).  WORM_LAT_LAYOUT=dual|compact pins the layout (experiments).
+    const char *pin = getenv("WORM_LAT_LAYOUT");
+    int best = 0;
     for (int dual = 1; dual >= 0; --dual) {
         if (!dual && CH != 1) continue;
+        if (pin && ((pin[0] == 'd') != (dual == 1))) continue;
         const size_t region = dual ? (size_t)4 * N * CH : (size_t)2 * N;
-        for (int nw : {4, 2, 1}) {
-            if (nw != 4 && CH != 1 && CH != 32) continue;
+        for (int nw : {4, 3, 2, 1}) {
             if (CH == 32 && nw != 1) continue;
+            if (nw * CH <= best) continue;
             const size_t need = (nw * (region + recw + logw) + 15) / 16 * 16 + histb;
             if (need + 1024 > (size_t)smem_optin) continue;
+            best = nw * CH;
             p.ok = true; p.dual = dual; p.smem = need;
             p.g.L = L; p.g.N = N; p.g.nb2 = 2 * N; p.g.nw = nw;
             p.g.SC = dual ? 4 * CH : 2;
@@ -896,7 +904,6 @@ LatPlan lat_plan(int L, int CH, bool hist, int smem_optin)
             p.g.HYF = (L - 1) * L * 64;
             p.g.lowt = 0;
             p.g.zero = 0;
-            return p;
         }
     }
     return p;

@@ -14,15 +14,24 @@ cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, bool lowt, i
         // of dependent steps, so throughput = (chains in flight) / (cycles per step), and the latency
         // kernel has by far the fewest cycles per step; batches larger than one wave simply run in
         // waves.  32 chains per walker ("solo", code 2) when the lattice allows it and the batch has
-        // at least two blocks, else one chain per walker (code 32), else 4 or 8.  Thread-per-chain
-        // (code 1) is left for lattices that are not a power of two or do not fit.
-        (void)sm_count;
+        // at least two blocks; else the variant with the most chains per block (8, 4 or 1 chains per
+        // walker, codes 4 / 8 / 32) once the batch exceeds one chain per walker of a full wave, and one
+        // chain per walker below that (fewest cycles per step).  Thread-per-chain (code 1) is left for
+        // lattices that are not a power of two or do not fit.
         G = 1;
         if (a.L >= 4 && !(a.L & (a.L - 1))) {
             if (lat_smem_bytes(a.L, 2, hist, smem_optin) && a.n_chains >= 64) G = 2;
-            else if (lat_smem_bytes(a.L, 32, hist, smem_optin)) G = 32;
-            else if (lat_smem_bytes(a.L, 8, hist, smem_optin)) G = 8;
-            else if (lat_smem_bytes(a.L, 4, hist, smem_optin)) G = 4;
+            else {
+                const int c32 = lat_chains_per_block(a.L, 32, hist, smem_optin);
+                int best = c32;
+                if (c32) G = 32;
+                if (!c32 || a.n_chains > (int64_t)c32 * sm_count) {
+                    for (int g : {8, 4}) {
+                        const int c = lat_chains_per_block(a.L, g, hist, smem_optin);
+                        if (c > best) { best = c; G = g; }
+                    }
+                }
+            }
         }
     }
     if (G == 2 || G == 4 || G == 8 || G == 32) {
