@@ -334,6 +334,7 @@ def run_b200_arm(a) -> None:
                 "worm_steps_per_s_per_gpu": kern_rate,
                 "peak_source": "148 SM x 128 lanes x sm_max_mhz (MEASURED_PEAKS.json)" if peaks else "fallback 1965 MHz",
                 "cycles_per_step_per_chain": f_max * n / kern_rate}
+    shapes = bench_shapes(torch, engine, dev, algo, issue_peak)
     roofline_blocking = bench_blocking(torch, engine, dev, peaks)
     roofline_pca = bench_pca(torch, engine, dev, peaks, cpu=(world == 1 and not a.no_cpu))
     pipeline_c3 = bench_pipeline(torch, engine, dev, peaks, cpu=(world == 1 and not a.no_cpu))
@@ -357,6 +358,7 @@ def run_b200_arm(a) -> None:
         "gpu_launches": a.steps * st.launches_per_run,
         "clocks": clocks,
         "roofline": roofline,
+        "lattice_shapes": shapes,
         "roofline_blocking": roofline_blocking,
         "roofline_pca": roofline_pca,
         "pipeline_c3": pipeline_c3,
@@ -367,6 +369,32 @@ def run_b200_arm(a) -> None:
     emit(line)
     if world > 1:
         td.destroy_process_group()
+
+
+def bench_shapes(torch, engine, dev, algo, issue_peak) -> list:
+    """The other lattice shapes BASELINE.json names (configs[0], [2], [3], [4]) on this GPU: worm steps/s and
+    independent sweeps/s of a 64-temperature sweep, state resident, CUDA events around one launch, and the
+    fraction of the same issue roofline (I_ALG thread-instructions per step).  Not the headline: the kernel
+    variant and the chains a block holds change with L."""
+    out = []
+    cases = [(16, 4096, 400_000, False), (32, 4096, 400_000, True), (64, 4096, 100_000, False),
+             (128, 1024, 100_000, False), (256, 512, 100_000, False), (32, 125_000, 20_000, True)]
+    for L, n, steps, hist in cases:
+        t_idx = np.arange(n) % N_T
+        T = sweep_temperatures()[t_idx]
+        seeds = (np.arange(n) // N_T).astype(np.uint64)
+        st = engine.PhiloxState(L, T, seeds, algo=algo, device=dev, group_index=t_idx, n_groups=N_T, hist=hist)
+        st.run(max(steps // 10, 1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record(); st.run(steps); e1.record()
+        torch.cuda.synchronize(dev)
+        rate = float(n) * steps / (e0.elapsed_time(e1) * 1e-3)
+        out.append({"L": L, "chains": n, "worm_steps_per_chain": steps, "G_r_histograms": hist,
+                    "worm_steps_per_s": rate, "sweeps_per_s": rate / (2 * L * L),
+                    "issue_roofline_frac": rate * I_ALG / issue_peak})
+        del st
+    return out
 
 
 def bench_pipeline(torch, engine, dev, peaks, cpu: bool) -> dict:
