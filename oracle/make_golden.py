@@ -85,6 +85,27 @@ def gen_runs():
         json.dump(out, f, indent=1)
 
 
+STAT_L, STAT_STEPS, STAT_SEEDS = 16, 2_000_000, 24
+STAT_T = [2.0, 2.1, 2.2, 2.269, 2.3, 2.4, 2.5, 2.6]
+
+
+def gen_stats():
+    """Statistics of the UNMODIFIED reference executable for the production-mode (Philox) comparison:
+    per (T, seed) the three numbers of output.txt that are estimators (Z_av, E_av, step_num;
+    worm_ising_2d.cpp:183-191).  24 seeds x 8 temperatures x 2e6 steps of L = 16: ~30 s on one core."""
+    E = np.zeros((len(STAT_T), STAT_SEEDS))
+    Zav = np.zeros_like(E)
+    steps = np.zeros(E.shape, dtype=np.int64)
+    for i, T in enumerate(STAT_T):
+        for k in range(STAT_SEEDS):
+            r = rr.run_ref(STAT_L, T, STAT_STEPS, float(100 + k), 0)
+            E[i, k], Zav[i, k], steps[i, k] = r.E_av, r.Z_av, r.step_num
+        print("ref stats T=%.3f: E = %.6f +- %.6f" % (T, E[i].mean(), E[i].std(ddof=1) / np.sqrt(STAT_SEEDS)))
+    with open(os.path.join(GOLD, "ref_stats.json"), "w") as f:
+        json.dump(dict(L=STAT_L, num_steps=STAT_STEPS, seeds=[100 + k for k in range(STAT_SEEDS)], T=STAT_T,
+                       E_av=E.tolist(), Z_av=Zav.tolist(), step_num=steps.tolist()), f, indent=1)
+
+
 def import_reference():
     """Import the reference's Python modules unmodified, with the App. F shims."""
     import pandas as pd
@@ -326,6 +347,8 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "runs"):
         gen_runs()
+    if what in ("all", "stats"):
+        gen_stats()
     if what in ("all", "post"):
         gen_post()
     if what in ("all", "pca"):

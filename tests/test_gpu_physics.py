@@ -104,6 +104,47 @@ def test_correlation_function_G_r(eng):
     assert abs(gx) < 3.5 * sx
 
 
+def test_production_mode_matches_reference_executable_statistics(eng, golden_dir):
+    """BASELINE north star: the Philox mode reproduces the REFERENCE's own estimates within 3 sigma.
+    `tests/golden/ref_stats.json` holds Z_av and E_av of the unmodified executable for 24 seeds at 8
+    temperatures of L = 16 (oracle/make_golden.py stats).  Same chain law, same start (empty lattice,
+    head = tail = 0), same estimator: the reference never excludes its warm-up from the sums
+    (worm_ising_2d.cpp:113 gates only the writing), so the GPU run measures from step 0 as well and both
+    have the same expectation.  sigma = standard error over independent seeds on both sides; the
+    reference's C_V (finite differences of E(T), specific_heat.py:134-150) is compared on the mean
+    curves with a delete-one-seed jackknife on both sides."""
+    import json
+    from worm_algorithm_b200 import stats
+    from worm_algorithm_b200.specific_heat import finite_difference_cv
+    with open(os.path.join(golden_dir, "ref_stats.json")) as f:
+        g = json.load(f)
+    L, steps, temps = g["L"], g["num_steps"], np.array(g["T"])
+    N = L * L
+    refE, refZ = np.array(g["E_av"]), np.array(g["Z_av"])            # [T][seed]
+    reps = 64
+    T = np.tile(temps, reps)
+    seeds = (np.arange(T.size) + 31337).astype(np.uint64)
+    st = eng.PhiloxState(L, T, seeds, algo=0)
+    st.run(steps, therm_steps=0)
+    acc = st.acc.cpu().numpy().reshape(reps, temps.size, 8)
+    obs = stats.taylor_observables(acc, temps, N)                    # per chain, like one output.txt each
+    for name, ref in (("E", refE), ("Z_av", refZ)):
+        m, se = stats.replica_mean_err(obs[name], axis=0)
+        rm, rse = stats.replica_mean_err(ref, axis=1)
+        z = (m - rm) / np.sqrt(se ** 2 + rse ** 2)
+        assert (np.abs(z) < 3.0).all(), (name, z)
+
+    def cv_with_err(E):                                              # E: [seed][T]
+        R = E.shape[0]
+        full = np.asarray(finite_difference_cv(temps, E.mean(axis=0))[1])
+        loo = np.array([finite_difference_cv(temps, np.delete(E, k, axis=0).mean(axis=0))[1] for k in range(R)])
+        return full, np.sqrt((R - 1) / R * ((loo - loo.mean(axis=0)) ** 2).sum(axis=0))
+    c, ce = cv_with_err(obs["E"])
+    rc, rce = cv_with_err(refE.T)
+    zc = (c - rc) / np.sqrt(ce ** 2 + rce ** 2)
+    assert c.size == temps.size - 4 and (np.abs(zc) < 3.0).all(), zc
+
+
 def test_lat_and_wide_kernels_agree_at_scale(eng):
     """BASELINE configs[4] shape, scaled: 16384 independent L = 32 chains with G(r) histograms; the
     thread-per-chain kernel and the latency kernel give identical reduced sums and histograms."""
