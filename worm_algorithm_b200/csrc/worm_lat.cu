@@ -37,6 +37,7 @@
 // reference loop worm_ising_2d.cpp:111-157 on a Philox4x32-10 stream.
 #include <cstdlib>
 #include <type_traits>
+#include <utility>
 
 #include "worm_run.cuh"
 
@@ -120,10 +121,19 @@ __device__ __forceinline__ void group_barrier(int id)
     asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(32 * GW) : "memory");
 }
 
+template <int... Js, class F>
+__device__ __forceinline__ void unroll_steps(std::integer_sequence<int, Js...>, F &&f)
+{
+    (f(std::integral_constant<int, Js>{}), ...);
+}
+
 struct LatState {
     int head, tail;      // scaled site indices (site * SC)
     uint32_t closed;     // 0 / 1.  When 1, head already holds the (folded) kick of the coming step.
     uint32_t dh;         // solo mode with histograms: head - tail in bin-address format (0 iff closed)
+    uint32_t aword, cword;   // full rounds: accept / closed log bytes of up to four steps, stored as one word each
+    uint32_t addr, nb;   // dual layout: shared address of the coming step's bond and its occupation, loaded
+                         // at the end of the previous step (right behind that step's bond stores)
 };
 
 // Observables are NOT accumulated by the walker (every instruction of its dependent chain costs
@@ -143,7 +153,7 @@ struct Account {
 //                 the bond is read at head + p and written at head + p and nh + q
 //        compact: p = addneg, q = address of bond byte (y bit) of site 0: the bond is owned by
 //                 own = (head & keep) | ((head + addneg) & ~keep) and lives at own + q
-//   rb = {kick, thr, flip, logbits}:  accept iff (nb < thr) xor (flip != 0);  Taylor: nb += 1 | flip
+//   rb = {kick, thr, delta, logbits}:  accept iff (nb < thr) xor (delta < 0);  Taylor: nb += delta (+1 / -1)
 //   rc = {addh, keeph, gaph, -} (solo mode with histograms): the same move applied to the displacement
 //        head - tail kept in bin-address format,  dh' = (dh & keeph) | (((dh | gaph) + addh) & ~keeph).
 //        Bin s = dy * L + dx of a chain lives at (s >> 1) * 128 + (s & 1) * 2 of the chain's bank, so
@@ -197,7 +207,7 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
             qd = (uint32_t)(q2 < 256ull ? q2 : 256ull);
         }
         rb.y = dec ? qd : qi;
-        rb.z = dec ? 0xffffffffu : 0u;
+        rb.z = dec ? 0xffffffffu : 1u;                           // occupation change; negative = flipped test
         rb.w = dec ? 0xc0u : 0x80u;                              // accept-log bits
     } else {
         rb.y = ((uint64_t)a < prm.hfix) ? 0u : 1u;               // accept iff nb >= thr (occupied: always)
@@ -209,10 +219,14 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
 // One worm step on a pre-decoded record.  On entry `head` already holds this step's kick when the
 // worm is closed; on exit it holds the NEXT step's kick (kick_next) when the worm is closed then.
 // alog / clog: shared addresses of this step's accept / closed log bytes.
-template <int ALGO, bool DUAL, int SCSH, bool HIST, bool SH, bool MEAS>
+// LOGK < 0: the log bytes are stored one by one.  LOGK = 0..3 (full rounds, step j = LOGK mod 4): they are
+// gathered in two registers and stored as one 32-bit word each after every fourth step -- a lone warp issues
+// a shared-memory instruction every ~4 cycles, and the ones between the accept test and the next bond load
+// are on the head -> head recurrence.
+template <int ALGO, bool DUAL, int SCSH, bool HIST, bool SH, bool MEAS, int LOGK = -1>
 __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long hist_row, uint32_t hist_writer,
                                          LatState &c, const uint4 ra, const uint4 rb, const uint4 rc, const int kick_next,
-                                         const uint32_t alog, const uint32_t clog)
+                                         const uint32_t p_next, const uint32_t alog, const uint32_t clog)
 {
     const int add = (int)ra.x, keep = (int)ra.y;
     const int kick = (int)rb.x;
@@ -233,15 +247,20 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
     uint32_t addr, addr2 = 0u;
     const int t = head + add;
     const int nh = (head & keep) | (t & ~keep);                 // neighbour table :88-95
+    uint32_t nb;
     if constexpr (DUAL) {
-        addr = (uint32_t)head + ra.z;                           // bond_number :214-244: slot d of this site ...
+        // bond_number :214-244: slot d of this site (address head + ra.z, formed and loaded by the previous
+        // step as soon as its head was selected: the load is the long pole of the head -> head recurrence,
+        // so it is issued right behind that step's stores instead of behind this step's address arithmetic)
+        addr = c.addr;
+        nb = c.nb;                                              // :139
         addr2 = (uint32_t)nh + ra.w;                            // ... and slot d^2 of the neighbour
     } else {
         const int u = head + (int)ra.z;
         const int own = (head & keep) | (u & ~keep);
         addr = (uint32_t)own + ra.w;
+        nb = lds_u8(addr);                                      // :139
     }
-    const uint32_t nb = lds_u8(addr);                           // :139
     // Solo mode with histograms: G(r) bin of (head - tail) before the move; a closed worm is bin 0
     // (dh == 0).  The chain's 16-bit bins live in its own bank and only this lane touches them between
     // the walker's flushes, so the count is a plain load / add / store (a shared-memory atomic costs
@@ -257,8 +276,11 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
     // closed iteration (worm_ising_2d.cpp:130-132): logged, measured by the accountant.  After the
     // load in program order: a store ahead of it would sit on the load's issue path (the compiler
     // cannot reorder shared-memory accesses that may alias).
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u8 [%1], %2;\n\t}"
-                 :: "r"(c.closed), "r"(clog), "r"(logbits) : "memory");
+    if constexpr (LOGK < 0)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u8 [%1], %2;\n\t}"
+                     :: "r"(c.closed), "r"(clog), "r"(logbits) : "memory");
+    else
+        c.cword = (LOGK == 0 ? 0u : c.cword) + (c.closed << (8 * LOGK));
     const uint32_t pc = (nh == tail) ? 1u : 0u;                 // closed after an accepted move?
     const int A = pc ? kick_next : nh;                          // head if accepted (kick folded in)
     const int B = closed ? kick_next : head;                    // head if rejected
@@ -266,29 +288,65 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
     // the first consumer of nb: the warp issues in order and stalls at that consumer, so everything
     // that does not depend on the load must sit in front of it (in the load's shadow), not behind
     const uint32_t thrx = thr | ((uint32_t)(A ^ B ^ (int)addr2 ^ (int)dnew) & (uint32_t)g.zero);
-    const uint32_t nn = (ALGO == ALGO_TAYLOR) ? nb + (1u | flip) : (nb ^ 1u);
+    const uint32_t nn = (ALGO == ALGO_TAYLOR) ? nb + flip : (nb ^ 1u);
     const uint32_t lg = (nb & 1u) | logbits;
     // accept test (:151), head select, bond stores (:152-154) and the accept-log byte in one opaque
     // block: the compiler must not re-associate "closed ? kick : ..." across the select.
     int head_new;
     uint32_t acc_i;
-    if constexpr (DUAL) {
+    if constexpr (DUAL && LOGK < 0) {
         asm volatile("{\n\t.reg .pred pa, pd;\n\t"
-                     "setp.lt.u32 pa, %2, %3;\n\t"
-                     "setp.ne.s32 pd, %4, 0;\n\t"
+                     "setp.lt.u32 pa, %4, %5;\n\t"
+                     "setp.lt.s32 pd, %6, 0;\n\t"
                      "xor.pred pa, pa, pd;\n\t"
-                     "selp.b32 %0, %5, %6, pa;\n\t"
+                     "selp.b32 %0, %7, %8, pa;\n\t"
+                     "add.u32 %2, %0, %14;\n\t"
                      "selp.u32 %1, 1, 0, pa;\n\t"
-                     "@pa st.shared.u8 [%7], %9;\n\t"
-                     "@pa st.shared.u8 [%8], %9;\n\t"
-                     "@pa st.shared.u8 [%10], %11;\n\t}"
-                     : "=&r"(head_new), "=&r"(acc_i)
-                     : "r"(nb), "r"(thrx), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(addr2), "r"(nn), "r"(alog), "r"(lg)
+                     "@pa st.shared.u8 [%9], %11;\n\t"
+                     "@pa st.shared.u8 [%10], %11;\n\t"
+                     "ld.shared.u8 %3, [%2];\n\t"
+                     "@pa st.shared.u8 [%12], %13;\n\t}"
+                     : "=&r"(head_new), "=&r"(acc_i), "=&r"(c.addr), "=&r"(c.nb)
+                     : "r"(nb), "r"(thrx), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(addr2), "r"(nn), "r"(alog), "r"(lg),
+                       "r"(p_next)
                      : "memory");
+    } else if constexpr (DUAL) {
+        uint32_t lgs;
+        asm volatile("{\n\t.reg .pred pa, pd;\n\t.reg .b32 nv, nw;\n\t"
+                     "setp.lt.u32 pa, %5, %6;\n\t"
+                     "setp.lt.s32 pd, %7, 0;\n\t"
+                     "xor.pred pa, pa, pd;\n\t"
+                     "selp.b32 %0, %8, %9, pa;\n\t"
+                     "selp.b32 nv, %10, %15, pa;\n\t"
+                     "selp.b32 nw, %11, %15, pa;\n\t"
+                     "st.shared.u8 [nv], %12;\n\t"
+                     "st.shared.u8 [nw], %12;\n\t"
+                     "add.u32 %2, %0, %14;\n\t"
+                     "ld.shared.u8 %3, [%2];\n\t"
+                     "selp.u32 %1, 1, 0, pa;\n\t"
+                     "selp.b32 %4, %13, 0, pa;\n\t}"
+                     : "=&r"(head_new), "=&r"(acc_i), "=&r"(c.addr), "=&r"(c.nb), "=&r"(lgs)
+                     : "r"(nb), "r"(thrx), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(addr2), "r"(nn), "r"(lg), "r"(p_next), "r"(alog)
+                     : "memory");
+        c.aword = (LOGK == 0 ? 0u : c.aword) + (lgs << (8 * LOGK));
+    } else if constexpr (LOGK >= 0) {
+        uint32_t lgs;
+        asm volatile("{\n\t.reg .pred pa, pd;\n\t"
+                     "setp.lt.u32 pa, %3, %4;\n\t"
+                     "setp.lt.s32 pd, %5, 0;\n\t"
+                     "xor.pred pa, pa, pd;\n\t"
+                     "selp.b32 %0, %6, %7, pa;\n\t"
+                     "selp.u32 %1, 1, 0, pa;\n\t"
+                     "@pa st.shared.u8 [%8], %9;\n\t"
+                     "selp.b32 %2, %10, 0, pa;\n\t}"
+                     : "=&r"(head_new), "=&r"(acc_i), "=&r"(lgs)
+                     : "r"(nb), "r"(thrx), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(nn), "r"(lg)
+                     : "memory");
+        c.aword = (LOGK == 0 ? 0u : c.aword) + (lgs << (8 * LOGK));
     } else {
         asm volatile("{\n\t.reg .pred pa, pd;\n\t"
                      "setp.lt.u32 pa, %2, %3;\n\t"
-                     "setp.ne.s32 pd, %4, 0;\n\t"
+                     "setp.lt.s32 pd, %4, 0;\n\t"
                      "xor.pred pa, pa, pd;\n\t"
                      "selp.b32 %0, %5, %6, pa;\n\t"
                      "selp.u32 %1, 1, 0, pa;\n\t"
@@ -300,6 +358,10 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
     }
     c.head = head_new;
     c.closed = acc_i ? pc : c.closed;
+    if constexpr (LOGK == 3) {
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(alog - 3u), "r"(c.aword) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(clog - 3u), "r"(c.cword) : "memory");
+    }
     if constexpr (HIST && SH) {
         c.dh = acc_i ? dnew : c.dh;
         if constexpr (MEAS) sts_u16(ha, hv + hist_writer);
@@ -483,6 +545,10 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
     {
         uint32_t *lg = reinterpret_cast<uint32_t *>(smem8 + g.log_off);
         for (int i = tid; i < nw * Cfg::LOGW / 4; i += nthreads) lg[i] = 0u;
+        // the record rings too: the last step of a launch forms (and loads) the address of a step that no
+        // producer has built -- 0 keeps that address inside the block's bond storage
+        uint32_t *rr = reinterpret_cast<uint32_t *>(smem8 + g.rec_off);
+        for (int i = tid; i < nw * Cfg::RECW / 4; i += nthreads) rr[i] = 0u;
         if constexpr (SH) {
             uint32_t *hb = reinterpret_cast<uint32_t *>(smem8 + g.hist_off);
             for (int i = tid; i < CH * g.N / 2; i += nthreads) hb[i] = 0u;
@@ -694,6 +760,8 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         c.tail = SC * a.tail[cl];
         c.closed = (c.head == c.tail) ? 1u : 0u;
         c.dh = 0u;
+        c.addr = sbase; c.nb = 0u;
+        c.aword = c.cword = 0u;
         if constexpr (SH) {
             const int hs = a.head[cl], ts = a.tail[cl];
             const int dx = (hs - ts) & (g.L - 1);
@@ -713,18 +781,19 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         uint4 p0c = make_uint4(0, 0, 0, 0), p1c = make_uint4(0, 0, 0, 0);      // SH only
         auto full_round = [&](auto meas_tag, uint32_t cur, uint32_t nxt, uint32_t lg) {
             constexpr bool MEAS = decltype(meas_tag)::value;
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
+            static_assert(R % 4 == 0, "log words hold four steps");
+            unroll_steps(std::make_integer_sequence<int, R>{}, [&](auto jc) {
+                constexpr int j = decltype(jc)::value;
                 if (j == R - 2) group_barrier<Cfg::GW>(bar_id);
                 const uint32_t nrec = (j < R - 2) ? rec_addr(cur, j + 2) : rec_addr(nxt, j + 2 - R);
                 const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
                 uint4 fc = make_uint4(0, 0, 0, 0);
                 if constexpr (SH) fc = lds_v4(nrec + Cfg::REC_C);
-                lat_step<ALGO, DUAL, SCSH, HIST, SH, MEAS>(g, hist_row, hist_writer, c, p0a, p0b, p0c, (int)p1b.x,
-                                                       lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j));
+                lat_step<ALGO, DUAL, SCSH, HIST, SH, MEAS, j % 4>(g, hist_row, hist_writer, c, p0a, p0b, p0c, (int)p1b.x, p1a.z,
+                                                              lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j));
                 p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
                 if constexpr (SH) { p0c = p1c; p1c = fc; }
-            }
+            });
         };
         // Any other round (segment edges): steps [jb, je), records straight from shared memory.  The
         // kick folded into the last step is the first record of the next round (slot jbn of `nxt`).
@@ -736,9 +805,11 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 uint32_t nrec = rec_addr(cur, j + 1);
                 if (j == je - 1) { group_barrier<Cfg::GW>(bar_id); nrec = rec_addr(nxt, jbn); }
                 const uint4 nb_ = lds_v4(nrec + Cfg::REC_B);
+                uint32_t pn = 0u;
+                if constexpr (DUAL) pn = lds_u32(nrec + 8u);         // ra.z of the next step's record
                 uint4 xc = make_uint4(0, 0, 0, 0);
                 if constexpr (SH) xc = lds_v4(rec + Cfg::REC_C);
-                lat_step<ALGO, DUAL, SCSH, HIST, SH, MEAS>(g, hist_row, hist_writer, c, xa, xb, xc, (int)nb_.x,
+                lat_step<ALGO, DUAL, SCSH, HIST, SH, MEAS>(g, hist_row, hist_writer, c, xa, xb, xc, (int)nb_.x, pn,
                                                        lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j));
             }
         };
@@ -779,6 +850,10 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     group_barrier<Cfg::GW>(bar_id);                  // the first round's records are complete
                     const uint4 kb = lds_v4(rec_addr(cur, bt.jb) + Cfg::REC_B);
                     c.head = c.closed ? (int)kb.x : c.head;          // kick of the first step
+                    if constexpr (DUAL) {                            // ... and its bond
+                        c.addr = (uint32_t)c.head + lds_u32(rec_addr(cur, bt.jb) + 8u);
+                        c.nb = lds_u8(c.addr);
+                    }
                     first = false;
                 }
                 if (bt.jb == 0 && bt.je == R) {
