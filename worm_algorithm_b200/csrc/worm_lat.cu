@@ -226,7 +226,7 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
 template <int ALGO, bool DUAL, int SCSH, bool HIST, bool SH, bool MEAS, int LOGK = -1>
 __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long hist_row, uint32_t hist_writer,
                                          LatState &c, const uint4 ra, const uint4 rb, const uint4 rc, const int kick_next,
-                                         const uint32_t p_next, const uint32_t alog, const uint32_t clog)
+                                         const uint32_t p_next, const uint32_t alog, const uint32_t clog, const uint32_t dummy = 0u)
 {
     const int add = (int)ra.x, keep = (int)ra.y;
     const int kick = (int)rb.x;
@@ -311,6 +311,10 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
                        "r"(p_next)
                      : "memory");
     } else if constexpr (DUAL) {
+        // Full rounds.  The two bond stores are unpredicated and take their ADDRESS by select: a guard
+        // predicate is ready ~13 cycles after its ISETP, a select operand after 4, and the next bond load has
+        // to follow the stores (the next step may walk straight back).  A rejected move writes the occupation
+        // it would have stored to `dummy`, the padding byte of the chain's log row.
         uint32_t lgs;
         asm volatile("{\n\t.reg .pred pa, pd;\n\t.reg .b32 nv, nw;\n\t"
                      "setp.lt.u32 pa, %5, %6;\n\t"
@@ -326,7 +330,7 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
                      "selp.u32 %1, 1, 0, pa;\n\t"
                      "selp.b32 %4, %13, 0, pa;\n\t}"
                      : "=&r"(head_new), "=&r"(acc_i), "=&r"(c.addr), "=&r"(c.nb), "=&r"(lgs)
-                     : "r"(nb), "r"(thrx), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(addr2), "r"(nn), "r"(lg), "r"(p_next), "r"(alog)
+                     : "r"(nb), "r"(thrx), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(addr2), "r"(nn), "r"(lg), "r"(p_next), "r"(dummy)
                      : "memory");
         c.aword = (LOGK == 0 ? 0u : c.aword) + (lgs << (8 * LOGK));
     } else if constexpr (LOGK >= 0) {
@@ -782,6 +786,8 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         auto full_round = [&](auto meas_tag, uint32_t cur, uint32_t nxt, uint32_t lg) {
             constexpr bool MEAS = decltype(meas_tag)::value;
             static_assert(R % 4 == 0, "log words hold four steps");
+            uint32_t pad = lg + (uint32_t)R;         // padding byte of the chain's log row: where a rejected move's stores go
+            asm volatile("" : "+r"(pad));            // (a register, not base + immediate: one address for all steps)
             unroll_steps(std::make_integer_sequence<int, R>{}, [&](auto jc) {
                 constexpr int j = decltype(jc)::value;
                 if (j == R - 2) group_barrier<Cfg::GW>(bar_id);
@@ -790,7 +796,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 uint4 fc = make_uint4(0, 0, 0, 0);
                 if constexpr (SH) fc = lds_v4(nrec + Cfg::REC_C);
                 lat_step<ALGO, DUAL, SCSH, HIST, SH, MEAS, j % 4>(g, hist_row, hist_writer, c, p0a, p0b, p0c, (int)p1b.x, p1a.z,
-                                                              lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j));
+                                                              lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j), pad);
                 p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
                 if constexpr (SH) { p0c = p1c; p1c = fc; }
             });
