@@ -62,11 +62,14 @@ struct LatGeo {
 // SH: per-chain G(r) bins in shared memory (solo mode with histograms): rounds are half as long to
 // make room for them.
 template <int CH, bool SH = false> struct LatCfg {
-    static constexpr int NP = (CH == 32) ? (SH ? 4 : 8) : (CH == 8) ? 2 : 1;   // producer warps per walker (one Philox block per lane per round)
+    static constexpr int NP = (CH == 32) ? 8 : (CH == 8) ? 2 : 1;   // producer warps per walker
+    static constexpr int RPL = SH ? 1 : 2;            // step records a producer lane builds per round (one Philox block
+                                                      // holds two steps; SH: the two lanes of a pair both draw it and
+                                                      // build one record each -- eight steps per round need 256 records)
     static constexpr int ACH = (CH > 8) ? 8 : CH;     // chains per accountant warp
     static constexpr int NA = CH / ACH;               // accountant warps per walker
     static constexpr int GW = NP + NA + 1;            // warps of a group: producers, accountants, walker
-    static constexpr int R = 64 * NP / CH;            // steps per chain per round
+    static constexpr int R = 32 * NP * RPL / CH;      // steps per chain per round
     static constexpr int BUF = R * CH * 16;           // bytes of one buffer of A (or B) records
     static constexpr int REC_B = 2 * BUF;             // byte offset of the B records (two buffers of A first)
     static constexpr int REC_C = 4 * BUF;             // SH: byte offset of the C records (displacement update)
@@ -565,16 +568,18 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         // Philox block b = u*32 + lane of a round (u = role: the group's two producers take one
         // block each) belongs to chain slot q = b % CH, pair p = b / CH: consecutive lanes store
         // consecutive 16-byte records (conflict-free 128-bit stores).
+        // (SH: record b = u*32 + lane is step j = b / CH of the round, half j & 1 of pair j >> 1)
         const int b = u * 32 + lane;
         const int q = b % CH;
-        const int p_of = b / CH;
+        const int p_of = (Cfg::RPL == 2) ? b / CH : (b / CH) >> 1;
+        const int half = (b / CH) & 1;
         const int64_t cg = chain0 + w * CH + q;
         const int64_t cl = cg < a.n_chains ? cg : 0;
         const PhiloxChain prm = a.prm[cl];
         const uint64_t chain_id = a.chain_id0 + (uint64_t)cl;
         const uint32_t c2 = (uint32_t)chain_id, c3 = (uint32_t)(chain_id >> 32);
         const uint32_t chain_abs = region_abs + (DUAL ? (uint32_t)q * 4u : 0u);
-        const uint32_t rec_q = rec_w + (uint32_t)q * 16u + (uint32_t)(2 * p_of) * (CH * 16);
+        const uint32_t rec_q = rec_w + (uint32_t)q * 16u + (uint32_t)(Cfg::RPL == 2 ? 2 * p_of : b / CH) * (CH * 16);
         const PhiloxKeys keys = philox_keys((uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
         const float numf = __fmul_ru(__uint2float_ru((uint32_t)(prm.kfix - 1)), 1.0f + 1.0f / 262144.0f);
         uint32_t buf = 0u;
@@ -587,13 +592,18 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 uint64_t pair = (bt.s0 >> 1) + (uint64_t)p_of;
                 for (uint32_t kk = 0; kk < bt.n; ++kk, pair += R / 2) {
                     const uint4 r = philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), c2, c3, keys);
-                    uint4 ra0, rb0, rc0, ra1, rb1, rc1;
-                    make_record<ALGO, DUAL, SH>(g, prm, numf, r.x, r.y, chain_abs, ra0, rb0, rc0);
-                    make_record<ALGO, DUAL, SH>(g, prm, numf, r.z, r.w, chain_abs, ra1, rb1, rc1);
                     const uint32_t p0 = rec_q + buf;
-                    sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0);
-                    sts_v4(p0 + CH * 16, ra1); sts_v4(p0 + CH * 16 + Cfg::REC_B, rb1);
-                    if constexpr (SH) { sts_v4(p0 + Cfg::REC_C, rc0); sts_v4(p0 + CH * 16 + Cfg::REC_C, rc1); }
+                    if constexpr (Cfg::RPL == 2) {
+                        uint4 ra0, rb0, rc0, ra1, rb1, rc1;
+                        make_record<ALGO, DUAL, SH>(g, prm, numf, r.x, r.y, chain_abs, ra0, rb0, rc0);
+                        make_record<ALGO, DUAL, SH>(g, prm, numf, r.z, r.w, chain_abs, ra1, rb1, rc1);
+                        sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0);
+                        sts_v4(p0 + CH * 16, ra1); sts_v4(p0 + CH * 16 + Cfg::REC_B, rb1);
+                    } else {
+                        uint4 ra0, rb0, rc0;
+                        make_record<ALGO, DUAL, SH>(g, prm, numf, half ? r.z : r.x, half ? r.w : r.y, chain_abs, ra0, rb0, rc0);
+                        sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0); sts_v4(p0 + Cfg::REC_C, rc0);
+                    }
                     group_barrier<Cfg::GW>(bar_id);
                     buf ^= (uint32_t)Cfg::BUF;
                 }
@@ -952,8 +962,8 @@ LatPlan lat_plan(int L, int CH, bool hist, int smem_optin)
     if (L < 4 || (L & (L - 1)) || (CH != 32 && CH != 8 && CH != 4 && CH != 1)) return p;
     const int N = L * L;
     const bool sh = hist && CH == 32;                    // 16-bit G(r) bins in shared memory
-    const int NP = (CH == 32) ? (sh ? 4 : 8) : (CH == 8) ? 2 : 1;
-    const int R = 64 * NP / CH;
+    const int NP = (CH == 32) ? 8 : (CH == 8) ? 2 : 1;
+    const int R = 32 * NP * (sh ? 1 : 2) / CH;
     const size_t histb = sh ? (size_t)CH * N * 2 : 0;
     const size_t recw = (size_t)(sh ? 6 : 4) * R * CH * 16;
     const size_t logw = (size_t)3 * 2 * (R + 4) * CH;
