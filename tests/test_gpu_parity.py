@@ -338,9 +338,14 @@ def test_philox_large_lattices_match_oracle(eng, L, lanes):
     n = 14
     T = np.array([2.269, 1.2, 3.0, 2.0, 2.5, 2.269, 1.5, 3.5, 2.1, 2.4, 2.269, 1.0, 2.8, 2.2])
     seeds = np.arange(n, dtype=np.uint64) + 3
-    st = eng.PhiloxState(L, T, seeds, algo=0, max_dumps=4).run(20000, therm_steps=1000, dump_every=50, lanes_per_chain=lanes)
+    gi = np.arange(n) % 3
+    st = eng.PhiloxState(L, T, seeds, algo=0, max_dumps=4, group_index=gi, n_groups=3, hist=True).run(
+        20000, therm_steps=1000, dump_every=50, lanes_per_chain=lanes)
     acc, bonds = st.acc.cpu().numpy(), st.bonds.cpu().numpy()
+    hist = np.zeros((3, L * L), dtype=np.int64)
     for c in range(n):
-        o = wo.run_philox(L, 0, c, int(seeds[c]), float(T[c]), 0, 20000, 1000, dump_every=50, max_dumps=4)
+        o = wo.run_philox(L, 0, c, int(seeds[c]), float(T[c]), 0, 20000, 1000, hist=True, dump_every=50, max_dumps=4)
         assert (acc[c, :6] == o["acc"][:6]).all() and (bonds[c] == o["bonds"]).all()
         assert (st.dumps[c, :min(o["n_dumps"], 4)].cpu().numpy() == o["dumps"]).all()
+        hist[gi[c]] += o["hist"]
+    assert (st.hist.cpu().numpy() == hist).all()
