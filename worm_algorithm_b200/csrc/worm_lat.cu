@@ -19,10 +19,10 @@
 //     It keeps no observables: it logs one byte per accepted step and one per closed step.
 //   * ACCOUNTANT warps replay those logs two rounds later and accumulate Z, sum Nb, sum Nb^2,
 //     sum n, sum n^2 with the exact Nb / n of every closed step; they also write the dump events
-//     and, in solo mode, sweep the shared-memory G(r) bins into the HBM histogram.
+//     (in solo mode the walker itself sweeps its shared-memory G(r) bins into the HBM histogram).
 //   The group meets at one named barrier per round.
-//   CH = 32 ("solo"): one group per block -- the walker has an SM sub-partition to itself, 8 (4 with
-//   histograms) producers and 4 accountants share the other three.  CH = 8 / 4 / 1: up to four
+//   CH = 32 ("solo"): one group per block -- the walker has an SM sub-partition to itself, 8 producers
+//   and 4 accountants share the other three.  CH = 8 / 4 / 1: up to four
 //   groups per block, the warps of a group on the same sub-partition (walker = highest warp id,
 //   which the sub-partition arbiter prefers).
 // Bond storage ("dual" layout): one 32-bit word per SITE holding the occupations of its four
