@@ -287,10 +287,10 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
     const uint32_t pc = (nh == tail) ? 1u : 0u;                 // closed after an accepted move?
     const int A = pc ? kick_next : nh;                          // head if accepted (kick folded in)
     const int B = closed ? kick_next : head;                    // head if rejected
-    // thr | 0, written so that the compiler has to finish A, B and the second store address before
+    // thr + x * 0, written so that the compiler has to finish A, B and the second store address before
     // the first consumer of nb: the warp issues in order and stalls at that consumer, so everything
     // that does not depend on the load must sit in front of it (in the load's shadow), not behind
-    const uint32_t thrx = thr | ((uint32_t)(A ^ B ^ (int)addr2 ^ (int)dnew) & (uint32_t)g.zero);
+    const uint32_t thrx = thr + (uint32_t)(A ^ B ^ (int)addr2 ^ (int)dnew) * (uint32_t)g.zero;   // IMAD: the FMA pipe is the idle one
     const uint32_t nn = (ALGO == ALGO_TAYLOR) ? nb + flip : (nb ^ 1u);
     const uint32_t lg = (nb & 1u) | logbits;
     // accept test (:151), head select, bond stores (:152-154) and the accept-log byte in one opaque
@@ -318,7 +318,7 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
         // predicate is ready ~13 cycles after its ISETP, a select operand after 4, and the next bond load has
         // to follow the stores (the next step may walk straight back).  A rejected move writes the occupation
         // it would have stored to `dummy`, the padding byte of the chain's log row.
-        uint32_t lgs;
+        uint32_t lgs = (LOGK == 0) ? 0u : c.aword;
         asm volatile("{\n\t.reg .pred pa, pd;\n\t.reg .b32 nv, nw;\n\t"
                      "setp.lt.u32 pa, %5, %6;\n\t"
                      "setp.lt.s32 pd, %7, 0;\n\t"
@@ -331,11 +331,12 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
                      "add.u32 %2, %0, %14;\n\t"
                      "ld.shared.u8 %3, [%2];\n\t"
                      "selp.u32 %1, 1, 0, pa;\n\t"
-                     "selp.b32 %4, %13, 0, pa;\n\t}"
-                     : "=&r"(head_new), "=&r"(acc_i), "=&r"(c.addr), "=&r"(c.nb), "=&r"(lgs)
-                     : "r"(nb), "r"(thrx), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(addr2), "r"(nn), "r"(lg), "r"(p_next), "r"(dummy)
+                     "@pa mad.lo.u32 %4, %13, %16, %4;\n\t}"        // accept-log byte into its word, under the guard
+                     : "=&r"(head_new), "=&r"(acc_i), "=&r"(c.addr), "=&r"(c.nb), "+r"(lgs)
+                     : "r"(nb), "r"(thrx), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(addr2), "r"(nn), "r"(lg), "r"(p_next), "r"(dummy),
+                       "n"(1u << (8 * LOGK))
                      : "memory");
-        c.aword = (LOGK == 0 ? 0u : c.aword) + (lgs << (8 * LOGK));
+        c.aword = lgs;
     } else if constexpr (LOGK >= 0) {
         uint32_t lgs;
         asm volatile("{\n\t.reg .pred pa, pd;\n\t"
