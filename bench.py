@@ -322,9 +322,19 @@ def run_b200_arm(a) -> None:
     kern_rate = float(n) * a.num_steps * a.steps / (kern_ms * 1e-3)   # per GPU, kernel only
     achieved = kern_rate * I_ALG
     traffic = None
+    executed = {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("worm_lat_kernel")          # dram bytes per launch, from the ncu --set full capture
+            tj = json.load(f)
+        traffic = tj.get("worm_lat_kernel")                        # dram bytes per launch, from the ncu --set full capture
+        # what the same capture executed (a 200k-step launch of the same 4096 chains): algorithmic vs actual
+        ncu_chain_steps = 200000.0 * n
+        if tj.get("worm_lat_kernel_thread_inst"):
+            executed = {"thread_instr_per_worm_step": tj["worm_lat_kernel_thread_inst"] / ncu_chain_steps,
+                        "warp_instr_per_worm_step": tj.get("worm_lat_kernel_warp_inst", 0.0) / ncu_chain_steps,
+                        "sm_issue_slots_used": tj.get("worm_lat_kernel_issue_pct", 0.0) / 100.0,
+                        "source": "ncu --set full of one 200k-step launch (profiles/traffic.json): the walker's 27 "
+                                  "instructions per step plus the producers' Philox / record building and the accountants"}
     except (OSError, ValueError):
         pass
     roofline = {"bound": "issue", "kernel": "worm_lat_kernel", "achieved": achieved / 1e9, "peak": issue_peak / 1e9,
@@ -333,7 +343,7 @@ def run_b200_arm(a) -> None:
                 "alg_instr_per_worm_step": I_ALG, "kernel_ms_per_launch": kern_ms / a.steps,
                 "worm_steps_per_s_per_gpu": kern_rate,
                 "peak_source": "148 SM x 128 lanes x sm_max_mhz (MEASURED_PEAKS.json)" if peaks else "fallback 1965 MHz",
-                "cycles_per_step_per_chain": f_max * n / kern_rate}
+                "cycles_per_step_per_chain": f_max * n / kern_rate, "executed": executed or None}
     shapes = bench_shapes(torch, engine, dev, algo, issue_peak)
     roofline_blocking = bench_blocking(torch, engine, dev, peaks)
     roofline_pca = bench_pca(torch, engine, dev, peaks, cpu=(world == 1 and not a.no_cpu))

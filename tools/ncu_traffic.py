@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""profiles/traffic.json: DRAM bytes (read + write) per launch of the kernels in an .ncu-rep."""
+"""profiles/traffic.json: DRAM bytes (read + write), executed instructions and issue utilisation per launch of the
+kernels in an .ncu-rep."""
 import csv, json, os, subprocess, sys
 rep = sys.argv[1]
 out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
@@ -21,5 +22,10 @@ for r in rows[2:]:
         tot += float(rec[m].replace(",", "")) * scale.get(u[m], 1)
     d[key] = tot
     d[key + "_source"] = os.path.basename(rep)
+    # executed instructions of the same launch (warp- and thread-level) and the SM's issue utilisation
+    for m, k in (("inst_executed", "_warp_inst"), ("sass__thread_inst_executed_true_per_opcode", "_thread_inst"),
+                 ("sm__inst_executed.avg.pct_of_peak_sustained_elapsed", "_issue_pct")):
+        if m in rec and rec[m] not in ("", "no data"):
+            d[key + k] = float(rec[m].replace(",", ""))
 json.dump(d, open(out, "w"), indent=1)
 print(d)
