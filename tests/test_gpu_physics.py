@@ -78,9 +78,10 @@ def test_temperature_sweep_L32_matches_kaufman(eng):
         assert sim.results["per_T"][j, 0] == tot[j, 0] and sim.results["per_T"][j, 2] == tot[j, 2]
 
 
-@pytest.mark.parametrize("L,steps", [(8, 400_000), (16, 1_500_000), (32, 6_000_000), (64, 24_000_000), (128, 100_000_000)])
+@pytest.mark.parametrize("L,steps", [(8, 400_000), (16, 1_500_000), (32, 6_000_000), (64, 24_000_000), (128, 100_000_000),
+                                     (256, 600_000_000)])
 def test_finite_size_scaling_specific_heat(eng, L, steps):
-    """BASELINE configs[3]: C/N at T = 2.269 for L = 8 .. 128 against Kaufman (fluctuation estimator)."""
+    """BASELINE configs[3]: C/N at T = 2.269 for L = 8 .. 256 against Kaufman (fluctuation estimator)."""
     st, T2d = _run(eng, L, [2.269], 64, steps, 0)
     _check_vs_kaufman(st.acc.cpu().numpy(), T2d, L, 0)
 
