@@ -120,7 +120,10 @@ int worm_mt_run(int L, int64_t n_chains, const double *h_T, const double *h_seed
  *                            the occupations d_dumps[c][e][2N]; d_n_dumps[c] (in/out) counts them.
  *                            dump_every = 0 disables.
  *   lanes_per_chain          kernel variant (results are identical for all of them):
- *                            0 = choose;  2 / 4 / 8 / 32 = latency kernel with 32 / 8 / 4 / 1 chains per
+ *                            0 = choose (the latency kernel whenever L is a power of two that fits shared memory:
+ *                            32 chains per walker if the lattice allows, else one chain per walker, or the variant
+ *                            holding the most chains per block once the batch exceeds one wave);
+ *                            2 / 4 / 8 / 32 = latency kernel with 32 / 8 / 4 / 1 chains per
  *                            walker warp (power-of-two L; 2 gives the walker an SM sub-partition to itself);
  *                            1 = one thread per chain, bonds in shared memory;  -1 = one thread per chain,
  *                            bonds left in global memory (taken automatically when a lattice does not fit)
