@@ -146,6 +146,24 @@ def test_production_mode_matches_reference_executable_statistics(eng, golden_dir
     assert c.size == temps.size - 4 and (np.abs(zc) < 3.0).all(), zc
 
 
+def test_bond_flag_run_switches_the_dump_rule_off_after_the_cap(eng):
+    """WormSimulation(bond_flag=1, rng='philox') keeps the first max_dumps dumps per chain and then runs the rest
+    without the dump rule (a segment boundary every write_steps steps halves the step rate): dumps, events,
+    sums and final configurations are those of one run with the rule on throughout."""
+    from worm_algorithm_b200.worm_simulation import WormSimulation
+    L, steps = 16, 300_000
+    sim = WormSimulation(L=L, num_steps=steps, verbose=False, T_arr=[2.6, 3.0, 3.4], bond_flag=1, n_replicas=8,
+                         rng="philox", max_dumps=8)        # (a paramagnetic worm closes often: the caps fill early)
+    st = sim.results["state"]
+    ref = eng.PhiloxState(L, sim.results["T"], sim.results["seeds"], algo=0, chain_id0=0,
+                          group_index=sim.results["t_index"], n_groups=3, max_dumps=8)
+    ref.run(steps, therm_steps=steps // 10, dump_every=50)
+    assert (st.dumps == ref.dumps).all() and (st.events == ref.events).all()
+    assert (st.acc == ref.acc).all() and (st.bonds == ref.bonds).all() and (st.group_acc == ref.group_acc).all()
+    assert int(st.n_dumps.min()) >= 8
+    assert int(st.n_dumps.max()) < int(ref.n_dumps.max())           # the rule really was switched off
+
+
 def test_lat_and_wide_kernels_agree_at_scale(eng):
     """BASELINE configs[4] shape, scaled: 16384 independent L = 32 chains with G(r) histograms; the
     thread-per-chain kernel and the latency kernel give identical reduced sums and histograms."""

@@ -160,6 +160,26 @@ class WormSimulation(object):
             self._T.append(rows[0][1])
 
     # -- production mode ------------------------------------------------------------------------
+    def _run_with_dump_cap(self, st, therm, max_dumps):
+        """The executable dumps at every closed multiple of write_steps (worm_ising_2d.cpp:113-125); here the
+        first `max_dumps` per chain are kept.  Once every chain of the shard has them, the dump rule is switched
+        off for the rest of the run: the trajectory does not depend on it (chunked runs are bit-identical), and
+        a segment boundary every write_steps steps costs ~45 % of the step rate (tools/dump_time.py)."""
+        dump_every = self._write_steps if max_dumps else 0
+        left = int(self._num_steps)
+        if not dump_every:
+            st.run(left, therm_steps=therm, dump_every=0, lanes_per_chain=self._lanes)
+            return
+        chunk = max(therm + 8 * dump_every * max_dumps, 50000)     # warm-up + ~8x the expected time to fill
+        while left > 0:
+            this = min(chunk, left)
+            st.run(this, therm_steps=therm, dump_every=dump_every, lanes_per_chain=self._lanes)
+            left -= this
+            if left > 0 and int(st.n_dumps.min()) >= max_dumps:
+                st.run(left, therm_steps=therm, dump_every=0, lanes_per_chain=self._lanes)
+                left = 0
+            chunk *= 2
+
     def _run_philox(self):
         import torch
         from . import dist
@@ -191,8 +211,7 @@ class WormSimulation(object):
             st = engine.PhiloxState(L, Tc[c0:c1], seeds[c0:c1], algo=self._algo, chain_id0=c0,
                                     group_index=t_idx[c0:c1], n_groups=nT, hist=self._hist,
                                     max_dumps=max_dumps, store_dumps=bool(self._bond_flag), device=self._device)
-            st.run(self._num_steps, therm_steps=therm, dump_every=self._write_steps if max_dumps else 0,
-                   lanes_per_chain=self._lanes)
+            self._run_with_dump_cap(st, therm, max_dumps)
             per_T = st.group_acc                  # summed over the chains of each temperature on the device
         per_T = dist.allreduce_sum(per_T, self._world)
         hist = None
