@@ -105,15 +105,15 @@ def test_mt_mode_batch_matches_oracle_with_trace(eng):
 # production mode: every kernel variant reproduces the CPU restatement bit for bit
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("algo", [0, 1])
-@pytest.mark.parametrize("lanes", [0, 1, 2, 4, 8, 32, -1])
+@pytest.mark.parametrize("lanes", [0, 1, 2, 4, 8, 32, -1, -2])
 @pytest.mark.parametrize("L,tmin", [(3, 0.8), (8, 0.8), (16, 1.0), (32, 1.2)])
 def test_philox_matches_oracle(eng, algo, lanes, L, tmin):
     """Every kernel variant (latency mode with 4/8/32 lanes per chain, thread per chain with bonds in
     shared or global memory) and both record builders (T >= 1 fast path, general T) against the CPU
     restatement: accumulators, final bonds, head/tail, dumps, events, G(r), per-group sums."""
     from oracle import worm_oracle as wo
-    if lanes in (2, 4, 8, 32) and (L & (L - 1)):
-        pytest.skip("latency mode needs a power-of-two L")
+    if lanes in (2, 4, 8, 32, -2) and (L & (L - 1)):
+        pytest.skip("latency mode and packed mode need a power-of-two L")
     rng = np.random.default_rng(100 * L + 10 * algo + lanes + 1)
     n = 37                      # not a multiple of the chains per warp: exercises dead lanes
     T = rng.uniform(tmin, 3.5, n)
@@ -135,6 +135,7 @@ def test_philox_matches_oracle(eng, algo, lanes, L, tmin):
         o = wo.run_philox(L, algo, cid0 + c, int(seeds[c]), float(T[c]), 0, steps, therm, hist=True,
                           dump_every=50, max_dumps=16)
         assert (acc[c, :6] == o["acc"][:6]).all(), (c, acc[c], o["acc"])
+        assert acc[c, 6] == 0                      # WORM_ACC_STATUS: nothing the packed format could not hold
         assert (bonds[c] == o["bonds"]).all()
         assert head[c] == o["head"] and tail[c] == o["tail"]
         assert nd[c] == o["n_dumps"]
@@ -146,6 +147,52 @@ def test_philox_matches_oracle(eng, algo, lanes, L, tmin):
     gacc = np.zeros((3, 8), dtype=np.int64)
     np.add.at(gacc, hidx, acc)
     assert (st.group_acc.cpu().numpy() == gacc).all()
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("L,n", [(8, 6007), (16, 80000), (32, 33152 + 4000), (64, 9000)])
+def test_philox_packed_big_batches(eng, algo, L, n):
+    """Packed mode with real blocks: whole warps plus a ragged last warp, several waves, dead lanes in the last
+    block.  Every chain against the thread-per-chain kernel (itself pinned to the oracle above), a sample of
+    chains against the oracle directly."""
+    from oracle import worm_oracle as wo
+    rng = np.random.default_rng(5 * L + algo)
+    nT = 16
+    gi = (np.arange(n) * nT // n).astype(np.int32)
+    T = (1.2 + 2.3 * np.arange(nT) / (nT - 1))[gi]
+    seeds = rng.integers(0, 2 ** 63, n, dtype=np.uint64)
+    steps, therm = 1500, 300
+    kw = dict(algo=algo, chain_id0=7, group_index=gi, n_groups=nT, hist=True, max_dumps=3)
+    a = eng.PhiloxState(L, T, seeds, **kw).run(700, therm_steps=therm, dump_every=50, lanes_per_chain=-2)
+    a.run(steps - 700, therm_steps=therm, dump_every=50, lanes_per_chain=-2)
+    b = eng.PhiloxState(L, T, seeds, **kw).run(steps, therm_steps=therm, dump_every=50, lanes_per_chain=1)
+    assert (a.acc == b.acc).all() and (a.bonds == b.bonds).all()
+    assert (a.head == b.head).all() and (a.tail == b.tail).all()
+    assert (a.hist == b.hist).all() and (a.group_acc == b.group_acc).all()
+    assert (a.n_dumps == b.n_dumps).all() and (a.events == b.events).all() and (a.dumps == b.dumps).all()
+    acc, bonds = a.acc.cpu().numpy(), a.bonds.cpu().numpy()
+    for c in (0, 31, 32, n // 2, n - 1):
+        o = wo.run_philox(L, algo, 7 + c, int(seeds[c]), float(T[c]), 0, steps, therm, hist=True, dump_every=50, max_dumps=3)
+        assert (acc[c, :6] == o["acc"][:6]).all() and acc[c, 6] == 0 and (bonds[c] == o["bonds"]).all()
+
+
+def test_philox_packed_refuses_what_it_cannot_hold(eng):
+    """An occupation above 15 cannot be packed in 4 bits: the chain is left untouched and says so in
+    WORM_ACC_STATUS (bit 0); the other chains of the batch run normally."""
+    L, n = 8, 40
+    T = np.full(n, 2.0)
+    seeds = np.arange(n, dtype=np.uint64)
+    st = eng.PhiloxState(L, T, seeds, algo=0)
+    ref = eng.PhiloxState(L, T, seeds, algo=0)
+    st.bonds[5, 17] = 16
+    st.run(500, lanes_per_chain=-2)
+    ref.run(500, lanes_per_chain=1)
+    acc = st.acc.cpu().numpy()
+    assert acc[5, 6] == 1 and (np.delete(acc[:, 6], 5) == 0).all()
+    assert int(st.bonds[5, 17]) == 16 and int(st.bonds[5].sum()) == 16 and (acc[5, :6] == 0).all()
+    keep = np.arange(n) != 5
+    assert (acc[keep] == ref.acc.cpu().numpy()[keep]).all()
+    assert (st.bonds.cpu().numpy()[keep] == ref.bonds.cpu().numpy()[keep]).all()
 
 
 def test_philox_thresholds_match_oracle(eng):
@@ -164,6 +211,8 @@ def test_philox_geometry_independence(eng):
     a = eng.PhiloxState(L, T, seeds, algo=0).run(5000, therm_steps=500, lanes_per_chain=1)
     b = eng.PhiloxState(L, T, seeds, algo=0).run(1233, therm_steps=500, lanes_per_chain=4).run(3767, therm_steps=500, lanes_per_chain=-1)
     assert (a.acc == b.acc).all() and (a.bonds == b.bonds).all()
+    p = eng.PhiloxState(L, T, seeds, algo=0).run(1501, therm_steps=500, lanes_per_chain=-2).run(3499, therm_steps=500, lanes_per_chain=2)
+    assert (a.acc == p.acc).all() and (a.bonds == p.bonds).all() and (a.head == p.head).all() and (a.tail == p.tail).all()
     d = eng.PhiloxState(L, T, seeds, algo=0).run(77, therm_steps=500, lanes_per_chain=32).run(2000, therm_steps=500, lanes_per_chain=8).run(2000, therm_steps=500, lanes_per_chain=2).run(923, therm_steps=500)
     assert (a.acc == d.acc).all() and (a.bonds == d.bonds).all() and (a.head == d.head).all() and (a.tail == d.tail).all()
     # second half of the chains run as their own batch with chain_id0 = 32
@@ -293,7 +342,7 @@ def test_host_entry_points(eng, ref_runs):
 # round / segment edges of the latency kernel: odd starts, runs shorter than a round, odd dump
 # periods, warm-up ending inside a round, empty ranges
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("lanes", [2, 4, 8, 32, 1])
+@pytest.mark.parametrize("lanes", [2, 4, 8, 32, 1, -2])
 def test_philox_segment_edges_match_oracle(eng, lanes):
     from oracle import worm_oracle as wo
     L, n = 8, 11
@@ -329,7 +378,8 @@ def test_philox_segment_edges_match_oracle(eng, lanes):
         assert (st.hist.cpu().numpy() == hist).all(), (lanes, chunks)
 
 
-@pytest.mark.parametrize("L,lanes", [(64, 32), (128, 32), (256, 32), (64, 0), (128, 0), (256, 0), (64, 8), (64, 4)])
+@pytest.mark.parametrize("L,lanes", [(64, 32), (128, 32), (256, 32), (64, 0), (128, 0), (256, 0), (64, 8), (64, 4),
+                                     (64, -2), (128, -2), (256, -2)])
 def test_philox_large_lattices_match_oracle(eng, L, lanes):
     """L = 64 (one chain per walker in the dual layout; three walkers of 4 chains or one of 8 for big
     batches), L = 128 (compact layout, four walkers of one chain) and L = 256 (compact, one chain per block).

@@ -213,8 +213,8 @@ int worm_philox_run(int L, int algo, int64_t n_chains, uint64_t chain_id0,
     if (d_group_index && n_groups <= 0) return fail(WORM_E_ARG, "n_groups must be positive with d_group_index");
     if (dump_every && (max_dumps <= 0 || !d_n_dumps)) return fail(WORM_E_ARG, "dump_every needs max_dumps > 0 and d_n_dumps");
     if (lanes_per_chain != 0 && lanes_per_chain != 1 && lanes_per_chain != 2 && lanes_per_chain != 4 &&
-        lanes_per_chain != 8 && lanes_per_chain != 32 && lanes_per_chain != -1)
-        return fail(WORM_E_ARG, "lanes_per_chain = %d (0, 1, 2, 4, 8, 32 or -1)", lanes_per_chain);
+        lanes_per_chain != 8 && lanes_per_chain != 32 && lanes_per_chain != -1 && lanes_per_chain != -2)
+        return fail(WORM_E_ARG, "lanes_per_chain = %d (0, 1, 2, 4, 8, 32, -1 or -2)", lanes_per_chain);
     if (step_begin + n_steps < step_begin) return fail(WORM_E_ARG, "step range overflows");
     if (workspace_bytes < worm_philox_workspace_bytes(n_chains) || !d_workspace)
         return fail(WORM_E_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, worm_philox_workspace_bytes(n_chains));

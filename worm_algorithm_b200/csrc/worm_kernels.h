@@ -9,6 +9,7 @@ namespace worm {
 
 constexpr int MT_STRIDE = 8;    // int64 words per chain in the deterministic result record
 constexpr int ACC_STRIDE = 8;   // int64 words per chain in the production accumulator record
+constexpr int ACC_STATUS = 6;   // sticky per-chain status word of that record (0 = fine; see WORM_ACC_STATUS)
 
 struct PhiloxArgs {
     int L;
@@ -38,7 +39,8 @@ cudaError_t launch_mt(int L, int64_t n_chains, int64_t n_pad, const MtChain *d_p
                       uint32_t *d_mt_state, int smem_optin, cudaStream_t st);
 
 // lanes_per_chain: 0 = choose; 4 / 8 / 32 = latency mode with that many lanes per chain; 1 = thread
-// per chain, bonds in shared memory when they fit; -1 = thread per chain, bonds in global memory.
+// per chain, bonds in shared memory when they fit; -1 = thread per chain, bonds in global memory;
+// -2 = thread per chain, packed bonds in shared memory (worm_pack.cu).
 // lowt: some chain has kfix > 2^32 or tfix < 2^32 (T < 1).  smem_optin = max opt-in dynamic shared
 // memory per block.
 cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, bool lowt, int smem_optin, int sm_count,
@@ -50,6 +52,9 @@ size_t lat_smem_bytes(int L, int G, bool hist, int smem_optin);   // 0 if this L
 int lat_chains_per_block(int L, int G, bool hist, int smem_optin);
 cudaError_t launch_philox_lat(const PhiloxArgs &a, int G, bool lowt, int smem_optin, cudaStream_t st);
 cudaError_t launch_philox_wide(const PhiloxArgs &a, bool force_global, int smem_optin, cudaStream_t st);
+// packed throughput kernel (worm_pack.cu): thread per chain, 4 bits (Taylor) / 1 bit (binary) per bond in shared memory
+int pack_chains_per_block(int L, int algo, int64_t n_chains, int smem_optin, int sm_count);   // 0: this L cannot run packed
+cudaError_t launch_philox_pack(const PhiloxArgs &a, bool lowt, int smem_optin, int sm_count, cudaStream_t st);
 
 cudaError_t launch_image(int L, int64_t n, const uint8_t *d_bonds, int32_t *d_img, cudaStream_t st);
 cudaError_t launch_block(int W, int64_t n, const int32_t *d_in, int32_t *d_out, int dbv, int variant,

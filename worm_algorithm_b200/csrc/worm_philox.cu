@@ -39,7 +39,11 @@ cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, bool lowt, i
         if (lat_smem_bytes(a.L, G, hist, smem_optin) == 0) { *why = "lattice too large for latency mode with this lanes_per_chain"; return cudaErrorInvalidValue; }
         return launch_philox_lat(a, G, lowt, smem_optin, st);
     }
-    if (G != 1 && G != -1) { *why = "lanes_per_chain must be 0, 1, 2, 4, 8, 32 or -1"; return cudaErrorInvalidValue; }
+    if (G == -2) {
+        if (pack_chains_per_block(a.L, a.algo, a.n_chains, smem_optin, sm_count) == 0) { *why = "packed mode (lanes_per_chain -2) needs a power-of-two L >= 4 whose packed bonds fit shared memory"; return cudaErrorInvalidValue; }
+        return launch_philox_pack(a, lowt, smem_optin, sm_count, st);
+    }
+    if (G != 1 && G != -1) { *why = "lanes_per_chain must be 0, 1, 2, 4, 8, 32, -1 or -2"; return cudaErrorInvalidValue; }
     return launch_philox_wide(a, G == -1, smem_optin, st);
 }
 
