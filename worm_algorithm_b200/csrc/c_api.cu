@@ -221,18 +221,24 @@ int worm_philox_run(int L, int algo, int64_t n_chains, uint64_t chain_id0,
     DevInfo dev;
     if (int rc = current_device_info(dev)) return rc;
     std::vector<worm::PhiloxChain> prm((size_t)n_chains);
-    double lastT = -1.0;
-    uint64_t k = 0, t = 0, h = 0;
-    bool lowt = false;            // some chain outside the T >= 1 fast path of the record builder
+    // a sweep has few distinct temperatures, in any order: the fixed-point constants (ceil / ldexp / tanh)
+    // are computed once per temperature, looked up by the bits of T in a small direct-mapped table
+    struct Slot { uint64_t bits; uint64_t k, t, h; bool used; };
+    std::vector<Slot> slots(1024, Slot{0, 0, 0, 0, false});
+    bool lowt = false;            // some chain outside the T >= 1 fast path of the kernels
     for (int64_t c = 0; c < n_chains; ++c) {
         const double T = h_T[c];
-        if (T != lastT) {
+        uint64_t bits;
+        memcpy(&bits, &T, sizeof bits);
+        Slot &sl = slots[(size_t)((bits * 0x9E3779B97F4A7C15ull) >> 54)];
+        if (!sl.used || sl.bits != bits) {
             if (bad_T(T)) return fail(WORM_E_ARG, "temperature[%lld] = %g out of range", (long long)c, T);
-            thresholds(T, k, t, h);
-            lastT = T;
-            if (k > 0x100000000ull || t < 0x100000000ull) lowt = true;
+            thresholds(T, sl.k, sl.t, sl.h);
+            sl.bits = bits;
+            sl.used = true;
+            if (sl.k > 0x100000000ull || sl.t < 0x100000000ull) lowt = true;
         }
-        prm[(size_t)c] = worm::PhiloxChain{k, t, h, h_seed[c]};
+        prm[(size_t)c] = worm::PhiloxChain{sl.k, sl.t, sl.h, h_seed[c]};
     }
     cudaStream_t st = (cudaStream_t)stream;
     worm::PhiloxChain *d_prm = (worm::PhiloxChain *)d_workspace;

@@ -97,7 +97,8 @@ struct PackConst {
     uint32_t lut_lane;           // byte offset of this lane's copy of a table entry
     uint32_t klo, khi;           // kfix (Taylor) / hfix (binary), 64 bits
     uint32_t tlo, thi;           // tfix (Taylor, T < 1 only)
-    unsigned long long hist_row; // HIST: this chain's row of the int64 histogram (0: do not count)
+    unsigned long long hist_row; // HIST: this chain's row of the int64 histogram
+    uint32_t hist_inc;           // HIST: 1 for a live chain, 0 for the lanes that only shadow one
     int ksh;
     uint32_t kmask;
 };
@@ -129,7 +130,7 @@ __device__ __forceinline__ void pack_step(const PackConst &k, PackChain &c, cons
         }
         // G(r): this iteration is one more at the current displacement head - tail (taken before the kick);
         // the count goes to the bin when the displacement changes (below) or the range ends
-        if constexpr (HIST) c.run += 1u;
+        if constexpr (HIST) c.run += k.hist_inc;
     }
     const uint32_t kick = (rb >> k.ksh) & k.kmask;                 // :128-129
     const uint32_t hs = closed ? kick : c.hs;
@@ -242,11 +243,25 @@ __device__ __forceinline__ void pack_step(const PackConst &k, PackChain &c, cons
     }
     c.hs = hs_new;
     if constexpr (HIST) {
-        // An accepted move always changes the head (L >= 3), hence the displacement: flush the run of
-        // iterations counted at the old one.  The scaled displacement is the byte offset of its int64 bin
-        // (Taylor: site * 8) or a quarter of it (binary: site * 2).  One `red` per accepted move instead
-        // of one per step, and far fewer hits on the hot bins (a closed worm waits in bin 0).
-        if ((hs_new != hs) && k.hist_row && c.run) pack_hist_flush<ALGO>(k, c);
+        // An accepted move always changes the head (L >= 3), hence the displacement: the run of iterations
+        // counted at the old one goes to its bin.  The scaled displacement is the byte offset of its int64 bin
+        // (Taylor: site * 8) or a quarter of it (binary: site * 2).  One predicated `red` per accepted move
+        // instead of one per step, and far fewer hits on the hot bins (a closed worm waits in bin 0).
+        // Lanes without a chain count nothing (hist_inc = 0): their `red` adds 0 to a valid bin.
+        if constexpr (MEAS) {
+            const unsigned long long p = k.hist_row + (unsigned long long)c.disp * (ALGO == ALGO_TAYLOR ? 1u : 4u);
+            uint32_t run_new;
+            asm volatile("{\n\t"
+                         ".reg .pred p;\n\t"
+                         ".reg .b64 rr;\n\t"
+                         "setp.ne.u32 p, %1, %2;\n\t"
+                         "mov.b64 rr, {%3, %4};\n\t"
+                         "@p red.global.add.u64 [%5], rr;\n\t"
+                         "selp.b32 %0, 0, %3, p;\n\t"
+                         "}"
+                         : "=r"(run_new) : "r"(hs_new), "r"(hs), "r"(c.run), "r"(0u), "l"(p) : "memory");
+            c.run = run_new;
+        }
         c.disp = disp_new;
     }
 }
@@ -351,9 +366,10 @@ worm_pack_kernel(const PhiloxArgs a, const PackGeo g)
     else { k.klo = (uint32_t)prm.hfix; k.khi = (uint32_t)(prm.hfix >> 32); }
     k.tlo = (uint32_t)prm.tfix; k.thi = (uint32_t)(prm.tfix >> 32);
     k.hist_row = 0ull;
+    k.hist_inc = 0u;
     if constexpr (HIST) {
-        if (live && a.hist && a.group_index)
-            k.hist_row = (unsigned long long)(a.hist + (int64_t)a.group_index[cl] * g.N);
+        k.hist_row = (unsigned long long)(a.hist + (int64_t)a.group_index[cl] * g.N);
+        k.hist_inc = live ? 1u : 0u;
     }
     k.ksh = g.ksh; k.kmask = g.kmask;
 
@@ -537,7 +553,7 @@ worm_pack_kernel(const PhiloxArgs a, const PackGeo g)
         else run_range(std::false_type{}, s, e);
         pack_fold(c);
         if constexpr (HIST) {
-            if (k.hist_row && c.run) pack_hist_flush<ALGO>(k, c);
+            if (c.run) pack_hist_flush<ALGO>(k, c);
         }
         s = e;
     }

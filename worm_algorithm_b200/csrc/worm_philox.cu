@@ -10,18 +10,23 @@ cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, bool lowt, i
     const bool hist = (a.hist != nullptr && a.group_index != nullptr);
     int G = lanes_per_chain;
     if (G == 0) {
-        // Latency mode for every power-of-two lattice that fits shared memory: a chain is a sequence
-        // of dependent steps, so throughput = (chains in flight) / (cycles per step), and the latency
-        // kernel has by far the fewest cycles per step; batches larger than one wave simply run in
-        // waves.  32 chains per walker ("solo", code 2) when the lattice allows it and the batch has
-        // at least two blocks; else the variant with the most chains per block (8, 4 or 1 chains per
-        // walker, codes 4 / 8 / 32) once the batch exceeds one chain per walker of a full wave, and one
-        // chain per walker below that (fewest cycles per step).  Thread-per-chain (code 1) is left for
-        // lattices that are not a power of two or do not fit.
+        // A chain is a sequence of dependent steps: throughput = (chains in flight) / (cycles per step), capped by
+        // the issue slots.  Two families, chosen by that estimate (cycle counts measured on B200):
+        //  * latency kernel (power-of-two L that fits shared memory; few cycles per step, few chains per SM):
+        //    32 chains per walker ("solo", code 2) when the lattice allows it and the batch has at least two
+        //    blocks; else one chain per walker (code 32), or the variant with the most chains per block
+        //    (codes 8 / 4) once the batch exceeds one chain per walker of a full wave;
+        //  * packed kernel (code -2; thread per chain, 4 / 1 bits per bond): ~3x the cycles per step, but 7 times
+        //    (Taylor, L = 32) to 24 times (binary) the chains per SM.
+        // Thread-per-chain on bytes (code 1) is left for lattices that are not a power of two or do not fit.
         G = 1;
+        double rate_lat = 0.0;
         if (a.L >= 4 && !(a.L & (a.L - 1))) {
-            if (lat_smem_bytes(a.L, 2, hist, smem_optin) && a.n_chains >= 64) G = 2;
-            else {
+            int cb = 0;
+            double cyc = 0.0;
+            if (lat_smem_bytes(a.L, 2, hist, smem_optin) && a.n_chains >= 64) {
+                G = 2; cb = 32; cyc = hist ? 94.0 : 58.0;
+            } else {
                 const int c32 = lat_chains_per_block(a.L, 32, hist, smem_optin);
                 int best = c32;
                 if (c32) G = 32;
@@ -31,6 +36,20 @@ cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, bool lowt, i
                         if (c > best) { best = c; G = g; }
                     }
                 }
+                cb = best;
+                cyc = (best <= 1 ? 56.0 : best <= 4 ? 72.0 : 95.0) + (hist ? 60.0 : 0.0);
+            }
+            if (cb) {
+                const double inflight = (double)(a.n_chains < (int64_t)cb * sm_count ? a.n_chains : (int64_t)cb * sm_count);
+                rate_lat = inflight / cyc;
+            }
+            const int pcb = pack_chains_per_block(a.L, a.algo, a.n_chains, smem_optin, sm_count);
+            if (pcb) {
+                const double warps = (double)((pcb + 31) / 32);
+                const double cyc_pack = (a.algo == ALGO_TAYLOR ? 176.0 + 13.0 * (warps - 1.0) : 130.0 + 21.0 * (warps - 1.0)) *
+                                        (hist ? 1.35 : 1.0);
+                const double inflight = (double)(a.n_chains < (int64_t)pcb * sm_count ? a.n_chains : (int64_t)pcb * sm_count);
+                if (inflight / cyc_pack > 1.1 * rate_lat) G = -2;
             }
         }
     }
