@@ -52,6 +52,12 @@ enum { WORM_ACC_Z = 0,      /* closed iterations measured          (Z of worm_is
        WORM_ACC_N = 3,      /* sum of n = number of odd-parity bonds (count_bonds.py:110-117)        */
        WORM_ACC_N2 = 4,     /* sum of n^2                                                            */
        WORM_ACC_ITERS = 5,  /* measured loop iterations (steps with step >= therm)                   */
+       WORM_ACC_STATUS = 6, /* sticky, 0 = fine.  Set only by the packed kernel (lanes_per_chain -2 / chosen
+                               by 0), whose Taylor chain keeps 4 bits per bond: bit 0 = the chain's input
+                               held an occupation > 15 (binary chain: > 1) and was left untouched; bit 1 =
+                               an occupation reached 16 during the run (results of that chain are void;
+                               rerun it with lanes_per_chain 1, which holds 0..255).  Never seen for
+                               T >= 1: the weight of occupation n falls like K^n / n!                  */
        WORM_ACC_STRIDE = 8 };
 
 /* per-chain result record written by worm_mt_run: int64 out[n_chains][WORM_MT_STRIDE] */
@@ -69,7 +75,8 @@ int worm_device_info(int device, int *sm_count, int *smem_optin_bytes, int *cloc
 
 /* ---------------------------------------------------------------------------------------------
  * Deterministic mode: n_chains independent copies of the reference loop (worm_ising_2d.cpp:47-57,
- * 111-157), one thread per chain, each consuming its own MT19937 stream seeded like the reference
+ * 111-157), one WARP per chain (every lane walks the loop redundantly, the 32 lanes share the MT19937
+ * refill and the dump copies), each chain consuming its own MT19937 stream seeded like the reference
  * (init_genrand((unsigned long)seed), worm_ising_2d.cpp:47 / mt19937ar.c:68-81).  Bit-exact: bond
  * dumps, Z, Nb_tot, step_num and Nb equal the reference executable's for the same (L, T, steps, seed).
  *
@@ -95,10 +102,21 @@ int worm_mt_run(int L, int64_t n_chains, const double *h_T, const double *h_seed
                 void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Production mode: counter-based Philox4x32-10, one call per worm step, counter = {step, chain id},
- * key = seed, so a chain's trajectory does not depend on launch geometry, chunking or the number
- * of GPUs.  Words: 0 kick site, 1 direction, 2 +/- coin, 3 acceptance draw -- the draw order of
- * worm_ising_2d.cpp:128,137,141,151.
+ * Production mode: counter-based Philox4x32-10 (Salmon et al., SC'11), random stream VERSION 2 --
+ * the normative statement is oracle/worm_oracle.c:worm_oracle_philox_run, and worm_philox_words()
+ * below returns the words so that a binder can check its reading of this paragraph:
+ *   ONE Philox call serves TWO worm steps.  For step s of the chain with global id c and seed k:
+ *     counter = { lo32(s >> 1), hi32(s >> 1), lo32(c), hi32(c) },  key = { lo32(k), hi32(k) },
+ *     output (x, y, z, w);  an even step uses (a, b) = (x, y), an odd step (a, b) = (z, w).
+ *     a                      acceptance draw, all 32 bits                        (worm_ising_2d.cpp:151)
+ *     b >> 30                direction 0:+x 1:+y 2:-x 3:-y                       (:137)
+ *     (b >> 29) & 1          0 = increment proposal, 1 = decrement proposal      (:141)
+ *     ((b << 3) * N) >> 32   kick site, from the low 29 bits of b (32-bit shift, 64-bit product)  (:128)
+ *   Acceptance in integers with kfix = ceil(2^32 K), tfix = ceil(2^32 / K), hfix = ceil(2^32 tanh K)
+ *   (worm_thresholds):  Taylor increment  (nb + 1) * a < kfix  (and nb < 255), decrement  a < nb * tfix;
+ *   binary chain: an occupied bond is always taken, an empty one iff a < hfix.
+ * A chain's trajectory is a pure function of (seed, global chain id, T): it does not depend on launch
+ * geometry, kernel variant, chunking or the number of GPUs.
  *
  * Runs steps [step_begin, step_begin + n_steps) of every chain, resuming from (d_bonds, d_head,
  * d_tail) and leaving the new state there.  Iterations with step >= therm_steps are measured into
@@ -125,8 +143,11 @@ int worm_mt_run(int L, int64_t n_chains, const double *h_T, const double *h_seed
  *                            holding the most chains per block once the batch exceeds one wave);
  *                            2 / 4 / 8 / 32 = latency kernel with 32 / 8 / 4 / 1 chains per
  *                            walker warp (power-of-two L; 2 gives the walker an SM sub-partition to itself);
- *                            1 = one thread per chain, bonds in shared memory;  -1 = one thread per chain,
- *                            bonds left in global memory (taken automatically when a lattice does not fit)
+ *                            1 = one thread per chain, a byte per bond in shared memory;  -1 = one thread per
+ *                            chain, bonds left in global memory (taken automatically when a lattice does not fit);
+ *                            -2 = packed kernel: one thread per chain, 4 bits (Taylor) / 1 bit (binary) per bond in
+ *                            shared memory (power-of-two L; see WORM_ACC_STATUS) -- what 0 chooses whenever the
+ *                            batch has more chains than the latency kernel can keep in flight
  *   d_workspace              worm_philox_workspace_bytes(n) bytes
  * ------------------------------------------------------------------------------------------- */
 size_t worm_philox_workspace_bytes(int64_t n_chains);
@@ -138,6 +159,12 @@ int worm_philox_run(int L, int algo, int64_t n_chains, uint64_t chain_id0,
                     uint64_t dump_every, int32_t max_dumps, int32_t *d_n_dumps,
                     int64_t *d_events, uint8_t *d_dumps,
                     int lanes_per_chain, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* The two words (a, b) of worm step `step` of chain `chain_id` under key `seed` -- the stream every
+ * production kernel consumes (host arithmetic only, no GPU needed; for binders' known-answer tests).
+ * Known answer, seed 1, chain 0: step 0 (0xe3e80670, 0xe50a0ebc), step 1 (0x95f222c0, 0xb615aa27),
+ * step 2 (0xac08141b, 0xdfc5ccbe), step 3 (0x79c07a47, 0xa7f66093). */
+int worm_philox_words(uint64_t seed, uint64_t chain_id, uint64_t step, uint32_t *a, uint32_t *b);
 
 /* fixed-point acceptance constants used by the production kernels for temperature T:
  * kfix = ceil(2^32/T), tfix = ceil(2^32 * (1/(1/T))), hfix = ceil(2^32 * tanh(1/T)) */

@@ -55,6 +55,64 @@ def test_thresholds_without_gpu_match_oracle():
         assert _lib.thresholds(T) == wo.thresholds(T)
 
 
+def test_header_stream_contract_matches_oracle():
+    """include/worm_b200.h states the production stream (version 2) in words; worm_philox_words() returns it.
+    (1) the words equal the oracle's Philox block read the way the header says; (2) a worm written here from
+    nothing but the header's paragraph (words, bit fields, integer acceptance tests) lands on the same state
+    and sums as oracle/worm_oracle.c:worm_oracle_philox_run -- so a binder reading the header gets the
+    contract the kernels implement."""
+    from oracle import worm_oracle as wo
+    from worm_algorithm_b200 import _lib
+    for seed, chain, step in ((1, 0, 0), (1, 0, 1), (1, 0, 2), (1, 0, 3), (2 ** 63 + 5, 2 ** 40 + 3, 2 ** 35 + 7),
+                              (0xDEADBEEF12345678, 77, 2 ** 33 - 1)):
+        pair = step >> 1
+        blk = wo.philox([pair & 0xFFFFFFFF, pair >> 32, chain & 0xFFFFFFFF, chain >> 32], [seed & 0xFFFFFFFF, seed >> 32])
+        a, b = _lib.philox_words(seed, chain, step)
+        assert (a, b) == ((int(blk[2]), int(blk[3])) if step & 1 else (int(blk[0]), int(blk[1])))
+    # the known answer printed in the header: chain 0, seed 1, steps 0..3
+    assert [_lib.philox_words(1, 0, s) for s in range(4)] == [(0xe3e80670, 0xe50a0ebc), (0x95f222c0, 0xb615aa27),
+                                                              (0xac08141b, 0xdfc5ccbe), (0x79c07a47, 0xa7f66093)]
+    for algo in (0, 1):
+        L, T, seed, chain, steps = 4, 1.7, 12345, 9, 600
+        N = L * L
+        kfix, tfix, hfix = _lib.thresholds(T)
+        bonds = [0] * (2 * N)
+        head = tail = 0
+        Z = SNb = 0
+        for s in range(steps):
+            a, b = _lib.philox_words(seed, chain, s)
+            if head == tail:
+                Z += 1
+                SNb += sum(bonds)
+                head = tail = (((b << 3) & 0xFFFFFFFF) * N) >> 32
+            d = b >> 30
+            x, y = head % L, head // L
+            if d == 0:
+                nh, ib = y * L + (x + 1) % L, 2 * head
+            elif d == 1:
+                nh, ib = ((y + 1) % L) * L + x, 2 * head + 1
+            elif d == 2:
+                nh = y * L + (x - 1) % L
+                ib = 2 * nh
+            else:
+                nh = ((y - 1) % L) * L + x
+                ib = 2 * nh + 1
+            nb = bonds[ib]
+            if algo == 0:
+                if (b >> 29) & 1 == 0:
+                    acc, delta = (nb < 255 and (nb + 1) * a < kfix), 1
+                else:
+                    acc, delta = (a < nb * tfix), -1
+            else:
+                acc, delta = (True, -1) if nb else (a < hfix, 1)
+            if acc:
+                bonds[ib] += delta
+                head = nh
+        o = wo.run_philox(L, algo, chain, seed, T, 0, steps, 0)
+        assert list(o["bonds"]) == bonds and o["head"] == head and o["tail"] == tail
+        assert int(o["acc"][0]) == Z and int(o["acc"][1]) == SNb
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "worm_algorithm_b200")
     for dirpath, _, files in os.walk(pkg):

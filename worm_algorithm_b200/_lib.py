@@ -15,7 +15,7 @@ SO_PATH = os.path.join(HERE, "libworm_b200.so")
 WORM_OK = 0
 ALGO_TAYLOR = 0
 ALGO_BINARY = 1
-ACC_Z, ACC_NB, ACC_NB2, ACC_N, ACC_N2, ACC_ITERS, ACC_STRIDE = 0, 1, 2, 3, 4, 5, 8
+ACC_Z, ACC_NB, ACC_NB2, ACC_N, ACC_N2, ACC_ITERS, ACC_STATUS, ACC_STRIDE = 0, 1, 2, 3, 4, 5, 6, 8
 MT_Z, MT_NB_TOT, MT_STEPS, MT_NB_FINAL, MT_STATUS, MT_STRIDE = 0, 1, 2, 3, 4, 8
 
 
@@ -43,6 +43,7 @@ SIGNATURES = {
                                   _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _u64, _i32, _vp, _vp, _vp,
                                   C.c_int, _vp, _sz, _vp]),
     "worm_thresholds": (C.c_int, [_dbl, _pu64, _pu64, _pu64]),
+    "worm_philox_words": (C.c_int, [_u64, _u64, _u64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "worm_image": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp]),
     "worm_block": (C.c_int, [C.c_int, _i64, _vp, _vp, C.c_int, C.c_int, _vp]),
     "worm_count": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp]),
@@ -93,6 +94,13 @@ def last_error() -> str:
 def check(rc: int) -> None:
     if rc != WORM_OK:
         raise WormError(rc, last_error())
+
+
+def philox_words(seed: int, chain_id: int, step: int):
+    """(a, b) of worm step `step` of chain `chain_id` under key `seed` (stream version 2, include/worm_b200.h)."""
+    a, b = C.c_uint32(), C.c_uint32()
+    check(lib().worm_philox_words(int(seed), int(chain_id), int(step), C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def thresholds(T: float):

@@ -137,6 +137,23 @@ int worm_thresholds(double T, uint64_t *kfix, uint64_t *tfix, uint64_t *hfix)
     return WORM_OK;
 }
 
+// Philox4x32-10 on the host: the words of one worm step of the production stream (version 2, see the header)
+int worm_philox_words(uint64_t seed, uint64_t chain_id, uint64_t step, uint32_t *a, uint32_t *b)
+{
+    const uint64_t pair = step >> 1;
+    uint32_t c0 = (uint32_t)pair, c1 = (uint32_t)(pair >> 32), c2 = (uint32_t)chain_id, c3 = (uint32_t)(chain_id >> 32);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    if (a) *a = (step & 1) ? c2 : c0;
+    if (b) *b = (step & 1) ? c3 : c1;
+    return WORM_OK;
+}
+
 /* ------------------------------------------------------------------------------------------- */
 size_t worm_mt_workspace_bytes(int64_t n_chains)
 {
@@ -250,8 +267,8 @@ int worm_philox_run(int L, int algo, int64_t n_chains, uint64_t chain_id0,
     a.bonds = d_bonds; a.head = d_head; a.tail = d_tail; a.acc = d_acc;
     a.group_index = d_group_index; a.hist = d_hist; a.group_acc = d_group_acc;
     a.dump_every = dump_every; a.max_dumps = max_dumps; a.n_dumps = d_n_dumps; a.events = d_events; a.dumps = d_dumps;
-    // One launch per chunk of <= 2^31 steps: the latency kernel keeps the G(r) bins of a launch in
-    // 32-bit shared-memory counters.  Chunking does not change any result (counter-based stream).
+    // One launch per chunk of <= 2^31 steps (round counters inside the kernels are 32-bit).  Chunking does
+    // not change any result (counter-based stream).
     const uint64_t chunk = 0x80000000ull;
     uint64_t s = step_begin;
     const uint64_t s_end = step_begin + n_steps;
