@@ -73,3 +73,64 @@ def test_unmodified_reference_classes_consume_our_tree(tmp_path):
         full, err = count_stats_with_err(n, 3)
         got = res["bond_stats"][str(float(T))]
         assert got == [float(full[0]), float(err[0]), float(full[1]), float(err[1])], (T, got)
+
+
+def _run_reference_on(root, L, temps):
+    """The unmodified reference classes (subprocess, cwd = <root>/worm_algorithm so that `../data` is our tree)."""
+    os.makedirs(os.path.join(root, "worm_algorithm"), exist_ok=True)
+    script = os.path.join(root, "ref_side.py")
+    with open(script, "w") as f:
+        f.write(_REF_SIDE)
+    p = subprocess.run([sys.executable, script, ROOT, str(L), json.dumps(temps)], cwd=os.path.join(root, "worm_algorithm"),
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("RESULT")][0][6:])
+
+
+def _check_reference_result(res, obs_file, dumps_by_T, L, temps):
+    from oracle import postproc_oracle as po
+    from worm_algorithm_b200.count_bonds import count_stats_with_err
+    from worm_algorithm_b200.specific_heat import SpecificHeat
+    ours = SpecificHeat(L, num_blocks=4, data_file=obs_file)
+    assert res["E_T"] == ours._energy_temps and res["E"] == [float(x) for x in ours._avg_energy]
+    assert res["E_err"] == [float(x) for x in ours._energy_error]
+    assert res["C_T"] == ours._spec_heat_temps and res["C"] == ours._spec_heat
+    for T in temps:
+        key = str(float(T)).rstrip('0')
+        imgs = np.array(res["images"][key]).reshape(-1, 2 * L, 2 * L)
+        want = np.array([po.image_from_bonds(d, L) for d in dumps_by_T[T]])
+        assert (imgs == want).all(), T
+        n = (dumps_by_T[T] & 1).sum(axis=1)
+        full, err = count_stats_with_err(n, 3)
+        assert res["bond_stats"][str(float(T))] == [float(full[0]), float(err[0]), float(full[1]), float(err[1])], T
+
+
+def test_unmodified_reference_classes_consume_production_tree(tmp_path):
+    """PRODUCTION mode (rng="philox"): the tree `WormSimulation._write_tree_philox` writes.  Built here from the
+    oracle's integers with the product's writer; tests/test_gpu_tree.py proves on the B200 that the GPU run writes
+    the same bytes."""
+    import tree_helpers as th
+    root = str(tmp_path)
+    dumps_by_T = th.oracle_tree(os.path.join(root, "data"))
+    res = _run_reference_on(root, th.L, th.TEMPS)
+    _check_reference_result(res, os.path.join(root, "data", "observables", "lattice_8", "observables_8.txt"),
+                            dumps_by_T, th.L, th.TEMPS)
+
+
+def test_unmodified_reference_classes_consume_the_gpu_written_tree(tmp_path):
+    """tests/golden/gpu_tree_L8.tar.gz was WRITTEN BY A B200 RUN (WormSimulation(rng="philox", data_dir=...) inside
+    tests/test_gpu_tree.py, brought back through gpurun_out/ and committed unchanged).  It must be the oracle-built tree,
+    file for file, and the unmodified reference classes must read it."""
+    import tarfile
+    import tree_helpers as th
+    tar = os.path.join(ROOT, "tests", "golden", "gpu_tree_L8.tar.gz")
+    if not os.path.exists(tar):
+        pytest.skip("fixture not generated yet")
+    root = str(tmp_path)
+    with tarfile.open(tar) as t:
+        t.extractall(os.path.join(root, "data"))
+    dumps_by_T = th.oracle_tree(os.path.join(root, "cpu"))
+    assert th.tree_digest(os.path.join(root, "data")) == th.tree_digest(os.path.join(root, "cpu"))
+    res = _run_reference_on(root, th.L, th.TEMPS)
+    _check_reference_result(res, os.path.join(root, "data", "observables", "lattice_8", "observables_8.txt"),
+                            dumps_by_T, th.L, th.TEMPS)

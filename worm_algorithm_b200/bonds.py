@@ -49,6 +49,8 @@ class Bonds(WormSimulation):
         res = getattr(self, "results", None)
         if res is not None and res.get("dumps") is not None:
             return self._dumps_from_results(res)
+        if res is not None:
+            raise ValueError("the run kept no dumps (bond_flag=0 or max_dumps=0): nothing to rasterise")
         out = {}
         if not os.path.isdir(self._bonds_dir):
             return out
@@ -77,12 +79,13 @@ class Bonds(WormSimulation):
                 d = [dumps[c, :k], final[c:c + 1]]            # the executable dumps once more at the end (:160-167)
                 out.setdefault(temperature_key(T[c]), []).extend(d)
         else:
-            st = res["state"]
-            nd = st.n_dumps.cpu().numpy()
+            # the stored dumps of every chain, then its final configuration -- what the executable leaves in
+            # bonds_{T}.txt (worm_ising_2d.cpp:120-124, :160-167)
+            dumps, final = res["dumps"], res["bonds"]
+            nd = res["n_dumps"].cpu().numpy()
             for c in range(T.size):
-                k = min(int(nd[c]), st.max_dumps)
-                if k:
-                    out.setdefault(temperature_key(T[c]), []).append(st.dumps[c, :k])
+                k = min(int(nd[c]), dumps.shape[1])
+                out.setdefault(temperature_key(float("%.12f" % T[c])), []).extend([dumps[c, :k], final[c:c + 1]])
         import torch
         return {k: torch.cat(v, dim=0) for k, v in out.items()}
 

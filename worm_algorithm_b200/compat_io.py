@@ -30,6 +30,17 @@ def averages(T: float, L: int, Z: int, Nb_tot: int, step: int):
     return Z_av, E_av, Nb_av
 
 
+def production_averages(T: float, L: int, Z: int, SNb: int, step: int, therm: int):
+    """(Z_av, E_av, Nb_av) of the production mode, where the sums start after the warm-up: Z_av = closed
+    fraction of the measured iterations, E_av = -T <Nb> / N (the reference's estimator, :116,185, on sums that
+    really exclude the warm-up), Nb_av = <Nb> / N (the reference's column is garbage)."""
+    N = L * L
+    measured = max(int(step) - int(therm), 1)
+    Z_av = Z / float(measured)
+    nb = SNb / float(Z * N) if Z else 0.0
+    return Z_av, -T * nb, nb
+
+
 def output_line(L: int, T: float, Z: int, Nb_tot: int, step: int) -> str:
     """setup/output.txt, worm_ising_2d.cpp:189-191."""
     Z_av, E_av, Nb_av = averages(T, L, Z, Nb_tot, step)
@@ -46,15 +57,52 @@ def observables_rows(L: int, T: float, events) -> str:
     return "".join(out)
 
 
-def bonds_text(dumps) -> str:
-    """bonds_{T}.txt: per configuration 2N lines `b occ` (worm_ising_2d.cpp:121-123,163-165)."""
+_BONDS_TEMPLATE = {}
+
+
+def _bonds_template(nb2: int):
+    """One configuration of bonds_{T}.txt with every occupation 0, as bytes, and where the digits sit."""
+    t = _BONDS_TEMPLATE.get(nb2)
+    if t is None:
+        text = "".join("%d 0\n" % b for b in range(nb2)).encode()
+        buf = np.frombuffer(text, dtype=np.uint8).copy()
+        pos = np.flatnonzero(buf == ord("\n")) - 1
+        t = _BONDS_TEMPLATE[nb2] = (buf, pos)
+    return t
+
+
+def bonds_bytes(dumps) -> bytes:
+    """bonds_{T}.txt: per configuration 2N lines `b occ` (worm_ising_2d.cpp:121-123,163-165).  Single-digit
+    occupations (all the Taylor chain produces at T >= 1) are poked into a byte template of the file, all
+    configurations at once; a configuration with an occupation >= 10 is formatted line by line."""
     d = np.asarray(dumps)
     d = d.reshape(-1, d.shape[-1])
-    idx = np.arange(d.shape[1])
-    lines = []
-    for cfg in d:
-        lines.append("".join("%d %d\n" % (b, o) for b, o in zip(idx.tolist(), cfg.tolist())))
-    return "".join(lines)
+    if d.shape[0] == 0:
+        return b""
+    buf, pos = _bonds_template(d.shape[1])
+    if int(d.max()) <= 9:
+        out = np.tile(buf, (d.shape[0], 1))
+        out[:, pos] = d.astype(np.uint8) + ord("0")
+        return out.tobytes()
+    idx = range(d.shape[1])
+    return "".join("".join("%d %d\n" % (b, o) for b, o in zip(idx, cfg.tolist())) for cfg in d).encode()
+
+
+def bonds_text(dumps) -> str:
+    return bonds_bytes(dumps).decode()
+
+
+def production_observables_rows(L: int, T: float, events, therm: int) -> str:
+    """observables_L.txt rows of the production mode, one per stored event {step, Z, sum Nb} (the values
+    before that iteration's own update, like worm_ising_2d.cpp:115-119).  An event with Z = 0 has nothing to
+    average yet and writes no row."""
+    out = []
+    for step, Z, snb in np.asarray(events, dtype=np.int64).reshape(-1, 3).tolist():
+        if Z <= 0:
+            continue
+        Z_av, E_av, Nb_av = production_averages(T, L, Z, snb, step, therm)
+        out.append("%g %g %g %g %d\n" % (T, E_av, Z_av, Nb_av, step))
+    return "".join(out)
 
 
 def temperature_file_tag(T: float) -> str:
@@ -121,12 +169,34 @@ class DataTree:
                     f.write(bonds_text(dumps))
                 if final_bonds is not None:
                     f.write(bonds_text(np.asarray(final_bonds).reshape(1, -1)))
+        self._write_tail(T, output_line(L, T, Z, Nb_tot, step), Nb_final)
+
+    def write_chain_production(self, T: float, Z: int, SNb: int, step: int, therm: int, Nb_final: int, events,
+                               dumps=None, final_bonds=None):
+        """The same files for one chain of the production mode (fixed-length run, sums measured after the
+        warm-up): observables rows from the stored events, the stored dumps plus the final configuration
+        (worm_ising_2d.cpp:160-167), output.txt, num_bonds."""
+        L = self.L
+        with open(os.path.join(self.obs_dir, "observables_%d.txt" % L), "a") as f:
+            f.write(production_observables_rows(L, T, events, therm))
+        if dumps is not None or final_bonds is not None:
+            with open(os.path.join(self.bonds_dir, "bonds_%s.txt" % temperature_file_tag(T)), "ab") as f:
+                if dumps is not None and len(dumps):
+                    f.write(bonds_bytes(dumps))
+                if final_bonds is not None:
+                    f.write(bonds_bytes(np.asarray(final_bonds).reshape(1, -1)))
+        Z_av, E_av, Nb_av = production_averages(T, L, Z, SNb, step, therm)
+        line = "%4i %.12f %.12f %.12f %.12f %.12f %u\n" % (L, T, 1.0 / T, Z_av, E_av, Nb_av, step)
+        self._write_tail(T, line, Nb_final)
+
+    def _write_tail(self, T: float, out_line: str, Nb_final: int):
+        L = self.L
         bm = os.path.join(self.bond_map_dir, "bond_map_%d.txt" % L)
         if not os.path.exists(bm):
             with open(bm, "w") as f:
                 f.write(bond_map_text(L))
         with open(os.path.join(self.setup, "output.txt"), "w") as f:
-            f.write(output_line(L, T, Z, Nb_tot, step))
+            f.write(out_line)
         with open(os.path.join(self.num_bonds_dir, "num_bonds_%d.txt" % L), "a") as f:
             f.write(num_bonds_line(L, T, Nb_final))
 

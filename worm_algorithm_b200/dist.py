@@ -28,3 +28,24 @@ def allreduce_sum(t: torch.Tensor, world: int) -> torch.Tensor:
             raise RuntimeError("world_size > 1 needs torch.distributed to be initialised")
         td.all_reduce(t, op=td.ReduceOp.SUM)
     return t
+
+
+def allgather_rows(t: torch.Tensor, n_total: int, rank: int, world: int) -> torch.Tensor:
+    """Rows of every rank's contiguous shard (shard_range) on every rank, in global order: [n_total, ...].
+    One all_gather of equally sized (padded) blocks -- the optional per-chain gather of SURVEY 8e, used for
+    error bars over replicas on rank 0."""
+    if world <= 1:
+        return t
+    import torch.distributed as td
+    if not td.is_initialized():
+        raise RuntimeError("world_size > 1 needs torch.distributed to be initialised")
+    width = -(-n_total // world)
+    pad = torch.zeros((width,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    td.all_gather(parts, pad)
+    rows = []
+    for r in range(world):
+        c0, c1 = shard_range(n_total, r, world)
+        rows.append(parts[r][:c1 - c0])
+    return torch.cat(rows, dim=0)

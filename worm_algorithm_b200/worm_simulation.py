@@ -13,15 +13,22 @@ Two modes:
   rng="philox"   production: counter-based RNG, fixed-length chains, warm-up excluded from the
                  averages; `_E` = -T<Nb>/N, `_Z` = closed fraction, `_Nb` = <Nb>/N.
 
+`rng="philox"` is the production mode (1e11-1e12 worm steps/s on a B200); the default `rng="mt19937"`
+is kept because it is what a literal drop-in call must reproduce, but it is the parity vehicle (one warp
+per chain, ~5e6 steps/s per chain).
+
 `data_dir` (default None = nothing written) reproduces the reference's `../data` tree
- so its analysis classes can read the results unchanged.
+ in BOTH modes -- observables rows, bonds_{T}.txt, num_bonds, output.txt, bond map -- so its
+analysis classes (`SpecificHeat`, `Bonds(run=False)`, `CountBonds`) read the results unchanged.
 """
 from __future__ import annotations
+
+import warnings
 
 import numpy as np
 
 from . import compat_io, engine
-from ._lib import ACC_ITERS, ACC_N, ACC_N2, ACC_NB, ACC_NB2, ACC_Z, ALGO_BINARY, ALGO_TAYLOR
+from ._lib import ACC_ITERS, ACC_N, ACC_N2, ACC_NB, ACC_NB2, ACC_STATUS, ACC_Z, ALGO_BINARY, ALGO_TAYLOR
 
 
 def temperature_key(T) -> str:
@@ -34,7 +41,7 @@ class WormSimulation(object):
                  T_start=1., T_end=3.5, T_step=0.1, T_arr=None, bond_flag=1,
                  seeds=None, n_replicas=1, rng="mt19937", algo="taylor", therm_frac=0.1,
                  write_steps=50, max_dumps=None, data_dir=None, device=None,
-                 lanes_per_chain=0, rank=0, world_size=1, hist=False):
+                 lanes_per_chain=0, rank=0, world_size=1, hist=False, gather_chains=False):
         self._L = int(L)
         self._num_steps = int(num_steps)
         self._verbose = verbose
@@ -61,6 +68,10 @@ class WormSimulation(object):
         self._rank, self._world = int(rank), int(world_size)
         self._seeds = seeds
         self._hist = bool(hist)
+        self._gather = bool(gather_chains)
+        if rng == "mt19937" and self._write_steps != 50:
+            raise ValueError("the deterministic mode dumps every 50 steps like worm_ising_2d.cpp:114; write_steps is a "
+                             "production-mode (rng='philox') option")
         self._tree = compat_io.DataTree(data_dir, self._L) if data_dir is not None else None
         self.results = None
         if self._run:
@@ -125,8 +136,19 @@ class WormSimulation(object):
         want_dumps = bool(self._bond_flag)
         max_events = self._max_dumps
         if max_events is None:
-            # every closed iteration at a multiple of 50 after warm-up is an event; Z_av <= ~0.5
-            max_events = min(int(0.9 * self._num_steps / self._write_steps) + 2, 4096)
+            # The executable keeps EVERY event (a closed iteration at a multiple of 50 after the warm-up,
+            # worm_ising_2d.cpp:113-125): size the buffers from a counting pass (max_events = 0 stores nothing
+            # and returns n_events; the chains are deterministic, the second pass repeats them).  Only asked
+            # for when the events are used -- for the files, or for the dumps.
+            if self._tree is not None or want_dumps:
+                cnt = engine.run_mt(L, Tc, seeds, self._num_steps, bond_flag=0, max_events=0, device=self._device)
+                max_events = int(cnt.n_events.max().item()) if n else 0
+                per_event = 24 + (2 * L * L if want_dumps else 0)
+                if n * max_events * per_event > (8 << 30):
+                    raise MemoryError("deterministic mode: {} chains x {} events x {} B exceed 8 GiB; pass max_dumps=... "
+                                      "to keep only the first events of every chain".format(n, max_events, per_event))
+            else:
+                max_events = 0
         res = engine.run_mt(L, Tc, seeds, self._num_steps, bond_flag=self._bond_flag,
                             max_events=max_events, device=self._device)
         out = res.out.cpu().numpy()
@@ -135,6 +157,11 @@ class WormSimulation(object):
                             n_events=res.n_events, events=res.events, dumps=res.dumps, mode="mt19937")
         if (out[:, 4] != 0).any():
             raise RuntimeError("bond occupation exceeded 254 (uint8 storage)")
+        self.results["n_events_dropped"] = int(np.maximum(n_ev - max_events, 0).sum())
+        if self.results["n_events_dropped"]:
+            warnings.warn("deterministic mode: {} events beyond max_dumps={} per chain were not stored; the files hold "
+                          "the first {} of each chain (the executable writes all)".format(
+                              self.results["n_events_dropped"], max_events, max_events))
         events = res.events.cpu().numpy() if (self._tree is not None) else None
         dumps = res.dumps.cpu().numpy() if (self._tree is not None and want_dumps and res.dumps is not None) else None
         final = res.bonds.cpu().numpy() if (self._tree is not None and want_dumps) else None
@@ -201,29 +228,44 @@ class WormSimulation(object):
         # Shard: contiguous block of the global chain range per rank.  Chain ids are global (they are
         # the Philox counter), so the reduced sums do not depend on the number of ranks.
         c0, c1 = dist.shard_range(n_all, self._rank, self._world)
+        if self._world > n_all:
+            raise ValueError("world_size {} exceeds the {} chains of the sweep".format(self._world, n_all))
+        # the reference reads T back from "%.12f" text (worm_simulation.py:53,119-121): same keys, same _T
+        T_round = np.array([float("%.12f" % t) for t in self._T_range])
         therm = int(self._therm_frac * self._num_steps)
         max_dumps = self._max_dumps
         if max_dumps is None:
-            max_dumps = 64 if self._bond_flag else 0
-        per_T = torch.zeros((nT, 8), dtype=torch.int64)
-        st = None
-        if c1 > c0:
-            st = engine.PhiloxState(L, Tc[c0:c1], seeds[c0:c1], algo=self._algo, chain_id0=c0,
-                                    group_index=t_idx[c0:c1], n_groups=nT, hist=self._hist,
-                                    max_dumps=max_dumps, store_dumps=bool(self._bond_flag), device=self._device)
-            self._run_with_dump_cap(st, therm, max_dumps)
-            per_T = st.group_acc                  # summed over the chains of each temperature on the device
-        per_T = dist.allreduce_sum(per_T, self._world)
+            # dumps (2N bytes each) are kept for the first 64 events of a chain; without dumps the events alone
+            # (observables rows, 24 bytes) are only wanted for the files
+            max_dumps = 64 if self._bond_flag else (256 if self._tree is not None else 0)
+        st = engine.PhiloxState(L, Tc[c0:c1], seeds[c0:c1], algo=self._algo, chain_id0=c0,
+                                group_index=t_idx[c0:c1], n_groups=nT, hist=self._hist,
+                                max_dumps=max_dumps, store_dumps=bool(self._bond_flag), device=self._device)
+        self._run_with_dump_cap(st, therm, max_dumps)
+        # per-temperature sums over the chains of this shard (device-side atomics), then over the ranks: a clone
+        # is reduced, the state keeps its local sums and can be run on
+        per_T = dist.allreduce_sum(st.group_acc.clone(), self._world)
         hist = None
         if self._hist:
             # G(r) histogram per temperature, [nT, N] with bin dy*L + dx; bin 0 == Z
-            hist = st.hist if st is not None else torch.zeros((nT, N), dtype=torch.int64, device=per_T.device)
-            hist = dist.allreduce_sum(hist, self._world)
+            hist = dist.allreduce_sum(st.hist.clone(), self._world)
+        acc_all = None
+        if self._gather:
+            # per-chain sums of every rank on every rank (the optional all-gather for error bars
+            # over replicas): rows in global chain order
+            acc_all = dist.allgather_rows(st.acc, n_all, self._rank, self._world)
+        status = int((st.acc[:, ACC_STATUS] != 0).sum().item())
+        if status:
+            raise RuntimeError("{} chains report a bond occupation the packed kernel cannot hold (WORM_ACC_STATUS); "
+                               "rerun with lanes_per_chain=1".format(status))
         self.results = dict(T=Tc[c0:c1], seeds=seeds[c0:c1], replica=r_idx[c0:c1], t_index=t_idx[c0:c1],
-                            chain_range=(c0, c1), acc=(st.acc if st is not None else None), state=st,
+                            chain_range=(c0, c1), acc=st.acc, acc_all=acc_all, state=st,
+                            dumps=st.dumps, n_dumps=st.n_dumps, events=st.events, bonds=st.bonds,
                             per_T=per_T, hist=hist, mode="philox", therm=therm)
+        if self._tree is not None:
+            self._write_tree_philox(st, Tc[c0:c1], therm, max_dumps)
         a = per_T.cpu().numpy().astype(np.float64)
-        for ti_, T in enumerate(self._T_range):
+        for ti_, T in enumerate(T_round):
             Z = a[ti_, ACC_Z]
             key = temperature_key(T)
             self._T.append(float(T))
@@ -234,3 +276,22 @@ class WormSimulation(object):
             self._sim_steps[key] = float(self._num_steps)
             if self._verbose:
                 print("Ran L = {}, T = {}, num_steps: {} x {} replicas".format(L, T, self._num_steps, self._n_replicas))
+
+    def _write_tree_philox(self, st, Tc, therm, max_dumps):
+        """The reference's files from the device buffers of a production run: per chain the
+        observables rows of its stored events (worm_ising_2d.cpp:113-119), with bond_flag its stored dumps and the
+        final configuration (:120-124, :160-167), output.txt (:189-191) and the num_bonds line (:195-198)."""
+        L = self._L
+        acc = st.acc.cpu().numpy()
+        nd = st.n_dumps.cpu().numpy()
+        ev = st.events.cpu().numpy()
+        want = bool(self._bond_flag)
+        dumps = st.dumps.cpu().numpy() if (want and st.dumps is not None) else None
+        final = st.bonds.cpu().numpy()
+        nb_final = final.sum(axis=1, dtype=np.int64)
+        for c in range(Tc.size):
+            T = float("%.12f" % Tc[c])
+            k = min(int(nd[c]), max_dumps)
+            self._tree.write_chain_production(T, int(acc[c, ACC_Z]), int(acc[c, ACC_NB]), int(st.step), therm,
+                                              int(nb_final[c]), ev[c, :k], dumps[c, :k] if dumps is not None else None,
+                                              final[c] if want else None)
