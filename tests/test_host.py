@@ -261,6 +261,11 @@ per_T = dist.allreduce_sum(per_T, world)
 full = np.zeros((nT, 8), dtype=np.int64)
 np.add.at(full, t_idx, acc)
 assert (per_T.numpy() == full).all(), "rank %d" % rank
+# the optional per-chain gather (SURVEY 8e): every rank ends up with all rows, in global chain order
+for n2 in (n, n - 5, 3):
+    a0, a1 = dist.shard_range(n2, rank, world)
+    got = dist.allgather_rows(torch.from_numpy(acc[a0:a1]), n2, rank, world)
+    assert got.shape == (n2, 8) and (got.numpy() == acc[:n2]).all(), "gather rank %d n %d" % (rank, n2)
 td.destroy_process_group()
 print("ok", rank)
 '''
