@@ -186,6 +186,18 @@ int worm_block(int W, int64_t n, const int32_t *d_in, int32_t *d_out,
                int double_bonds_value, int variant, void *stream);
 int worm_count(int W, int64_t n, const int32_t *d_img, int64_t *d_count, void *stream);
 
+/* worm_pipeline  the whole chain bonds.py:199-319 -> iterated_blocking.py:6-59 (x k) -> count_bonds.py:107-123 in
+ *              ONE launch, for the "1+1=0" blocking (double_bonds_value 0) of power-of-two lattices:
+ *              d_bonds u8 [n][2N] -> d_counts i64 [n][levels], d_counts[c][k] = number of odd-parity bond pixels
+ *              of configuration c after k blocking steps (k = 0: the image of the dump itself; lattice size
+ *              L >> k >= 2).  Identical to worm_count(worm_block^k(worm_image(.))) -- the kernel works on the
+ *              2 L^2 parity BITS of a configuration (a blocking step XORs the two bonds leaving each 2x2 block)
+ *              and reads 2 L^2 bytes per configuration instead of building the 16 L^2-byte int32 image pyramid.
+ *              h_level_images: NULL, or a HOST array of `levels` device pointers; a non-NULL entry k receives the
+ *              int32 images [n][2(L>>k)][2(L>>k)] of level k (what worm_image / worm_block would have produced). */
+int worm_pipeline(int L, int64_t n, const uint8_t *d_bonds, int levels, int64_t *d_counts,
+                  int32_t *const *h_level_images, void *stream);
+
 /* worm_boundaries  boundaries between the black and white regions of thresholded grey images
  *              (image_analysis/image.py:46-80, Image._cutoff + Image.get_boundaries), all images x all
  *              cutoffs in one launch: d_img f64 [n][Nx][Ny] (the class's `_image`, 1 - bytes/255),

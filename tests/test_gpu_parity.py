@@ -274,6 +274,41 @@ def test_postproc_matches_oracle_random(eng, L):
     assert (cnt == po.bond_counts(a, 2 * L)).all()
 
 
+@pytest.mark.parametrize("L", [4, 8, 16, 32, 64, 128, 256])
+def test_fused_pipeline_equals_the_launch_chain_and_the_oracle(eng, L):
+    """worm_pipeline (one launch, works on parity bits) == worm_count(worm_block^k(worm_image(.))) at every level,
+    images included, and == oracle/postproc_oracle.py (pinned to block_configs.py:6-71 / iterated_blocking.py:6-59)."""
+    import torch
+    from oracle import postproc_oracle as po
+    rng = np.random.default_rng(1000 + L)
+    n = 37 if L <= 64 else 9
+    bonds = rng.integers(0, 5, (n, 2 * L * L)).astype(np.uint8)
+    bonds[0] = 0
+    bonds[1] = 1
+    bt = torch.from_numpy(bonds).cuda()
+    levels = L.bit_length() - 1
+    counts, imgs = eng.pipeline(bt, L, images=range(levels))
+    assert counts.shape == (n, levels)
+    cur = eng.image(bt, L)
+    for k in range(levels):
+        assert (imgs[k] == cur).all(), (L, k)
+        assert (counts[:, k] == eng.count(cur)).all(), (L, k)
+        if k + 1 < levels:
+            cur = eng.block(cur, 0)
+    assert (eng.pipeline(bt, L) == counts).all()                       # without images
+    assert (eng.pipeline(bt, L, levels=1)[:, 0] == torch.from_numpy((bonds & 1).sum(axis=1).astype(np.int64)).cuda()).all()
+    if L <= 64:
+        c = counts.cpu().numpy()
+        for i in (0, 1, 2, n - 1):
+            img = po.image_from_bonds(bonds[i], L)
+            lv = L
+            for k in range(levels):
+                assert c[i, k] == po.bond_counts(img.reshape(1, -1), 2 * lv)[0], (L, i, k)
+                if k + 1 < levels:
+                    img = po.block_config(img.reshape(-1), 1, 0).reshape(lv, lv)
+                    lv //= 2
+
+
 def test_full_size_pipeline_properties(eng):
     """BASELINE config 3 sizes (L = 64, 128): size-independent properties at full size."""
     import torch

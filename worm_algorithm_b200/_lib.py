@@ -47,6 +47,7 @@ SIGNATURES = {
     "worm_image": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp]),
     "worm_block": (C.c_int, [C.c_int, _i64, _vp, _vp, C.c_int, C.c_int, _vp]),
     "worm_count": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp]),
+    "worm_pipeline": (C.c_int, [C.c_int, _i64, _vp, C.c_int, _vp, _vp, _vp]),
     "worm_sim_host": (C.c_int, [C.c_int, _i64, _pd, _pd, _pu64, _u64, _u64, C.c_int, C.c_int, _vp, _vp]),
     "worm_image_host": (C.c_int, [C.c_int, _i64, _vp, _vp]),
     "worm_block_host": (C.c_int, [C.c_int, _i64, _vp, _vp, C.c_int, C.c_int]),

@@ -322,6 +322,21 @@ int worm_count(int W, int64_t n, const int32_t *d_img, int64_t *d_count, void *s
     return WORM_OK;
 }
 
+int worm_pipeline(int L, int64_t n, const uint8_t *d_bonds, int levels, int64_t *d_counts,
+                  int32_t *const *h_level_images, void *stream)
+{
+    if (L < 4 || L > 1024 || (L & (L - 1))) return fail(WORM_E_ARG, "L = %d must be a power of two in [4, 1024]", L);
+    int maxlev = 0;
+    while ((L >> maxlev) >= 2) ++maxlev;
+    if (levels < 1 || levels > maxlev) return fail(WORM_E_ARG, "levels = %d out of range [1, %d] for L = %d", levels, maxlev, L);
+    if (n < 0 || (n > 0 && (!d_bonds || !d_counts))) return fail(WORM_E_ARG, "bad n / null pointer");
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    cudaError_t e = worm::launch_pipeline(L, n, d_bonds, levels, d_counts, h_level_images, dev.smem_optin, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "pipeline_kernel launch");
+    return WORM_OK;
+}
+
 int worm_boundaries(int Nx, int Ny, int64_t n, const double *d_img, int m, const double *d_cutoffs,
                     int32_t *d_links, void *stream)
 {

@@ -302,6 +302,135 @@ count_kernel(int W, int64_t n, const int32_t *__restrict__ img, int64_t *__restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused C3 pipeline: dumped occupations -> parity bits -> (images) -> every "1+1=0" blocking level -> counts,
+// one launch (bonds.py:199-319 -> iterated_blocking.py:6-59 x k -> count_bonds.py:107-123).
+//
+// Everything the chain computes is a function of the odd-parity bonds.  With X(x, y) / Y(x, y) the parities
+// of the +x / +y bond of site (x, y), one blocking step of a bond image is, in bond language
+// (block_configs.py:35-39,58-59 read through the pixel map of bonds.py:241-319):
+//     Y'(p, q) = Y(2p, 2q+1) ^ Y(2p+1, 2q+1)        (the two +y bonds leaving the 2x2 block; pixel B[2p][2q+1])
+//     X'(p, q) = X(2p+1, 2q) ^ X(2p+1, 2q+1)        (the two +x bonds leaving it;             pixel B[2p+1][2q])
+// the site pixel is the OR of the site's four incident bonds at every level (imaging: bonds.py:271-299;
+// blocking: :56-57 + the fix-up :61-65), and the bond count (count_bonds.py:110-117, pixels with i + j odd)
+// is popcount(X) + popcount(Y).  So a configuration is 2 L^2 BITS: a warp reads its 2 L^2 occupation bytes
+// once (coalesced 16-byte loads), keeps the bit rows of every level in shared memory (L^2 / 4 bytes at
+// level 0) and writes `levels` counts -- 2 L^2 bytes of HBM traffic per configuration instead of the
+// 16 L^2-byte int32 image and its pyramid.  Images of any level are written only on request.
+// Power-of-two L >= 4; level k has lattice size L >> k (>= 2).
+// ---------------------------------------------------------------------------------------------
+constexpr int PIPE_WARPS = 8;
+
+__device__ __forceinline__ uint32_t squeeze_even(uint32_t w)      // bits 0, 2, 4, ... -> bits 0, 1, 2, ... (16 of them)
+{
+    w &= 0x55555555u;
+    w = (w | (w >> 1)) & 0x33333333u;
+    w = (w | (w >> 2)) & 0x0f0f0f0fu;
+    w = (w | (w >> 4)) & 0x00ff00ffu;
+    return (w | (w >> 8)) & 0x0000ffffu;
+}
+
+struct PipeImages { int32_t *level[12]; };
+
+// bit rows of one level: X rows then Y rows, `wpr` words per row (row y of X at X[y * wpr ...])
+__device__ __forceinline__ void pipe_write_image(const uint32_t *X, const uint32_t *Y, int Ll, int wpr, int32_t *img, int lane)
+{
+    const int W = 2 * Ll, qn = W / 4;              // int4 per pixel row (W >= 4)
+    auto xb = [&](int x, int y) { return (int)((X[y * wpr + (x >> 5)] >> (x & 31)) & 1u); };
+    auto yb = [&](int x, int y) { return (int)((Y[y * wpr + (x >> 5)] >> (x & 31)) & 1u); };
+    int4 *dst = reinterpret_cast<int4 *>(img);
+    for (int t = lane; t < W * qn; t += 32) {
+        const int px = t / qn, qq = t - px * qn;
+        const int x = px >> 1, y0 = 2 * qq;
+        int4 o;
+        if (px & 1) {
+            o.x = xb(x, y0); o.y = 0;
+            o.z = (y0 + 1 < Ll) ? xb(x, y0 + 1) : 0; o.w = 0;
+        } else {
+            const int xm = x ? x - 1 : Ll - 1, ym = y0 ? y0 - 1 : Ll - 1;
+            const int yb0 = yb(x, y0), yb1 = yb(x, y0 + 1);
+            o.x = xb(x, y0) | yb0 | xb(xm, y0) | yb(x, ym);
+            o.y = yb0;
+            o.z = xb(x, y0 + 1) | yb1 | xb(xm, y0 + 1) | yb0;
+            o.w = yb1;
+        }
+        dst[t] = o;
+    }
+}
+
+__global__ void __launch_bounds__(PIPE_WARPS * 32)
+pipeline_kernel(int L, int64_t n, const uint8_t *__restrict__ bonds, int levels, int64_t *__restrict__ counts,
+                const PipeImages imgs, int words_per_warp)
+{
+    extern __shared__ __align__(16) uint32_t pipe_sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *buf = pipe_sm + (size_t)warp * words_per_warp;
+    const int N = L * L, nb2 = 2 * N;
+    const int wpr0 = L >= 32 ? L / 32 : 1;
+    const int lvl0_words = L * wpr0;                         // words of the X (or Y) rows at level 0
+    // level 0 lives in [0, 2 * lvl0_words), level 1 behind it, level 2 back at 0 (it is at most 1/4 the size) ...
+    for (int64_t cfg = (int64_t)blockIdx.x * PIPE_WARPS + warp; cfg < n; cfg += (int64_t)gridDim.x * PIPE_WARPS) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(bonds + cfg * (int64_t)nb2);
+        uint32_t *X = buf, *Y = buf + lvl0_words;
+        uint8_t *Xb = reinterpret_cast<uint8_t *>(X), *Yb = reinterpret_cast<uint8_t *>(Y);
+        if (L < 32) {
+            for (int i = lane; i < 2 * lvl0_words; i += 32) buf[i] = 0u;      // rows are padded to a word
+            __syncwarp();
+        }
+        // 16 occupation bytes = 8 sites = 8 X parities + 8 Y parities
+        for (int i = lane; i < nb2 / 16; i += 32) {
+            const uint4 v = src[i];
+            const uint32_t m0 = ((v.x & 0x01010101u) * 0x01020408u) >> 24;    // [X s, Y s, X s+1, Y s+1]
+            const uint32_t m1 = ((v.y & 0x01010101u) * 0x01020408u) >> 24;
+            const uint32_t m2 = ((v.z & 0x01010101u) * 0x01020408u) >> 24;
+            const uint32_t m3 = ((v.w & 0x01010101u) * 0x01020408u) >> 24;
+            const uint32_t m = (m0 & 15u) | ((m1 & 15u) << 4) | ((m2 & 15u) << 8) | ((m3 & 15u) << 12);
+            const uint32_t xs = squeeze_even(m), ys = squeeze_even(m >> 1);  // 8 bits each
+            if (L >= 8) {
+                const int s0 = 8 * i, y = s0 / L, x0 = s0 - y * L;
+                Xb[y * wpr0 * 4 + (x0 >> 3)] = (uint8_t)xs;
+                Yb[y * wpr0 * 4 + (x0 >> 3)] = (uint8_t)ys;
+            } else {                                                          // L = 4: two rows per piece
+                Xb[(2 * i) * 4] = (uint8_t)(xs & 15u); Xb[(2 * i + 1) * 4] = (uint8_t)(xs >> 4);
+                Yb[(2 * i) * 4] = (uint8_t)(ys & 15u); Yb[(2 * i + 1) * 4] = (uint8_t)(ys >> 4);
+            }
+        }
+        __syncwarp();
+        int Ll = L, wpr = wpr0;
+        for (int lv = 0; lv < levels; ++lv) {
+            int c = 0;
+            for (int i = lane; i < Ll * wpr; i += 32) c += __popc(X[i]) + __popc(Y[i]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) counts[cfg * levels + lv] = c;
+            if (imgs.level[lv]) pipe_write_image(X, Y, Ll, wpr, imgs.level[lv] + cfg * (int64_t)(4 * Ll * Ll), lane);
+            if (lv + 1 == levels) break;
+            // one blocking step into the other region
+            const int Ln = Ll / 2, wprn = Ln >= 32 ? Ln / 32 : 1;
+            uint32_t *Xn = (X == buf) ? buf + 2 * lvl0_words : buf;
+            uint32_t *Yn = Xn + Ln * wprn;
+            for (int i = lane; i < Ln * wprn; i += 32) {
+                const int q = i / wprn, j = i - q * wprn;
+                // X'(p, q), p = 32 j ..: odd bits of X rows 2q, 2q+1 (xor), words 2j and 2j+1
+                uint32_t t0 = X[(2 * q) * wpr + 2 * j] ^ X[(2 * q + 1) * wpr + 2 * j];
+                uint32_t u0 = Y[(2 * q + 1) * wpr + 2 * j];
+                uint32_t xn = squeeze_even(t0 >> 1);
+                uint32_t yn = squeeze_even(u0 ^ (u0 >> 1));
+                if (2 * j + 1 < wpr) {
+                    const uint32_t t1 = X[(2 * q) * wpr + 2 * j + 1] ^ X[(2 * q + 1) * wpr + 2 * j + 1];
+                    const uint32_t u1 = Y[(2 * q + 1) * wpr + 2 * j + 1];
+                    xn |= squeeze_even(t1 >> 1) << 16;
+                    yn |= squeeze_even(u1 ^ (u1 >> 1)) << 16;
+                }
+                Xn[i] = xn; Yn[i] = yn;
+            }
+            __syncwarp();
+            X = Xn; Y = Yn; Ll = Ln; wpr = wprn;
+        }
+        __syncwarp();
+    }
+}
+
 int grid_for(int64_t work_items, int threads, int waves_cap = 148 * 16)
 {
     int64_t b = (work_items + threads - 1) / threads;
@@ -424,6 +553,31 @@ cudaError_t launch_boundaries(int Nx, int Ny, int64_t n, int m, const double *d_
     const dim3 grid((unsigned)ims, (unsigned)nblk);
     if (pair) boundaries_kernel_pair<<<grid, threads, 0, st>>>(Nx, Ny, n, m, d_img, d_cutoffs, d_out);
     else boundaries_kernel<<<grid, threads, 0, st>>>(Nx, Ny, n, m, d_img, d_cutoffs, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pipeline(int L, int64_t n, const uint8_t *d_bonds, int levels, int64_t *d_counts,
+                            int32_t *const *h_level_images, int smem_optin, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    PipeImages imgs{};
+    for (int k = 0; k < 12; ++k) imgs.level[k] = (h_level_images && k < levels) ? h_level_images[k] : nullptr;
+    const int wpr0 = L >= 32 ? L / 32 : 1;
+    const int lvl0 = L * wpr0;
+    const int Ln = L / 2, wprn = Ln >= 32 ? Ln / 32 : 1;
+    const int words_per_warp = 2 * lvl0 + 2 * Ln * wprn;
+    const size_t smem = (size_t)PIPE_WARPS * words_per_warp * 4;
+    if (smem > (size_t)smem_optin) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t blocks_needed = (n + PIPE_WARPS - 1) / PIPE_WARPS;
+    // resident blocks per SM by shared memory (<= 8 by threads), a few waves at most
+    int per_sm = (int)((size_t)smem_optin / (smem + 1024));
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t cap = (int64_t)148 * per_sm * 4;
+    const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+    pipeline_kernel<<<grid, PIPE_WARPS * 32, smem, st>>>(L, n, d_bonds, levels, d_counts, imgs, words_per_warp);
     return cudaGetLastError();
 }
 

@@ -60,6 +60,9 @@ cudaError_t launch_image(int L, int64_t n, const uint8_t *d_bonds, int32_t *d_im
 cudaError_t launch_block(int W, int64_t n, const int32_t *d_in, int32_t *d_out, int dbv, int variant,
                          cudaStream_t st);
 cudaError_t launch_count(int W, int64_t n, const int32_t *d_img, int64_t *d_count, cudaStream_t st);
+// dumps -> bond counts of `levels` blocking levels (+ optional int32 images per level) in one launch
+cudaError_t launch_pipeline(int L, int64_t n, const uint8_t *d_bonds, int levels, int64_t *d_counts,
+                            int32_t *const *h_level_images, int smem_optin, cudaStream_t st);
 cudaError_t launch_boundaries(int Nx, int Ny, int64_t n, int m, const double *d_img, const double *d_cutoffs, int32_t *d_out,
                               cudaStream_t st);
 

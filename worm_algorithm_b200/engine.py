@@ -216,6 +216,32 @@ def count(images: torch.Tensor) -> torch.Tensor:
     return out.reshape(lead) if len(lead) else out.reshape(())
 
 
+def pipeline(bonds: torch.Tensor, L: int, levels: int | None = None, images=()):
+    """The C3 chain in one launch: uint8 occupations [..., 2N] -> int64 bond counts [..., levels] of the dump's image
+    and of its 1+1=0 blockings (bonds.py:199-319 -> iterated_blocking.py:6-59 -> count_bonds.py:107-123).
+    `images`: levels whose int32 images [..., 2(L>>k), 2(L>>k)] are also wanted -> (counts, {level: images})."""
+    dev = _dev(bonds.device)
+    b = bonds.contiguous()
+    if b.dtype != torch.uint8:
+        raise TypeError("bonds must be uint8")
+    if b.shape[-1] != 2 * L * L:
+        raise ValueError("last dimension must be 2*L*L")
+    lead = b.shape[:-1]
+    n = int(np.prod(lead)) if len(lead) else 1
+    if levels is None:
+        levels = max(int(L).bit_length() - 1, 1)            # down to the 2 x 2 lattice
+    want = sorted(set(int(k) for k in images))
+    with torch.cuda.device(dev):
+        counts = torch.empty((n, levels), dtype=torch.int64, device=dev)
+        imgs = {k: torch.empty((n, 2 * (L >> k), 2 * (L >> k)), dtype=torch.int32, device=dev) for k in want}
+        ptrs = (C.c_void_p * levels)(*[imgs[k].data_ptr() if k in imgs else None for k in range(levels)])
+        check(lib().worm_pipeline(L, n, _ptr(b), levels, _ptr(counts), ptrs if want else None, _stream_ptr(dev)))
+    counts = counts.reshape(*lead, levels)
+    if want:
+        return counts, {k: v.reshape(*lead, 2 * (L >> k), 2 * (L >> k)) for k, v in imgs.items()}
+    return counts
+
+
 def boundaries(images: torch.Tensor, cutoffs) -> torch.Tensor:
     """Black / white boundaries of thresholded grey images (image_analysis/image.py:46-80):
     f64 [n, Nx, Ny] x cutoffs [m] -> int32 [n, m, 2Nx, 2Ny]."""
