@@ -40,11 +40,19 @@ def _log_z(K: torch.Tensor, m: int, n: int) -> torch.Tensor:
         ax = torch.abs(x)
         return ax + torch.log(-torch.expm1(-2.0 * ax))
 
-    terms = [log2cosh(half_m * odd).sum(), log2sinh_abs(half_m * odd).sum(),
-             log2cosh(half_m * even).sum(), log2sinh_abs(half_m * even).sum()]
-    signs = [1.0, 1.0, 1.0, float(torch.sign(even[0]).item()) if even[0] != 0 else 0.0]   # only g_0 can be negative
-    mx = max(t for t in terms).detach()
-    s = sum(sg * torch.exp(t - mx) for sg, t in zip(signs, terms))
+    t1, t2 = log2cosh(half_m * odd).sum(), log2sinh_abs(half_m * odd).sum()
+    t3 = log2cosh(half_m * even).sum()
+    r4 = log2sinh_abs(half_m * even[1:]).sum()
+    x0 = half_m * even[0]
+    # g_0 goes through zero at T_c: its factor 2 sinh(m g_0 / 2) is kept in linear space there (in log space the
+    # value is right but the derivatives are not: ln|sinh| is singular at 0), in signed log space elsewhere
+    if abs(float(x0.detach())) < 1.0:
+        mx = max(float(t1.detach()), float(t2.detach()), float(t3.detach()), float(r4.detach()))
+        s = torch.exp(t1 - mx) + torch.exp(t2 - mx) + torch.exp(t3 - mx) + 2.0 * torch.sinh(x0) * torch.exp(r4 - mx)
+    else:
+        t4 = r4 + log2sinh_abs(x0)
+        mx = max(float(t1.detach()), float(t2.detach()), float(t3.detach()), float(t4.detach()))
+        s = torch.exp(t1 - mx) + torch.exp(t2 - mx) + torch.exp(t3 - mx) + float(torch.sign(x0.detach())) * torch.exp(t4 - mx)
     return -np.log(2.0) + 0.5 * m * n * torch.log(2.0 * torch.sinh(two_k)) + mx + torch.log(s)
 
 

@@ -113,6 +113,32 @@ def test_header_stream_contract_matches_oracle():
         assert int(o["acc"][0]) == Z and int(o["acc"][1]) == SNb
 
 
+def test_product_kaufman_matches_enumeration_and_the_oracle():
+    """worm_algorithm_b200/kaufman.py (second-order jets in numpy) against a brute-force enumeration written here
+    (L = 2, 3, 4, T_c included: the formula's g_0 changes sign there) and against oracle/kaufman.py (torch
+    autograd) on the lattices of BASELINE configs[3]."""
+    import itertools
+    from oracle import kaufman as ok
+    from worm_algorithm_b200 import kaufman as pk
+    tc = pk.T_C
+    for L in (2, 3, 4):
+        idx = np.arange(L * L).reshape(L, L)
+        right, down = np.roll(idx, -1, axis=1), np.roll(idx, -1, axis=0)
+        es = np.array([-(np.array(b)[idx] * np.array(b)[right]).sum() - (np.array(b)[idx] * np.array(b)[down]).sum()
+                       for b in itertools.product((-1, 1), repeat=L * L)], dtype=np.float64)
+        for T in (1.2, 2.269, tc, tc * (1 + 1e-9), 3.5):
+            w = np.exp(-(es - es.min()) / T)
+            e1, e2 = (w * es).sum() / w.sum(), (w * es * es).sum() / w.sum()
+            e, c = pk.energy_and_specific_heat(T, L)
+            assert abs(e - e1 / (L * L)) < 1e-12 and abs(c - (e2 - e1 * e1) / (T * T * L * L)) < 1e-10, (L, T)
+    for L in (8, 16, 32, 64, 128, 256):
+        for T in (1.0, 1.5, 2.269, tc, 3.5):
+            a, b = pk.energy_and_specific_heat(T, L), ok.energy_and_specific_heat(T, L)
+            assert abs(a[0] - b[0]) < 1e-11 and abs(a[1] - b[1]) < 1e-8, (L, T, a, b)
+    E, Cv = pk.exact_curve([2.0, 2.269], 32)
+    assert abs(E[1] + 1.43400062226) < 1e-9 and abs(Cv[1] - 1.84594475339) < 1e-9
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "worm_algorithm_b200")
     for dirpath, _, files in os.walk(pkg):
