@@ -20,7 +20,11 @@ Numbers:
          reduced sums are all inside the timed region (wall clock around a synchronised call).
   roofline        SM integer-issue roofline of the worm kernel (64 thread-instr/step).
   roofline_blocking  HBM roofline of the RG blocking kernel (20 L^2 bytes per config per level).
-  pipeline_c3     images -> blocking chain -> counts of 4096 L=64 dumps on the device (configs/s) + the numpy port.
+  roofline_packed the same issue roofline for the packed throughput kernel (worm_pack_kernel) on 125 000 L=32 chains.
+  lattice_shapes  the other lattice shapes / batch sizes BASELINE.json names, with the kernel variant chosen for each.
+  c5              BASELINE configs[4]: 1e6 L=32 chains with G(r) histograms over the N ranks, one all-reduce.
+  pipeline_c3     4096 L=64 dumps -> images -> blocking levels -> counts: the fused one-launch kernel and the
+                  12-launch chain on the device (configs/s) + the numpy port.
   roofline_pca    tensor roofline of the PCA Gram kernel (int8 tcgen05) + stage times + sklearn CPU baseline.
   cpu_baseline    the UNMODIFIED reference executable (oracle/_ref) on all host cores, bounded sample.
 """
@@ -298,6 +302,24 @@ def run_b200_arm(a) -> None:
     h2d = n * 32 + n * 4                      # PhiloxChain records + group index
     d2h = N_T * 8 * 8                         # reduced per-temperature sums
 
+    # ---- multi-GPU correctness under the driver's eyes: a short pass whose per-chain sums are gathered from every
+    # rank; rank 0 re-runs 64 chains owned by the LAST rank as their own batch and compares (chain ids are global,
+    # so a chain's trajectory must not depend on which GPU, block or launch geometry ran it)
+    from worm_algorithm_b200 import dist
+    st.reset()
+    st.run(100_000, therm_steps=10_000, lanes_per_chain=a.lanes)
+    acc_all = dist.allgather_rows(st.acc, n * world, rank, world)
+    multi_equal = None
+    if rank == 0:
+        lo = (world - 1) * n
+        sl = slice(0, 64)
+        chk = engine.PhiloxState(L_BENCH, T_chain[sl], (r_idx[sl] - rank * N_REP + (world - 1) * N_REP).astype(np.uint64),
+                                 algo=algo, chain_id0=lo, device=dev)
+        chk.run(100_000, therm_steps=10_000, lanes_per_chain=1)        # a different kernel on purpose
+        multi_equal = bool((chk.acc == acc_all[lo:lo + 64]).all().item())
+        del chk
+    c5 = bench_c5(torch, td, engine, dist, dev, rank, world, algo)
+
     if rank != 0:
         if world > 1:
             td.destroy_process_group()
@@ -345,6 +367,7 @@ def run_b200_arm(a) -> None:
                 "peak_source": "148 SM x 128 lanes x sm_max_mhz (MEASURED_PEAKS.json)" if peaks else "fallback 1965 MHz",
                 "cycles_per_step_per_chain": f_max * n / kern_rate, "executed": executed or None}
     shapes = bench_shapes(torch, engine, dev, algo, issue_peak)
+    roofline_packed = bench_packed(torch, engine, dev, algo, issue_peak, f_max)
     roofline_blocking = bench_blocking(torch, engine, dev, peaks)
     roofline_pca = bench_pca(torch, engine, dev, peaks, cpu=(world == 1 and not a.no_cpu))
     pipeline_c3 = bench_pipeline(torch, engine, dev, peaks, cpu=(world == 1 and not a.no_cpu))
@@ -368,12 +391,17 @@ def run_b200_arm(a) -> None:
         "gpu_launches": a.steps * st.launches_per_run,
         "clocks": clocks,
         "roofline": roofline,
+        "roofline_packed": roofline_packed,
         "lattice_shapes": shapes,
+        "c5": c5,
         "roofline_blocking": roofline_blocking,
         "roofline_pca": roofline_pca,
         "pipeline_c3": pipeline_c3,
         "cpu_baseline": cpu,
-        "check": {"E_T1.5": float(E[0]), "E_T3.5": float(E[-1]), "e2e_E_T1.5": float(e2e_E[0]),
+        "check": {"multi_gpu_equal": multi_equal,
+                  "multi_gpu_equal_what": "64 chains owned by rank %d, 1e5 steps: per-chain sums all-gathered to rank 0 == "
+                                          "the same chains re-run on rank 0 as their own batch by another kernel" % (world - 1),
+                  "E_T1.5": float(E[0]), "E_T3.5": float(E[-1]), "e2e_E_T1.5": float(e2e_E[0]),
                   "kaufman_E_T1.5": -1.9511165659, "kaufman_E_T3.5": -0.6601217470},
     }
     emit(line)
@@ -381,30 +409,111 @@ def run_b200_arm(a) -> None:
         td.destroy_process_group()
 
 
+def _time_run(torch, engine, dev, L, n, steps, algo, hist, lanes=0):
+    from worm_algorithm_b200 import _lib
+    t_idx = np.repeat(np.arange(N_T), -(-n // N_T))[:n]          # temperature-major: a block's chains share a temperature
+    T = sweep_temperatures()[t_idx]
+    seeds = (np.arange(n) % max(-(-n // N_T), 1)).astype(np.uint64)
+    st = engine.PhiloxState(L, T, seeds, algo=algo, device=dev, group_index=t_idx, n_groups=N_T, hist=hist)
+    st.run(max(steps // 10, 1), lanes_per_chain=lanes)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record(); st.run(steps, lanes_per_chain=lanes); e1.record()
+    torch.cuda.synchronize(dev)
+    status = int((st.acc[:, 6] != 0).sum().item())
+    del st
+    variant = lanes if lanes else _lib.philox_choice(L, algo, n, hist)
+    return float(n) * steps / (e0.elapsed_time(e1) * 1e-3), _lib.VARIANT_NAMES.get(variant, str(variant)), status
+
+
 def bench_shapes(torch, engine, dev, algo, issue_peak) -> list:
     """The other lattice shapes BASELINE.json names (configs[0], [2], [3], [4]) on this GPU: worm steps/s and
-    independent sweeps/s of a 64-temperature sweep, state resident, CUDA events around one launch, and the
-    fraction of the same issue roofline (I_ALG thread-instructions per step).  Not the headline: the kernel
-    variant and the chains a block holds change with L."""
+    independent sweeps/s of a 64-temperature sweep, state resident, CUDA events around one launch (the per-chain
+    parameter upload of the call included), the kernel variant `lanes_per_chain = 0` chose, and the fraction of the
+    same issue roofline (I_ALG thread-instructions per step).  A chain is a sequence of dependent steps, so a shape's
+    rate is (chains in flight) / (cycles per step) until the issue slots run out: small batches of large lattices
+    are bounded by the chains given, not by the GPU."""
     out = []
-    cases = [(16, 4096, 400_000, False), (32, 4096, 400_000, True), (64, 4096, 100_000, False),
-             (128, 1024, 100_000, False), (256, 512, 100_000, False), (32, 125_000, 20_000, True)]
-    for L, n, steps, hist in cases:
-        t_idx = np.arange(n) % N_T
-        T = sweep_temperatures()[t_idx]
-        seeds = (np.arange(n) // N_T).astype(np.uint64)
-        st = engine.PhiloxState(L, T, seeds, algo=algo, device=dev, group_index=t_idx, n_groups=N_T, hist=hist)
-        st.run(max(steps // 10, 1))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(dev)
-        e0.record(); st.run(steps); e1.record()
-        torch.cuda.synchronize(dev)
-        rate = float(n) * steps / (e0.elapsed_time(e1) * 1e-3)
-        out.append({"L": L, "chains": n, "worm_steps_per_chain": steps, "G_r_histograms": hist,
-                    "worm_steps_per_s": rate, "sweeps_per_s": rate / (2 * L * L),
-                    "issue_roofline_frac": rate * I_ALG / issue_peak})
-        del st
+    T_, B_ = engine.ALGO_TAYLOR, engine.ALGO_BINARY
+    cases = [(16, 4096, 400_000, False, algo), (32, 4096, 400_000, True, algo),
+             (32, 125_000, 40_000, False, T_), (32, 125_000, 40_000, False, B_), (32, 125_000, 20_000, True, T_),
+             (64, 4096, 100_000, False, algo), (64, 8288, 100_000, False, T_), (64, 32_768, 40_000, False, B_),
+             (128, 1024, 100_000, False, algo), (128, 2072, 100_000, False, T_), (128, 8192, 100_000, False, B_),
+             (256, 512, 100_000, False, algo), (256, 2072, 100_000, False, B_)]
+    for L, n, steps, hist, al in cases:
+        rate, variant, status = _time_run(torch, engine, dev, L, n, steps, al, hist)
+        out.append({"L": L, "chains": n, "algo": "taylor" if al == T_ else "binary", "worm_steps_per_chain": steps,
+                    "G_r_histograms": hist, "kernel": variant, "worm_steps_per_s": rate, "sweeps_per_s": rate / (2 * L * L),
+                    "issue_roofline_frac": rate * I_ALG / issue_peak, "chains_with_status": status})
     return out
+
+
+def bench_packed(torch, engine, dev, algo, issue_peak, f_max) -> dict:
+    """Issue roofline of the packed throughput kernel (worm_pack.cu) on one wave and on 125 000 chains of the L=32
+    sweep (no histograms), with what ncu saw it execute (profiles/traffic.json, written by tools/ncu_traffic.py)."""
+    T_ = engine.ALGO_TAYLOR
+    n, steps = 125_000, 40_000
+    rate, variant, _ = _time_run(torch, engine, dev, L_BENCH, n, steps, T_, False, lanes=-2)
+    rate1, _, _ = _time_run(torch, engine, dev, L_BENCH, 148 * 224, 100_000, T_, False, lanes=-2)
+    executed = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("worm_pack_kernel_thread_inst"):
+            cs = float(tj["worm_pack_kernel_chain_steps"])
+            executed = {"thread_instr_per_worm_step": tj["worm_pack_kernel_thread_inst"] / cs,
+                        "sm_issue_slots_used": tj.get("worm_pack_kernel_issue_pct", 0.0) / 100.0,
+                        "alu_pipe_pct": tj.get("worm_pack_kernel_alu_pct"), "fmaheavy_pipe_pct": tj.get("worm_pack_kernel_fmaheavy_pct"),
+                        "smem_bank_conflicts": tj.get("worm_pack_kernel_bank_conflicts"),
+                        "smem_wavefronts": tj.get("worm_pack_kernel_smem_wavefronts"),
+                        "dram_bytes_per_launch": tj.get("worm_pack_kernel"),
+                        "source": "ncu --set full of one launch of 33 152 chains (profiles/r02_pack_*): each of the two math "
+                                  "pipes (ALU, FMA-heavy) takes a warp instruction every other cycle, and a step is ~35 ALU + "
+                                  "~25 FMA-pipe instructions, so the pipes, not the issue port, are what saturates"}
+    except (OSError, ValueError):
+        pass
+    return {"bound": "issue", "kernel": "worm_pack_kernel", "workload": "%d chains x %d steps of the L=32 sweep, Taylor chain, 4 bits per bond" % (n, steps),
+            "achieved": rate * I_ALG / 1e9, "peak": issue_peak / 1e9, "unit": "G thread-instr/s", "frac": rate * I_ALG / issue_peak,
+            "worm_steps_per_s": rate, "one_wave": {"chains": 148 * 224, "worm_steps_per_s": rate1, "frac": rate1 * I_ALG / issue_peak,
+                                                   "cycles_per_step_per_chain": f_max * 148 * 224 / rate1},
+            "alg_instr_per_worm_step": I_ALG, "executed": executed, "traffic": (executed or {}).get("dram_bytes_per_launch")}
+
+
+def bench_c5(torch, td, engine, dist, dev, rank, world, algo) -> dict:
+    """BASELINE configs[4]: 1e6 independent L=32 chains (64 temperatures x 15 625 seeds) with G(r) histograms, sharded
+    over the ranks (contiguous blocks of the global chain range), ONE all-reduce of the per-temperature sums and
+    histograms.  Timed on the device, max over ranks; every rank checks G(0) = Z and sum of bins = iterations."""
+    n_all, steps = 1_000_000, 20_000
+    c0, c1 = dist.shard_range(n_all, rank, world)
+    t_idx = (np.arange(c0, c1) // 15_625).astype(np.int32)                    # temperature-major
+    T = sweep_temperatures()[t_idx]
+    seeds = (np.arange(c0, c1) % 15_625).astype(np.uint64)
+    st = engine.PhiloxState(L_BENCH, T, seeds, algo=algo, chain_id0=c0, device=dev, group_index=t_idx, n_groups=N_T, hist=True)
+    st.run(2_000)                                                             # warm-up launch (also thermalises)
+    st.group_acc.zero_(); st.hist.zero_(); st.acc.zero_()
+    if world > 1:
+        td.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    st.run(steps)
+    per_T = dist.allreduce_sum(st.group_acc.clone(), world)
+    hist = dist.allreduce_sum(st.hist.clone(), world)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(ms, op=td.ReduceOp.MAX)
+    ok = bool((hist[:, 0] == per_T[:, 0]).all().item()) and int(hist.sum().item()) == n_all * steps \
+        and bool((hist.sum(dim=1) == per_T[:, 5]).all().item())
+    from worm_algorithm_b200 import _lib
+    variant = _lib.philox_choice(L_BENCH, algo, c1 - c0, True)
+    del st
+    return {"workload": "1e6 L=32 chains x %d steps with G(r) histograms over %d GPU(s), one all-reduce (sums 4 KiB + "
+                        "histograms 512 KiB)" % (steps, world), "chains_total": n_all, "chains_per_gpu": c1 - c0,
+            "worm_steps_per_s": float(n_all) * steps / (float(ms[0]) * 1e-3), "ms": float(ms[0]),
+            "kernel": _lib.VARIANT_NAMES.get(variant, str(variant)),
+            "hist_checks": {"G0_equals_Z_and_bins_sum_to_iterations": ok}}
 
 
 def bench_pipeline(torch, engine, dev, peaks, cpu: bool) -> dict:
@@ -422,20 +531,36 @@ def bench_pipeline(torch, engine, dev, peaks, cpu: bool) -> dict:
             counts.append(engine.count(img))
         return counts
 
-    for _ in range(3):
-        counts = chain()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
-    e0.record()
-    for _ in range(reps):
-        counts = chain()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / reps
-    out = {"workload": "L=64: %d dumps -> images -> blocking chain to L=2 -> counts per level" % n,
-           "configs_per_s": n / (ms * 1e-3), "ms_per_batch": ms, "launches_per_batch": 1 + 6 + 5,
-           "levels": len(counts), "mean_count_level0": float(counts[0].double().mean())}
+    def timed(fn, reps):
+        for _ in range(3):
+            r = fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps, r
+
+    ms_chain, counts = timed(chain, 10)
+    ms, fused = timed(lambda: engine.pipeline(bonds, L), 20)
+    same = all(bool((fused[:, k] == counts[k]).all().item()) for k in range(len(counts)))
+    # a batch larger than L2 for the bandwidth figure (the 4096-config batch is 32 MiB and launch-bound)
+    nb_ = 65536
+    big = (torch.rand((nb_, 2 * L * L), device=dev, generator=gen) < 0.3).to(torch.uint8)
+    ms_big, _ = timed(lambda: engine.pipeline(big, L), 10)
+    del big
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    out = {"workload": "L=64: %d dumps -> images -> blocking levels to L=2 -> counts per level" % n,
+           "kernel": "pipeline_kernel (one launch, on the 2 L^2 parity bits of a configuration)",
+           "configs_per_s": n / (ms * 1e-3), "ms_per_batch": ms, "launches_per_batch": 1,
+           "equals_launch_chain": same, "levels": len(counts), "mean_count_level0": float(counts[0].double().mean()),
+           "launch_chain": {"configs_per_s": n / (ms_chain * 1e-3), "ms_per_batch": ms_chain, "launches_per_batch": 1 + 6 + 5},
+           "roofline": {"bound": "hbm", "configs": nb_, "alg_bytes_per_config": 2 * L * L + 8 * len(counts), "ms_per_launch": ms_big,
+                        "configs_per_s": nb_ / (ms_big * 1e-3), "achieved": nb_ * (2.0 * L * L + 8 * len(counts)) / (ms_big * 1e-3) / 1e9,
+                        "peak": peak, "unit": "GB/s", "frac": nb_ * (2.0 * L * L + 8 * len(counts)) / (ms_big * 1e-3) / 1e9 / peak,
+                        "traffic": _traffic("pipeline_kernel")}}
     if cpu:
         from oracle import postproc_oracle as po
         sample = bonds[:4].cpu().numpy()
@@ -482,6 +607,27 @@ def bench_pca(torch, engine, dev, peaks, cpu: bool) -> dict:
     lib.worm_pca_timing(0)
     ops = float(n) * d * (d + 1)
     peak = 2.0 * float(peaks.get("bf16_tflops", 1627.0))
+    peak_source = "2 x bf16_tflops of MEASURED_PEAKS.json (int8 dense is 2x bf16 nominally)"
+    try:
+        # a measured int8 figure: cuBLASLt s8 x s8 -> s32 GEMM 8192^3 through torch._int_mm, best of 10
+        ai = torch.randint(-8, 8, (8192, 8192), device=dev, dtype=torch.int8)
+        bi = torch.randint(-8, 8, (8192, 8192), device=dev, dtype=torch.int8)
+        for _ in range(2):
+            torch._int_mm(ai, bi)
+        bestms = None
+        for _ in range(10):
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(); torch._int_mm(ai, bi); g1.record()
+            torch.cuda.synchronize(dev)
+            t_ = g0.elapsed_time(g1)
+            bestms = t_ if bestms is None else min(bestms, t_)
+        meas = 2.0 * 8192.0 ** 3 / (bestms * 1e-3) / 1e12
+        del ai, bi
+        if meas > 100.0:
+            peak = meas
+            peak_source = "measured here: torch._int_mm (cuBLASLt s8 x s8 -> s32) 8192^3, best of 10, %.0f Top/s" % meas
+    except Exception as ex:                       # noqa: BLE001  (no int8 GEMM in this torch build: keep the nominal figure)
+        peak_source += "; torch._int_mm unavailable (%s)" % type(ex).__name__
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -490,7 +636,7 @@ def bench_pca(torch, engine, dev, peaks, cpu: bool) -> dict:
         pass
     out = {"bound": "tensor", "kernel": "gram_kernel", "achieved": ops / (best[2] * 1e-3) / 1e12, "peak": peak,
            "unit": "Top/s (int8)", "frac": ops / (best[2] * 1e-3) / 1e12 / peak, "traffic": traffic,
-           "peak_source": "2 x bf16_tflops of MEASURED_PEAKS.json (no measured int8 figure; int8 dense is 2x bf16 nominally)",
+           "peak_source": peak_source,
            "alg_ops": "2 x n x d(d+1)/2, n = %d images, d = %d pixels" % (n, d),
            "stage_ms": {"pack": best[0], "gate": best[1], "gram": best[2], "iterate": best[3]},
            "iterations": res.iters, "ms_per_call": wall_best * 1e3, "images_per_s": n / wall_best,
@@ -529,10 +675,24 @@ def bench_blocking(torch, engine, dev, peaks) -> dict:
     alg = 20.0 * L * L * n
     peak = float(peaks.get("hbm_gbs", 6650.0))
     del out
+    need = 16.0 * L * L * n          # rows 4p, 4p+2, 4p+3 of the input (row 4p+1 is never needed) + the output
     return {"bound": "hbm", "kernel": "block_kernel_vec", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak,
-            "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+            "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": _traffic("block_kernel_vec"),
             "alg_bytes_per_config": 20 * L * L, "configs_per_launch": n, "ms_per_launch": ms,
+            "needed_bytes_per_config": 16 * L * L, "achieved_on_needed_bytes": need / (ms * 1e-3) / 1e9,
+            "frac_on_needed_bytes": need / (ms * 1e-3) / 1e9 / peak,
+            "note": "the contract's 20 L^2 B per config counts all four input rows of a block; the kernel reads three (12 L^2 B) "
+                    "and writes 4 L^2 B, so `frac` above 1 is not faster than HBM -- frac_on_needed_bytes is the honest one",
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}
+
+
+def _traffic(kernel: str):
+    """dram__bytes_read + dram__bytes_write per launch of `kernel` from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except (OSError, ValueError):
+        return None
 
 
 _REAL_STDOUT = None

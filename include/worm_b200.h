@@ -160,6 +160,9 @@ int worm_philox_run(int L, int algo, int64_t n_chains, uint64_t chain_id0,
                     int64_t *d_events, uint8_t *d_dumps,
                     int lanes_per_chain, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* the kernel variant lanes_per_chain = 0 runs for this batch on the current device (2 / 4 / 8 / 32 / 1 / -2) */
+int worm_philox_choice(int L, int algo, int64_t n_chains, int hist, int *lanes_per_chain);
+
 /* The two words (a, b) of worm step `step` of chain `chain_id` under key `seed` -- the stream every
  * production kernel consumes (host arithmetic only, no GPU needed; for binders' known-answer tests).
  * Known answer, seed 1, chain 0: step 0 (0xe3e80670, 0xe50a0ebc), step 1 (0x95f222c0, 0xb615aa27),

@@ -43,6 +43,7 @@ SIGNATURES = {
                                   _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _u64, _i32, _vp, _vp, _vp,
                                   C.c_int, _vp, _sz, _vp]),
     "worm_thresholds": (C.c_int, [_dbl, _pu64, _pu64, _pu64]),
+    "worm_philox_choice": (C.c_int, [C.c_int, C.c_int, _i64, C.c_int, C.POINTER(C.c_int)]),
     "worm_philox_words": (C.c_int, [_u64, _u64, _u64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "worm_image": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp]),
     "worm_block": (C.c_int, [C.c_int, _i64, _vp, _vp, C.c_int, C.c_int, _vp]),
@@ -102,6 +103,18 @@ def philox_words(seed: int, chain_id: int, step: int):
     a, b = C.c_uint32(), C.c_uint32()
     check(lib().worm_philox_words(int(seed), int(chain_id), int(step), C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+VARIANT_NAMES = {2: "worm_lat_kernel (32 chains per walker)", 4: "worm_lat_kernel (8 chains per walker)",
+                 8: "worm_lat_kernel (4 chains per walker)", 32: "worm_lat_kernel (1 chain per walker)",
+                 1: "worm_wide_kernel", -1: "worm_wide_kernel (global memory)", -2: "worm_pack_kernel"}
+
+
+def philox_choice(L: int, algo: int, n_chains: int, hist: bool = False) -> int:
+    """The variant `lanes_per_chain = 0` picks for this batch on the current device."""
+    g = C.c_int(0)
+    check(lib().worm_philox_choice(int(L), int(algo), int(n_chains), int(bool(hist)), C.byref(g)))
+    return g.value
 
 
 def thresholds(T: float):

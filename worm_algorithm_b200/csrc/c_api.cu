@@ -287,6 +287,16 @@ int worm_philox_run(int L, int algo, int64_t n_chains, uint64_t chain_id0,
     return WORM_OK;
 }
 
+int worm_philox_choice(int L, int algo, int64_t n_chains, int hist, int *lanes_per_chain)
+{
+    if (!lanes_per_chain) return fail(WORM_E_ARG, "null pointer");
+    if (L < 3 || L > 1024 || n_chains <= 0) return fail(WORM_E_ARG, "L = %d / n_chains = %lld out of range", L, (long long)n_chains);
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    *lanes_per_chain = worm::choose_philox_variant(L, algo, n_chains, hist != 0, dev.smem_optin, dev.sm);
+    return WORM_OK;
+}
+
 /* ------------------------------------------------------------------------------------------- */
 int worm_image(int L, int64_t n, const uint8_t *d_bonds, int32_t *d_img, void *stream)
 {

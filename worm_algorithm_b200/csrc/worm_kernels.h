@@ -46,6 +46,9 @@ cudaError_t launch_mt(int L, int64_t n_chains, int64_t n_pad, const MtChain *d_p
 cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, bool lowt, int smem_optin, int sm_count,
                           cudaStream_t st, const char **why);
 
+// the variant launch_philox runs for lanes_per_chain = 0 (one of 2, 4, 8, 32, 1, -2)
+int choose_philox_variant(int L, int algo, int64_t n_chains, bool hist, int smem_optin, int sm_count);
+
 // the two kernels behind launch_philox.  G = lanes_per_chain of the C ABI (4 / 8 / 32 <-> 8 / 4 / 1
 // chains per walker warp of the latency kernel).
 size_t lat_smem_bytes(int L, int G, bool hist, int smem_optin);   // 0 if this L / G cannot run in latency mode

@@ -3,12 +3,10 @@
 
 namespace worm {
 
-cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, bool lowt, int smem_optin, int sm_count,
-                          cudaStream_t st, const char **why)
+int choose_philox_variant(int L, int algo, int64_t n_chains, bool hist, int smem_optin, int sm_count)
 {
-    *why = "";
-    const bool hist = (a.hist != nullptr && a.group_index != nullptr);
-    int G = lanes_per_chain;
+    struct { int L, algo; int64_t n_chains; } a{L, algo, n_chains};
+    int G = 0;
     if (G == 0) {
         // A chain is a sequence of dependent steps: throughput = (chains in flight) / (cycles per step), capped by
         // the issue slots.  Two families, chosen by that estimate (cycle counts measured on B200):
@@ -53,6 +51,16 @@ cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, bool lowt, i
             }
         }
     }
+    return G;
+}
+
+cudaError_t launch_philox(const PhiloxArgs &a, int lanes_per_chain, bool lowt, int smem_optin, int sm_count,
+                          cudaStream_t st, const char **why)
+{
+    *why = "";
+    const bool hist = (a.hist != nullptr && a.group_index != nullptr);
+    int G = lanes_per_chain;
+    if (G == 0) G = choose_philox_variant(a.L, a.algo, a.n_chains, hist, smem_optin, sm_count);
     if (G == 2 || G == 4 || G == 8 || G == 32) {
         if (a.L < 4 || (a.L & (a.L - 1))) { *why = "latency mode (lanes_per_chain 2/4/8/32) needs a power-of-two L >= 4"; return cudaErrorInvalidValue; }
         if (lat_smem_bytes(a.L, G, hist, smem_optin) == 0) { *why = "lattice too large for latency mode with this lanes_per_chain"; return cudaErrorInvalidValue; }
