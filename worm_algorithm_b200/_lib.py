@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libworm_b200.so")
+# WORM_B200_SO: another build of the same library (kernel A/B experiments, tools/build_variant.sh)
+SO_PATH = os.environ.get("WORM_B200_SO") or os.path.join(HERE, "libworm_b200.so")
 
 WORM_OK = 0
 ALGO_TAYLOR = 0
