@@ -149,6 +149,28 @@ def test_philox_matches_oracle(eng, algo, lanes, L, tmin):
     assert (st.group_acc.cpu().numpy() == gacc).all()
 
 
+def test_philox_nibble_solo_L64_matches_oracle(eng):
+    """L = 64 runs 32 chains per SM in the latency kernel's nibble layout with a solo walker (what lanes_per_chain = 0
+    picks for the Taylor chain): 70 chains = two full blocks and a ragged one, dumps and events, resumed once."""
+    from oracle import worm_oracle as wo
+    from worm_algorithm_b200 import _lib
+    n, L = 70, 64
+    assert _lib.philox_choice(L, 0, 4096, False) == 2
+    rng = np.random.default_rng(64)
+    T = rng.uniform(1.0, 3.5, n)
+    T[:5] = 2.269
+    seeds = rng.integers(0, 2 ** 63, n, dtype=np.uint64)
+    st = eng.PhiloxState(L, T, seeds, algo=0, chain_id0=9, max_dumps=5)
+    st.run(4001, therm_steps=500, dump_every=50, lanes_per_chain=2).run(9999, therm_steps=500, dump_every=50, lanes_per_chain=0)
+    acc, bonds = st.acc.cpu().numpy(), st.bonds.cpu().numpy()
+    for c in range(0, n, 3):
+        o = wo.run_philox(L, 0, 9 + c, int(seeds[c]), float(T[c]), 0, 14000, 500, dump_every=50, max_dumps=5)
+        assert (acc[c, :6] == o["acc"][:6]).all() and acc[c, 6] == 0 and (bonds[c] == o["bonds"]).all()
+        k = min(o["n_dumps"], 5)
+        assert int(st.n_dumps[c]) == o["n_dumps"] and (st.dumps[c, :k].cpu().numpy() == o["dumps"]).all()
+        assert (st.events[c, :k].cpu().numpy() == o["events"]).all()
+
+
 @pytest.mark.parametrize("algo", [0, 1])
 @pytest.mark.parametrize("L,n", [(8, 6007), (16, 80000), (32, 33152 + 4000), (64, 9000)])
 def test_philox_packed_big_batches(eng, algo, L, n):
@@ -174,6 +196,48 @@ def test_philox_packed_big_batches(eng, algo, L, n):
     for c in (0, 31, 32, n // 2, n - 1):
         o = wo.run_philox(L, algo, 7 + c, int(seeds[c]), float(T[c]), 0, steps, therm, hist=True, dump_every=50, max_dumps=3)
         assert (acc[c, :6] == o["acc"][:6]).all() and acc[c, 6] == 0 and (bonds[c] == o["bonds"]).all()
+
+
+@pytest.mark.parametrize("lanes", [2, 4, 8, 32])
+@pytest.mark.parametrize("L,tmin", [(4, 1.0), (8, 0.8), (16, 1.0), (32, 1.2)])
+def test_latency_kernel_nibble_layout_matches_oracle(eng, monkeypatch, L, tmin, lanes):
+    """The latency kernel's nibble layout (one byte per site, 1 / 4 / 8 chains per walker) is what large lattices
+    run on (L >= 64, tests below); pinned here on small ones so that every path -- both record builders, segment
+    edges, dumps, events, G(r), resumed launches -- is compared with the oracle chain by chain."""
+    from oracle import worm_oracle as wo
+    monkeypatch.setenv("WORM_LAT_LAYOUT", "nibble")
+    rng = np.random.default_rng(7 * L + lanes)
+    n = 45
+    T = rng.uniform(tmin, 3.5, n)
+    T[:6] = 2.269
+    seeds = rng.integers(0, 2 ** 63, n, dtype=np.uint64)
+    hidx = np.arange(n) % 3
+    steps, therm, cid0 = 2311, 390, 77
+    st = eng.PhiloxState(L, T, seeds, algo=0, chain_id0=cid0, group_index=hidx, n_groups=3, hist=True, max_dumps=9)
+    for ch in (1, 700, 33, steps - 734):
+        st.run(ch, therm_steps=therm, dump_every=50, lanes_per_chain=lanes)
+    acc, bonds = st.acc.cpu().numpy(), st.bonds.cpu().numpy()
+    head, tail, nd = st.head.cpu().numpy(), st.tail.cpu().numpy(), st.n_dumps.cpu().numpy()
+    ev, dm = st.events.cpu().numpy(), st.dumps.cpu().numpy()
+    hist = np.zeros((3, L * L), dtype=np.int64)
+    for c in range(n):
+        o = wo.run_philox(L, 0, cid0 + c, int(seeds[c]), float(T[c]), 0, steps, therm, hist=True, dump_every=50, max_dumps=9)
+        assert (acc[c, :6] == o["acc"][:6]).all() and acc[c, 6] == 0, (c, acc[c], o["acc"])
+        assert (bonds[c] == o["bonds"]).all() and head[c] == o["head"] and tail[c] == o["tail"]
+        assert nd[c] == o["n_dumps"]
+        k = min(o["n_dumps"], 9)
+        assert (ev[c, :k] == o["events"]).all() and (dm[c, :k] == o["dumps"]).all()
+        hist[hidx[c]] += o["hist"]
+    assert (st.hist.cpu().numpy() == hist).all()
+    # an input the layout cannot hold: reported, left untouched, the neighbours unaffected
+    st2 = eng.PhiloxState(L, T, seeds, algo=0, chain_id0=cid0)
+    st2.bonds[3, 5] = 16
+    st2.run(300, lanes_per_chain=lanes)
+    ref = eng.PhiloxState(L, T, seeds, algo=0, chain_id0=cid0).run(300, lanes_per_chain=1)
+    a2 = st2.acc.cpu().numpy()
+    keep = np.arange(n) != 3
+    assert a2[3, 6] == 1 and int(st2.bonds[3].sum()) == 16 and (a2[3, :6] == 0).all()
+    assert (a2[keep] == ref.acc.cpu().numpy()[keep]).all() and (st2.bonds.cpu().numpy()[keep] == ref.bonds.cpu().numpy()[keep]).all()
 
 
 def test_philox_packed_refuses_what_it_cannot_hold(eng):
@@ -414,7 +478,7 @@ def test_philox_segment_edges_match_oracle(eng, lanes):
 
 
 @pytest.mark.parametrize("L,lanes", [(64, 32), (128, 32), (256, 32), (64, 0), (128, 0), (256, 0), (64, 8), (64, 4),
-                                     (64, -2), (128, -2), (256, -2)])
+                                     (128, 8), (128, 4), (64, -2), (128, -2), (256, -2)])
 def test_philox_large_lattices_match_oracle(eng, L, lanes):
     """L = 64 (one chain per walker in the dual layout; three walkers of 4 chains or one of 8 for big
     batches), L = 128 (compact layout, four walkers of one chain) and L = 256 (compact, one chain per block).

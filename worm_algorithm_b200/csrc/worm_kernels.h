@@ -51,8 +51,10 @@ int choose_philox_variant(int L, int algo, int64_t n_chains, bool hist, int smem
 
 // the two kernels behind launch_philox.  G = lanes_per_chain of the C ABI (4 / 8 / 32 <-> 8 / 4 / 1
 // chains per walker warp of the latency kernel).
-size_t lat_smem_bytes(int L, int G, bool hist, int smem_optin);   // 0 if this L / G cannot run in latency mode
-int lat_chains_per_block(int L, int G, bool hist, int smem_optin);
+size_t lat_smem_bytes(int L, int G, int algo, bool hist, int smem_optin);   // 0 if this L / G cannot run in latency mode
+int lat_chains_per_block(int L, int G, int algo, bool hist, int smem_optin);
+// chains per block, walker groups per block and bond layout (0 dual, 1 byte per bond, 2 nibble) of a variant; false: cannot run
+bool lat_info(int L, int G, int algo, bool hist, int smem_optin, int *chains_per_block, int *walkers, int *layout);
 cudaError_t launch_philox_lat(const PhiloxArgs &a, int G, bool lowt, int smem_optin, cudaStream_t st);
 cudaError_t launch_philox_wide(const PhiloxArgs &a, bool force_global, int smem_optin, cudaStream_t st);
 // packed throughput kernel (worm_pack.cu): thread per chain, 4 bits (Taylor) / 1 bit (binary) per bond in shared memory

@@ -30,7 +30,11 @@
 // both of its sites, so the load address is head + constant (one IADD, no neighbour arithmetic in
 // front of the load), a chain only ever touches its own banks (no conflicts between the chains of
 // a warp), and an accepted move stores twice off the critical path.  Lattices whose dual layout
-// does not fit use the compact one-byte-per-bond layout (one chain per walker).
+// does not fit use the compact one-byte-per-bond layout (one chain per walker) or, for the Taylor chain, the
+// nibble layout: ONE BYTE PER SITE (+x occupation in the low nibble, +y in the high one; occupations 0..15, an
+// occupation that reaches 16 is reported in WORM_ACC_STATUS like in worm_pack.cu), bytes interleaved across the
+// 1 / 4 / 8 chains of a walker.  A quarter of the dual layout's bytes: 32 chains per SM at L = 64 instead of 12,
+// 12 at L = 128 instead of 4, 3 at L = 256 instead of 1 -- chains in flight are what bounds a large lattice.
 // Power-of-two L only: the head is a scaled site index whose x and y bit fields wrap by masking.
 //
 // Algorithm and random stream: oracle/worm_oracle.c:worm_oracle_philox_run (bit-for-bit), i.e. the
@@ -45,6 +49,8 @@ namespace worm {
 
 namespace {
 
+enum { LAY_DUAL = 0, LAY_BYTE = 1, LAY_NIB = 2 };
+
 struct LatGeo {
     int L, N, nb2;       // nb2 = 2N bonds per chain
     int nw;              // groups (walkers) per block
@@ -55,6 +61,7 @@ struct LatGeo {
     int log_off;         // byte offset of the step logs
     int hist_off;        // byte offset of the 16-bit G(r) bins (solo mode with histograms)
     int HXF, HYF;        // x / y bit fields of a displacement in bin-address format (solo mode with histograms)
+    int bad_off;         // nibble layout: byte offset of the per-chain "input does not fit 4 bits" flags
     int lowt;            // some chain has T < 1 (general record builder)
     int zero;            // 0 (a value the compiler cannot see through)
 };
@@ -142,7 +149,8 @@ struct LatState {
 // Observables are NOT accumulated by the walker (every instruction of its dependent chain costs
 // ~3 cycles of the step): it logs one byte per accepted step and one per closed step, and the
 // producer warp of the pair replays the log two rounds later (account_round below).
-//   accept log byte: 0x80 | (decrement ? 0x40 : 0) | (old occupation & 1);  0 = rejected
+//   accept log byte: 0x80 | (decrement ? 0x40 : 0) | (old occupation & 1, in bit 0 -- bit 4 when the occupation is
+//                    the high nibble of a site byte);  0 = rejected
 //   closed log byte: non-zero iff the worm was closed at the start of the step
 struct Account {
     int Nb, npar;                        // state at the start of the next round to be replayed (all lanes of a chain)
@@ -163,7 +171,7 @@ struct Account {
 //        the x field is bit 1 plus bits 7.. : a +x move fills the gap (bits 2..6) with ones so that the
 //        carry out of bit 1 reaches bit 7; a -x move borrows through the gap's zeros.
 // numf = float(kfix - 1) * (1 + 2^-18), rounded up (see the threshold computation below)
-template <int ALGO, bool DUAL, bool SH>
+template <int ALGO, int LAY, bool SH>
 __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &prm, const float numf, uint32_t a,
                                             uint32_t b, uint32_t chain_abs, uint4 &ra, uint4 &rb, uint4 &rc)
 {
@@ -173,12 +181,17 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
     const int add = neg ? -stepsz : stepsz;
     ra.x = (uint32_t)add;
     ra.y = ym ? ~(uint32_t)g.YM : ~(uint32_t)g.XM;
+    constexpr bool DUAL = (LAY == LAY_DUAL);
+    const uint32_t sh4 = (LAY == LAY_NIB && ym) ? 4u : 0u;      // nibble layout: the +y occupation is the high nibble
     if constexpr (DUAL) {
         ra.z = chain_abs + d;
         ra.w = chain_abs + (d ^ 2u);
-    } else {
+    } else if constexpr (LAY == LAY_BYTE) {
         ra.z = neg ? (uint32_t)add : 0u;
         ra.w = chain_abs + (uint32_t)ym;
+    } else {
+        ra.z = neg ? (uint32_t)add : 0u;
+        ra.w = chain_abs;                                        // the owner site's byte
     }
     if constexpr (SH) {
         const int hstep = ym ? g.L * 64 : 2;
@@ -200,18 +213,19 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
             const uint32_t q0 = __float2uint_rz(__fdividef(numf, __uint2float_rn(a)));
             const unsigned long long pq = (unsigned long long)q0 * (unsigned long long)a;
             const uint32_t q = q0 - (uint32_t)(pq > (unsigned long long)num);
-            qi = min(q, 255u);
+            qi = min(q, LAY == LAY_NIB ? 16u : 255u);            // (nibbles: 15 -> 16 is let through and caught at the end)
             qd = 1u;                                             // a < nb*tfix      <=>  nb >= 1
         } else {
             const unsigned long long num = prm.kfix - 1;
             const unsigned long long q1 = a ? num / (unsigned long long)a : 255ull;
             const unsigned long long q2 = (unsigned long long)a / (unsigned long long)prm.tfix + 1ull;   // nb > floor(a/tfix)
-            qi = (uint32_t)(q1 < 255ull ? q1 : 255ull);
-            qd = (uint32_t)(q2 < 256ull ? q2 : 256ull);
+            constexpr unsigned long long CAPI = (LAY == LAY_NIB) ? 16ull : 255ull, CAPD = (LAY == LAY_NIB) ? 16ull : 256ull;
+            qi = (uint32_t)(q1 < CAPI ? q1 : CAPI);
+            qd = (uint32_t)(q2 < CAPD ? q2 : CAPD);
         }
-        rb.y = dec ? qd : qi;
-        rb.z = dec ? 0xffffffffu : 1u;                           // occupation change; negative = flipped test
-        rb.w = dec ? 0xc0u : 0x80u;                              // accept-log bits
+        rb.y = (dec ? qd : qi) << sh4;
+        rb.z = dec ? (0u - (1u << sh4)) : (1u << sh4);           // occupation change (in place); negative = flipped test
+        rb.w = (dec ? 0xc0u : 0x80u) | ((LAY == LAY_NIB) ? ((15u << sh4) << 8) : 0u);   // accept-log bits | nibble mask
     } else {
         rb.y = ((uint64_t)a < prm.hfix) ? 0u : 1u;               // accept iff nb >= thr (occupied: always)
         rb.z = 0xffffffffu;
@@ -226,14 +240,15 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
 // gathered in two registers and stored as one 32-bit word each after every fourth step -- a lone warp issues
 // a shared-memory instruction every ~4 cycles, and the ones between the accept test and the next bond load
 // are on the head -> head recurrence.
-template <int ALGO, bool DUAL, int SCSH, bool HIST, bool SH, bool MEAS, int LOGK = -1>
+template <int ALGO, int LAY, int SCSH, bool HIST, bool SH, bool MEAS, int LOGK = -1>
 __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long hist_row, uint32_t hist_writer,
                                          LatState &c, const uint4 ra, const uint4 rb, const uint4 rc, const int kick_next,
                                          const uint32_t p_next, const uint32_t alog, const uint32_t clog, const uint32_t dummy = 0u)
 {
+    constexpr bool DUAL = (LAY == LAY_DUAL);
     const int add = (int)ra.x, keep = (int)ra.y;
     const int kick = (int)rb.x;
-    const uint32_t thr = rb.y, flip = rb.z, logbits = rb.w;
+    const uint32_t thr = rb.y, flip = rb.z, logbits = (LAY == LAY_NIB) ? (rb.w & 0xffu) : rb.w;
     const bool closed = c.closed != 0u;
     if constexpr (MEAS && HIST && !SH) {
         // G(r) bin of (head - tail) before the kick; a closed worm is bin 0
@@ -262,8 +277,11 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
         const int u = head + (int)ra.z;
         const int own = (head & keep) | (u & ~keep);
         addr = (uint32_t)own + ra.w;
-        nb = lds_u8(addr);                                      // :139
+        nb = lds_u8(addr);                                      // :139  (nibble layout: the site's byte, both occupations)
     }
+    // nibble layout: the occupation under test stays in place (masked), threshold and change come pre-shifted
+    const uint32_t whole = nb;
+    if constexpr (LAY == LAY_NIB) nb &= (rb.w >> 8);
     // Solo mode with histograms: G(r) bin of (head - tail) before the move; a closed worm is bin 0
     // (dh == 0).  The chain's 16-bit bins live in its own bank and only this lane touches them between
     // the walker's flushes, so the count is a plain load / add / store (a shared-memory atomic costs
@@ -291,8 +309,8 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
     // the first consumer of nb: the warp issues in order and stalls at that consumer, so everything
     // that does not depend on the load must sit in front of it (in the load's shadow), not behind
     const uint32_t thrx = thr + (uint32_t)(A ^ B ^ (int)addr2 ^ (int)dnew) * (uint32_t)g.zero;   // IMAD: the FMA pipe is the idle one
-    const uint32_t nn = (ALGO == ALGO_TAYLOR) ? nb + flip : (nb ^ 1u);
-    const uint32_t lg = (nb & 1u) | logbits;
+    const uint32_t nn = (ALGO == ALGO_TAYLOR) ? whole + flip : (nb ^ 1u);
+    const uint32_t lg = (nb & (LAY == LAY_NIB ? 0x11u : 1u)) | logbits;
     // accept test (:151), head select, bond stores (:152-154) and the accept-log byte in one opaque
     // block: the compiler must not re-associate "closed ? kick : ..." across the select.
     int head_new;
@@ -405,7 +423,7 @@ __device__ __forceinline__ void account_round(Account &k, uint32_t logbuf_abs, i
     for (int i = 0; i < SP; ++i) {
         const uint32_t al = (aw >> (8 * i)) & 0xffu;
         const int accd = (int)(al >> 7);
-        const int par = 1 - 2 * (int)(al & 1u);
+        const int par = (al & 0x11u) ? -1 : 1;                       // old parity: bit 0 (bit 4 for a high nibble)
         dn[i] = accd * par;
         dNb[i] = (ALGO == ALGO_TAYLOR) ? accd * (1 - (int)((al >> 5) & 2u)) : dn[i];
         sNb += dNb[i]; sn += dn[i];
@@ -478,16 +496,19 @@ __device__ __forceinline__ uint32_t dual_word(const uint8_t *gb, int s, int L, i
     return xy | ((uint32_t)gb[2 * left] << 16) | ((uint32_t)gb[2 * down + 1] << 24);
 }
 
-template <int ALGO, int CH, bool DUAL, bool HIST>
+template <int ALGO, int CH, int LAY, bool HIST>
 __global__ void __launch_bounds__(512, 1)
 worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
 {
+    constexpr bool DUAL = (LAY == LAY_DUAL);
+    constexpr bool NIB = (LAY == LAY_NIB);
     constexpr bool SH = HIST && CH == 32;               // per-chain G(r) bins in shared memory
     using Cfg = LatCfg<CH, SH>;
     constexpr int R = Cfg::R, NP = Cfg::NP;
-    constexpr int SC = DUAL ? 4 * CH : 2;
-    constexpr int SCSH = (SC == 2) ? 1 : (SC == 4) ? 2 : (SC == 16) ? 4 : (SC == 32) ? 5 : 7;
-    static_assert(DUAL || CH == 1, "the compact layout is one chain per walker");
+    constexpr int SC = DUAL ? 4 * CH : NIB ? CH : 2;    // bytes per unit of the scaled site index
+    constexpr int SCSH = (SC == 1) ? 0 : (SC == 2) ? 1 : (SC == 4) ? 2 : (SC == 8) ? 3 : (SC == 16) ? 4 : (SC == 32) ? 5 : 7;
+    static_assert(LAY != LAY_BYTE || CH == 1, "the byte-per-bond layout is one chain per walker");
+    static_assert(!NIB || ALGO == ALGO_TAYLOR, "nibble layout: Taylor chain only");
     extern __shared__ __align__(16) uint8_t smem8[];
     const int tid = threadIdx.x;
     const int nthreads = blockDim.x;
@@ -537,6 +558,22 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             const int64_t cg = chain0 + wk * CH + q;
             dst[i] = (cg < a.n_chains) ? dual_word<CH>(a.bonds + cg * (int64_t)g.nb2, s, g.L, g.N) : 0u;
         }
+    } else if constexpr (NIB) {
+        // byte (walker * N + s) * CH + q = occupations of site s of chain slot q: +x | +y << 4
+        uint8_t *bad = smem8 + g.bad_off;
+        for (int i = tid; i < bch; i += nthreads) bad[i] = 0;
+        __syncthreads();
+        const int total = bch * g.N;
+        for (int i = tid; i < total; i += nthreads) {
+            const int q = i % CH;
+            const int ws = i / CH;
+            const int wk = ws / g.N, s = ws - wk * g.N;
+            const int64_t cg = chain0 + wk * CH + q;
+            uint32_t xy = 0u;
+            if (cg < a.n_chains) xy = *reinterpret_cast<const uint16_t *>(a.bonds + cg * (int64_t)g.nb2 + 2 * s);
+            if (xy & 0xf0f0u) bad[wk * CH + q] = 1;              // an occupation above 15 does not fit
+            smem8[i] = (uint8_t)((xy & 15u) | ((xy >> 4) & 0xf0u));
+        }
     } else {
         const int vec_per_chain = g.nb2 / 16;
         const int total = bch * vec_per_chain;
@@ -579,7 +616,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         const PhiloxChain prm = a.prm[cl];
         const uint64_t chain_id = a.chain_id0 + (uint64_t)cl;
         const uint32_t c2 = (uint32_t)chain_id, c3 = (uint32_t)(chain_id >> 32);
-        const uint32_t chain_abs = region_abs + (DUAL ? (uint32_t)q * 4u : 0u);
+        const uint32_t chain_abs = region_abs + (DUAL ? (uint32_t)q * 4u : NIB ? (uint32_t)q : 0u);
         const uint32_t rec_q = rec_w + (uint32_t)q * 16u + (uint32_t)(Cfg::RPL == 2 ? 2 * p_of : b / CH) * (CH * 16);
         const PhiloxKeys keys = philox_keys((uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
         const float numf = __fmul_ru(__uint2float_ru((uint32_t)(prm.kfix - 1)), 1.0f + 1.0f / 262144.0f);
@@ -596,13 +633,13 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     const uint32_t p0 = rec_q + buf;
                     if constexpr (Cfg::RPL == 2) {
                         uint4 ra0, rb0, rc0, ra1, rb1, rc1;
-                        make_record<ALGO, DUAL, SH>(g, prm, numf, r.x, r.y, chain_abs, ra0, rb0, rc0);
-                        make_record<ALGO, DUAL, SH>(g, prm, numf, r.z, r.w, chain_abs, ra1, rb1, rc1);
+                        make_record<ALGO, LAY, SH>(g, prm, numf, r.x, r.y, chain_abs, ra0, rb0, rc0);
+                        make_record<ALGO, LAY, SH>(g, prm, numf, r.z, r.w, chain_abs, ra1, rb1, rc1);
                         sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0);
                         sts_v4(p0 + CH * 16, ra1); sts_v4(p0 + CH * 16 + Cfg::REC_B, rb1);
                     } else {
                         uint4 ra0, rb0, rc0;
-                        make_record<ALGO, DUAL, SH>(g, prm, numf, half ? r.z : r.x, half ? r.w : r.y, chain_abs, ra0, rb0, rc0);
+                        make_record<ALGO, LAY, SH>(g, prm, numf, half ? r.z : r.x, half ? r.w : r.y, chain_abs, ra0, rb0, rc0);
                         sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0); sts_v4(p0 + Cfg::REC_C, rc0);
                     }
                     group_barrier<Cfg::GW>(bar_id);
@@ -618,8 +655,15 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         // accountant identity of this lane: chain slot aq, part ap of that chain's steps
         const int aq = u * ACH + lane % ACH, ap = lane / ACH;
         const int64_t acg = chain0 + w * CH + aq;
-        const bool alive = acg < a.n_chains;
+        bool alive = acg < a.n_chains;
         const int64_t acl = alive ? acg : 0;
+        if constexpr (NIB) {
+            // a chain whose input does not fit 4 bits per bond is reported and left untouched
+            if (smem8[g.bad_off + w * CH + aq]) {
+                if (alive && ap == 0) a.acc[acl * ACC_STRIDE + ACC_STATUS] |= 1;
+                alive = false;
+            }
+        }
         Account k;
         k.Z = k.SNb = k.SNb2 = k.Sn = k.Sn2 = 0;
         int64_t *ac = a.acc + acl * ACC_STRIDE;
@@ -637,6 +681,12 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     const uint32_t v = lds_u32(region_abs + (uint32_t)((s * CH + aq) * 4)) & 0xffffu;
                     Nb += (int)__vsadu4(v, 0);
                     npar += __popc(v & 0x0101u);
+                }
+            } else if constexpr (NIB) {
+                for (int s = ap; s < g.N; s += Cfg::PARTS) {
+                    const uint32_t v = lds_u8(region_abs + (uint32_t)(s * CH + aq));
+                    Nb += (int)((v & 15u) + (v >> 4));
+                    npar += (int)((v & 1u) + ((v >> 4) & 1u));
                 }
             } else {
                 for (int i = ap; i < g.nb2 / 16; i += Cfg::PARTS) {
@@ -703,6 +753,18 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         group_barrier<Cfg::GW>(bar_id);                            // the walker has finished its last step
         if (pend[0].valid) account(pend[0]);
         if (pend[1].valid) account(pend[1]);
+        if constexpr (NIB) {
+            // an occupation that reached 16 carried out of its nibble: the sum over the chain's bytes has lost 16
+            // against the replayed sum of occupations
+            int sum = 0;
+            for (int s = ap; s < g.N; s += Cfg::PARTS) {
+                const uint32_t v = lds_u8(region_abs + (uint32_t)(s * CH + aq));
+                sum += (int)((v & 15u) + (v >> 4));
+            }
+#pragma unroll
+            for (int o = ACH; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (ap == 0 && alive && sum != k.Nb) a.acc[acl * ACC_STRIDE + ACC_STATUS] |= 2;
+        }
         // reduce the parts' shares and write the chain's record
 #pragma unroll
         for (int o = ACH; o < 32; o <<= 1) {
@@ -727,7 +789,8 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         constexpr unsigned wmask = (CH == 32) ? 0xffffffffu : ((1u << CH) - 1u);
         const int q = lane;                  // chain slot within the warp
         const int64_t cidx = chain0 + w * CH + q;
-        const bool live = cidx < a.n_chains;
+        bool live = cidx < a.n_chains;
+        if constexpr (NIB) live = live && smem8[g.bad_off + w * CH + q] == 0;   // a chain that does not fit is left untouched
         const int64_t cl = live ? cidx : 0;  // dead slots shadow chain 0 in their own shared-memory slot, never write
         uint32_t rec_q = rec_w + (uint32_t)q * 16u;
         uint32_t log_q = log_w + (uint32_t)(q * Cfg::LSTR);
@@ -806,7 +869,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
                 uint4 fc = make_uint4(0, 0, 0, 0);
                 if constexpr (SH) fc = lds_v4(nrec + Cfg::REC_C);
-                lat_step<ALGO, DUAL, SCSH, HIST, SH, MEAS, j % 4>(g, hist_row, hist_writer, c, p0a, p0b, p0c, (int)p1b.x, p1a.z,
+                lat_step<ALGO, LAY, SCSH, HIST, SH, MEAS, j % 4>(g, hist_row, hist_writer, c, p0a, p0b, p0c, (int)p1b.x, p1a.z,
                                                               lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j), pad);
                 p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
                 if constexpr (SH) { p0c = p1c; p1c = fc; }
@@ -826,7 +889,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 if constexpr (DUAL) pn = lds_u32(nrec + 8u);         // ra.z of the next step's record
                 uint4 xc = make_uint4(0, 0, 0, 0);
                 if constexpr (SH) xc = lds_v4(rec + Cfg::REC_C);
-                lat_step<ALGO, DUAL, SCSH, HIST, SH, MEAS>(g, hist_row, hist_writer, c, xa, xb, xc, (int)nb_.x, pn,
+                lat_step<ALGO, LAY, SCSH, HIST, SH, MEAS>(g, hist_row, hist_writer, c, xa, xb, xc, (int)nb_.x, pn,
                                                        lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j));
             }
         };
@@ -854,6 +917,12 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                         uint16_t *dst = reinterpret_cast<uint16_t *>(dstb);
                         for (int sI = lane; sI < g.N; sI += CH)
                             dst[sI] = (uint16_t)lds_u32(region_abs + (uint32_t)((sI * CH + src_lane) * 4));
+                    } else if constexpr (NIB) {
+                        uint16_t *dst = reinterpret_cast<uint16_t *>(dstb);
+                        for (int sI = lane; sI < g.N; sI += CH) {
+                            const uint32_t v = lds_u8(region_abs + (uint32_t)(sI * CH + src_lane));
+                            dst[sI] = (uint16_t)((v & 15u) | ((v >> 4) << 8));
+                        }
                     } else {
                         uint4 *dst = reinterpret_cast<uint4 *>(dstb);
                         for (int i = lane; i < g.nb2 / 16; i += CH) dst[i] = lds_v4(region_abs + (uint32_t)(i * 16));
@@ -935,6 +1004,18 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 if (cg < a.n_chains)
                     reinterpret_cast<uint16_t *>(a.bonds + cg * (int64_t)g.nb2)[s] = (uint16_t)src[i];
             }
+        } else if constexpr (NIB) {
+            const uint8_t *bad = smem8 + g.bad_off;
+            const int total = bch * g.N;
+            for (int i = tid - wb0; i < total; i += pthreads) {
+                const int q = i % CH;
+                const int ws = i / CH;
+                const int wk = ws / g.N, s = ws - wk * g.N;
+                const int64_t cg = chain0 + wk * CH + q;
+                const uint32_t v = smem8[i];
+                if (cg < a.n_chains && !bad[wk * CH + q])
+                    reinterpret_cast<uint16_t *>(a.bonds + cg * (int64_t)g.nb2)[s] = (uint16_t)((v & 15u) | ((v >> 4) << 8));
+            }
         } else {
             const int vec_per_chain = g.nb2 / 16;
             const int total = bch * vec_per_chain;
@@ -952,12 +1033,12 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
 // ---- launch geometry: layout, warps per block and shared memory for a lattice and CH chains per walker
 struct LatPlan {
     bool ok = false;
-    bool dual = false;
+    int lay = LAY_DUAL;
     LatGeo g{};
     size_t smem = 0;
 };
 
-LatPlan lat_plan(int L, int CH, bool hist, int smem_optin)
+LatPlan lat_plan(int L, int CH, int algo, bool hist, int smem_optin)
 {
     LatPlan p;
     if (L < 4 || (L & (L - 1)) || (CH != 32 && CH != 8 && CH != 4 && CH != 1)) return p;
@@ -969,29 +1050,34 @@ LatPlan lat_plan(int L, int CH, bool hist, int smem_optin)
     const size_t recw = (size_t)(sh ? 6 : 4) * R * CH * 16;
     const size_t logw = (size_t)3 * 2 * (R + 4) * CH;
     // Throughput = (chains in flight) / (cycles per step): of the (layout, walkers per block) pairs that
-    // fit, take the one with the most chains per block; the dual layout wins ties (fewer instructions in
-    // front of the bond load).  WORM_LAT_LAYOUT=dual|compact pins the layout (experiments).
+    // fit, take the one with the most chains per block; ties go to the layout with the fewest instructions in
+    // front of the bond load (dual, then byte per bond, then the nibble layout, which masks its occupation).
+    // WORM_LAT_LAYOUT=dual|byte|nibble pins the layout (experiments).
     const char *pin = getenv("WORM_LAT_LAYOUT");
     int best = 0;
-    for (int dual = 1; dual >= 0; --dual) {
-        if (!dual && CH != 1) continue;
-        if (pin && ((pin[0] == 'd') != (dual == 1))) continue;
-        const size_t region = dual ? (size_t)4 * N * CH : (size_t)2 * N;
+    for (int lay : {LAY_DUAL, LAY_BYTE, LAY_NIB}) {
+        if (lay == LAY_BYTE && CH != 1) continue;
+        if (lay == LAY_NIB && algo != ALGO_TAYLOR) continue;
+        if (pin && ((pin[0] == 'd') != (lay == LAY_DUAL) || (pin[0] == 'b') != (lay == LAY_BYTE) || (pin[0] == 'n') != (lay == LAY_NIB))) continue;
+        const size_t region = lay == LAY_DUAL ? (size_t)4 * N * CH : lay == LAY_BYTE ? (size_t)2 * N : (size_t)N * CH;
+        const int sc = lay == LAY_DUAL ? 4 * CH : lay == LAY_BYTE ? 2 : CH;
         for (int nw : {4, 3, 2, 1}) {
             if (CH == 32 && nw != 1) continue;
             if (nw * CH <= best) continue;
-            const size_t need = (nw * (region + recw + logw) + 15) / 16 * 16 + histb;
+            const size_t body = (nw * (region + recw + logw) + 15) / 16 * 16 + histb;
+            const size_t need = body + (lay == LAY_NIB ? (size_t)((nw * CH + 15) / 16 * 16) : 0);
             if (need + 1024 > (size_t)smem_optin) continue;
             best = nw * CH;
-            p.ok = true; p.dual = dual; p.smem = need;
+            p.ok = true; p.lay = lay; p.smem = need;
             p.g.L = L; p.g.N = N; p.g.nb2 = 2 * N; p.g.nw = nw;
-            p.g.SC = dual ? 4 * CH : 2;
+            p.g.SC = sc;
             p.g.XM = (L - 1) * p.g.SC;
             p.g.YM = (L - 1) * L * p.g.SC;
             p.g.region = (int)region;
             p.g.rec_off = (int)(nw * region);
             p.g.log_off = (int)(nw * (region + recw));
             p.g.hist_off = (int)((nw * (region + recw + logw) + 15) / 16 * 16);
+            p.g.bad_off = (int)body;
             p.g.HXF = 2 | ((L / 2 - 1) << 7);
             p.g.HYF = (L - 1) * L * 64;
             p.g.lowt = 0;
@@ -1001,10 +1087,10 @@ LatPlan lat_plan(int L, int CH, bool hist, int smem_optin)
     return p;
 }
 
-template <int ALGO, int CH, bool DUAL, bool HIST>
+template <int ALGO, int CH, int LAY, bool HIST>
 cudaError_t launch_lat(const PhiloxArgs &a, const LatPlan &p, cudaStream_t st)
 {
-    auto kern = worm_lat_kernel<ALGO, CH, DUAL, HIST>;
+    auto kern = worm_lat_kernel<ALGO, CH, LAY, HIST>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
     const int64_t bch = (int64_t)p.g.nw * CH;
@@ -1017,12 +1103,25 @@ cudaError_t launch_lat(const PhiloxArgs &a, const LatPlan &p, cudaStream_t st)
 template <int ALGO, bool HIST>
 cudaError_t launch_lat_ah(const PhiloxArgs &a, const LatPlan &p, int CH, cudaStream_t st)
 {
-    if (!p.dual) return launch_lat<ALGO, 1, false, HIST>(a, p, st);
+    if (p.lay == LAY_BYTE) return launch_lat<ALGO, 1, LAY_BYTE, HIST>(a, p, st);
+    if (p.lay == LAY_NIB) {
+        if constexpr (ALGO == ALGO_TAYLOR) {
+            switch (CH) {
+            case 32: return launch_lat<ALGO, 32, LAY_NIB, HIST>(a, p, st);
+            case 8: return launch_lat<ALGO, 8, LAY_NIB, HIST>(a, p, st);
+            case 4: return launch_lat<ALGO, 4, LAY_NIB, HIST>(a, p, st);
+            case 1: return launch_lat<ALGO, 1, LAY_NIB, HIST>(a, p, st);
+            default: return cudaErrorInvalidValue;
+            }
+        } else {
+            return cudaErrorInvalidValue;
+        }
+    }
     switch (CH) {
-    case 32: return launch_lat<ALGO, 32, true, HIST>(a, p, st);
-    case 8: return launch_lat<ALGO, 8, true, HIST>(a, p, st);
-    case 4: return launch_lat<ALGO, 4, true, HIST>(a, p, st);
-    case 1: return launch_lat<ALGO, 1, true, HIST>(a, p, st);
+    case 32: return launch_lat<ALGO, 32, LAY_DUAL, HIST>(a, p, st);
+    case 8: return launch_lat<ALGO, 8, LAY_DUAL, HIST>(a, p, st);
+    case 4: return launch_lat<ALGO, 4, LAY_DUAL, HIST>(a, p, st);
+    case 1: return launch_lat<ALGO, 1, LAY_DUAL, HIST>(a, p, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -1032,16 +1131,27 @@ cudaError_t launch_lat_ah(const PhiloxArgs &a, const LatPlan &p, int CH, cudaStr
 // G = lanes_per_chain of the C ABI: 2 / 4 / 8 / 32 <-> 32 / 8 / 4 / 1 chains per walker warp
 static int chains_per_walker(int G) { return G == 2 ? 32 : 32 / G; }
 
-int lat_chains_per_block(int L, int G, bool hist, int smem_optin)
+int lat_chains_per_block(int L, int G, int algo, bool hist, int smem_optin)
 {
-    const LatPlan p = lat_plan(L, chains_per_walker(G), hist, smem_optin);
+    const LatPlan p = lat_plan(L, chains_per_walker(G), algo, hist, smem_optin);
     return p.ok ? p.g.nw * chains_per_walker(G) : 0;
 }
 
-size_t lat_smem_bytes(int L, int G, bool hist, int smem_optin)
+bool lat_info(int L, int G, int algo, bool hist, int smem_optin, int *chains_per_block, int *walkers, int *layout)
+{
+    if (G != 2 && G != 4 && G != 8 && G != 32) return false;
+    const LatPlan p = lat_plan(L, chains_per_walker(G), algo, hist, smem_optin);
+    if (!p.ok) return false;
+    *chains_per_block = p.g.nw * chains_per_walker(G);
+    *walkers = p.g.nw;
+    *layout = p.lay;
+    return true;
+}
+
+size_t lat_smem_bytes(int L, int G, int algo, bool hist, int smem_optin)
 {
     if (G != 2 && G != 4 && G != 8 && G != 32) return 0;
-    const LatPlan p = lat_plan(L, chains_per_walker(G), hist, smem_optin);
+    const LatPlan p = lat_plan(L, chains_per_walker(G), algo, hist, smem_optin);
     return p.ok ? p.smem : 0;
 }
 
@@ -1049,7 +1159,7 @@ cudaError_t launch_philox_lat(const PhiloxArgs &a, int G, bool lowt, int smem_op
 {
     const bool hist = (a.hist != nullptr && a.group_index != nullptr);
     const int CH = chains_per_walker(G);
-    LatPlan p = lat_plan(a.L, CH, hist, smem_optin);
+    LatPlan p = lat_plan(a.L, CH, a.algo, hist, smem_optin);
     if (!p.ok) return cudaErrorInvalidValue;
     p.g.lowt = lowt ? 1 : 0;
     if (a.algo == ALGO_TAYLOR)

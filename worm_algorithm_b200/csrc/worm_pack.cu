@@ -46,6 +46,9 @@ struct PackGeo {
     int ksh;             // kick: scaled site = (b >> ksh) & kmask
     uint32_t kmask;
     uint32_t fold;       // steps between folds of the 32-bit partial sums (even)
+    uint32_t perm;       // block b walks chain group (b * perm) % gridDim.x: blocks resident together come from
+                         // all over the batch (all temperatures of a temperature-major batch at once, so the G(r)
+                         // atomics of a moment spread over all histogram rows instead of hammering one)
 };
 
 // Step table: 8 entries (direction, coin) of {add, field, own | y offset, occupation change}, each in eight
@@ -352,7 +355,8 @@ worm_pack_kernel(const PhiloxArgs a, const PackGeo g)
     const unsigned wmask = __ballot_sync(0xffffffffu, has_col);
     const int wlanes = wcols;
 
-    const int64_t cidx = (int64_t)blockIdx.x * g.CB + tid;
+    const int64_t grp = (int64_t)(((unsigned long long)blockIdx.x * g.perm) % gridDim.x);
+    const int64_t cidx = grp * g.CB + tid;
     const bool live = has_col && cidx < a.n_chains;
     const int64_t cl = live ? cidx : 0;          // dead lanes shadow chain 0 of the launch in their own column, never write
     const PhiloxChain prm = a.prm[cl];
@@ -645,6 +649,12 @@ PackPlan pack_plan(int L, int algo, int64_t n_chains, int smem_optin, int sm_cou
     p.smem = (p.smem + 15) & ~(size_t)15;
     if (p.smem > (size_t)smem_optin) { p.ok = false; return p; }
     p.blocks = (n_chains + cb - 1) / cb;
+    // a multiplier coprime to the number of blocks, near the golden section of it
+    auto gcd = [](int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; };
+    int64_t mul = (int64_t)((double)p.blocks * 0.6180339887) | 1;
+    while (mul > 1 && gcd(mul, p.blocks) != 1) mul -= 2;
+    if (mul < 1 || p.blocks < 4) mul = 1;
+    p.g.perm = (uint32_t)mul;
     return p;
 }
 
