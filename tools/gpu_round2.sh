@@ -1,0 +1,39 @@
+#!/bin/bash
+# Round-2 GPU-box visit: parity tests, smoke, bench (+ reference arm), launch list, ncu --set full per kernel family.
+set -x
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/smoke.log
+python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+tail -3 gpurun_out/bench.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
+NCU_CMD="python bench.py --steps 1 --warmup 3 --num-steps 200000 --no-cpu --e2e-steps 1"
+$NCU_CMD > gpurun_out/plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $NCU_CMD > gpurun_out/ncu_launches.log 2>&1
+$NCU_CMD > gpurun_out/plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:worm_lat -s 3 -c 1 -f -o gpurun_out/prof_worm $NCU_CMD > gpurun_out/ncu_full.log 2>&1
+# packed kernel, one wave of the L=32 sweep
+C1="python tools/pack_case.py 32 33152 20000 0 -2 0"
+$C1 > gpurun_out/plain_pack.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:worm_pack -s 1 -c 1 -f -o gpurun_out/prof_pack $C1 > gpurun_out/ncu_pack.log 2>&1
+# binary chain, bit-packed, 125000 chains
+C2="python tools/pack_case.py 32 125000 10000 1 -2 0"
+$C2 > gpurun_out/plain_packb.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:worm_pack -s 1 -c 1 -f -o gpurun_out/prof_packb $C2 > gpurun_out/ncu_packb.log 2>&1
+# latency kernel, nibble layout, L = 64
+C3="python tools/pack_case.py 64 4096 50000 0 0 0"
+$C3 > gpurun_out/plain_nib.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:worm_lat -s 1 -c 1 -f -o gpurun_out/prof_nib $C3 > gpurun_out/ncu_nib.log 2>&1
+# thread-per-chain byte kernel (non-power-of-two lattices)
+C4="python tools/pack_case.py 24 33152 5000 0 1 0"
+$C4 > gpurun_out/plain_wide.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:worm_wide -s 1 -c 1 -f -o gpurun_out/prof_wide $C4 > gpurun_out/ncu_wide.log 2>&1
+# post-processing kernels
+C5="python tools/ncu_post_case.py"
+$C5 > gpurun_out/plain_post.log 2>&1 &&
+ncu --set full --clock-control none -k regex:"image_kernel|block_kernel|count_kernel|pipeline_kernel|boundaries" -s 5 -c 5 -f -o gpurun_out/prof_post $C5 > gpurun_out/ncu_post.log 2>&1
+python tools/postproc_time.py > gpurun_out/postproc_time.log 2>&1
+python tools/pipeline_time.py > gpurun_out/pipeline_time.log 2>&1
+python tools/dump_time.py > gpurun_out/dump_time.log 2>&1
+ls -la gpurun_out | head -60
