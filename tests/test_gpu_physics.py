@@ -158,6 +158,23 @@ def test_product_fss_driver(eng):
     assert rows[0]["C_exact"] < rows[1]["C_exact"] < rows[2]["C_exact"]        # C(T_c) grows like ln L
 
 
+def test_multi_gpu_run_equals_single_gpu_run(eng):
+    """N-GPU result equality of the reduced accumulators.  Needs two visible GPUs (skipped on a
+    one-GPU box; `gpurun --gpus 2 -- python -m pytest tests -m gpu -k multi_gpu`): two ranks under torchrun shard the
+    chains of a sweep with G(r) histograms, all-reduce over NCCL, and rank 0 compares with its own single-rank run."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU visible")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(root, "tools", "multi_gpu_check.py")],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-1500:]
+    assert "identical to the single-rank run: True; result dicts identical: True" in p.stdout
+
+
 def test_correlation_function_G_r(eng):
     """G(r) histogram: bin 0 = Z, sum of bins = measured iterations (so sum G / G(0) = 1/Z_av = chi),
     G(1,0)/G(0) = <s0 s1> = -(E/N)/2 (Kaufman), and the x / y symmetry of the torus."""
