@@ -257,6 +257,8 @@ int worm_image_host(int L, int64_t n, const uint8_t *h_bonds, int32_t *h_img);
 int worm_block_host(int W, int64_t n, const int32_t *h_in, int32_t *h_out,
                     int double_bonds_value, int variant);
 int worm_count_host(int W, int64_t n, const int32_t *h_img, int64_t *h_count);
+/* h_counts i64 [n][levels]: worm_pipeline on host buffers (counts only) */
+int worm_pipeline_host(int L, int64_t n, const uint8_t *h_bonds, int levels, int64_t *h_counts);
 int worm_boundaries_host(int Nx, int Ny, int64_t n, const double *h_img, int m, const double *h_cutoffs,
                          int32_t *h_links);
 /* h_explained f64 [1 + num_blocks]; h_component f64 [d] or NULL */

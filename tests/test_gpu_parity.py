@@ -432,6 +432,12 @@ def test_host_entry_points(eng, ref_runs):
     cnt = np.zeros(1, dtype=np.int64)
     _lib.check(lib.worm_count_host(2 * L, 1, img.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)))
     assert cnt[0] == (bonds[0] & 1).sum()
+    pc = np.zeros((1, 3), dtype=np.int64)
+    _lib.check(lib.worm_pipeline_host(L, 1, bonds.ctypes.data_as(C.c_void_p), 3, pc.ctypes.data_as(C.c_void_p)))
+    lvl = img[0]
+    for k in range(3):
+        assert pc[0, k] == po.bond_counts(lvl.reshape(1, -1), lvl.shape[0])[0]
+        lvl = po.block_config(lvl.reshape(-1), 1, 0).reshape(lvl.shape[0] // 2, lvl.shape[0] // 2)
     # error path: bad argument -> status code + message, no exception from C
     rc = lib.worm_count_host(0, 1, img.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p))
     assert rc == -1 and "W" in _lib.last_error()

@@ -53,6 +53,7 @@ SIGNATURES = {
     "worm_sim_host": (C.c_int, [C.c_int, _i64, _pd, _pd, _pu64, _u64, _u64, C.c_int, C.c_int, _vp, _vp]),
     "worm_image_host": (C.c_int, [C.c_int, _i64, _vp, _vp]),
     "worm_block_host": (C.c_int, [C.c_int, _i64, _vp, _vp, C.c_int, C.c_int]),
+    "worm_pipeline_host": (C.c_int, [C.c_int, _i64, _vp, C.c_int, _vp]),
     "worm_count_host": (C.c_int, [C.c_int, _i64, _vp, _vp]),
     "worm_boundaries": (C.c_int, [C.c_int, C.c_int, _i64, _vp, C.c_int, _vp, _vp, _vp]),
     "worm_boundaries_host": (C.c_int, [C.c_int, C.c_int, _i64, _vp, C.c_int, _vp, _vp]),

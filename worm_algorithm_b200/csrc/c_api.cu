@@ -505,6 +505,23 @@ int worm_block_host(int W, int64_t n, const int32_t *h_in, int32_t *h_out, int d
     return WORM_OK;
 }
 
+int worm_pipeline_host(int L, int64_t n, const uint8_t *h_bonds, int levels, int64_t *h_counts)
+{
+    if (n < 0 || (n > 0 && (!h_bonds || !h_counts))) return fail(WORM_E_ARG, "bad n / null pointer");
+    if (n == 0) return WORM_OK;
+    DevInfo dev;
+    if (int rc = current_device_info(dev)) return rc;
+    const size_t in_b = (size_t)n * 2 * L * L, out_b = (size_t)n * (levels > 0 ? levels : 1) * sizeof(int64_t);
+    DevBuf in, out;
+    cudaError_t e;
+    if ((e = in.alloc(in_b)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = out.alloc(out_b)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMemcpy(in.p, h_bonds, in_b, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "H2D");
+    if (int rc = worm_pipeline(L, n, (const uint8_t *)in.p, levels, (int64_t *)out.p, nullptr, nullptr)) return rc;
+    if ((e = cudaMemcpy(h_counts, out.p, out_b, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "D2H");
+    return WORM_OK;
+}
+
 int worm_count_host(int W, int64_t n, const int32_t *h_img, int64_t *h_count)
 {
     if (n <= 0 || !h_img || !h_count) return fail(WORM_E_ARG, "bad n / null pointer");

@@ -377,15 +377,15 @@ pipeline_kernel(int L, int64_t n, const uint8_t *__restrict__ bonds, int levels,
             for (int i = lane; i < 2 * lvl0_words; i += 32) buf[i] = 0u;      // rows are padded to a word
             __syncwarp();
         }
-        // 16 occupation bytes = 8 sites = 8 X parities + 8 Y parities
+        // 16 occupation bytes = 8 sites = 8 X parities (bytes 0, 2 of each word) + 8 Y parities (bytes 1, 3).
+        // Each word's two X bits sit at bits 0 / 16 and its Y bits at bits 8 / 24: the four words are merged with
+        // shifts of 2 (one IMAD each), then one fold by 15 brings the odd-site bits next to the even-site ones.
         for (int i = lane; i < nb2 / 16; i += 32) {
             const uint4 v = src[i];
-            const uint32_t m0 = ((v.x & 0x01010101u) * 0x01020408u) >> 24;    // [X s, Y s, X s+1, Y s+1]
-            const uint32_t m1 = ((v.y & 0x01010101u) * 0x01020408u) >> 24;
-            const uint32_t m2 = ((v.z & 0x01010101u) * 0x01020408u) >> 24;
-            const uint32_t m3 = ((v.w & 0x01010101u) * 0x01020408u) >> 24;
-            const uint32_t m = (m0 & 15u) | ((m1 & 15u) << 4) | ((m2 & 15u) << 8) | ((m3 & 15u) << 12);
-            const uint32_t xs = squeeze_even(m), ys = squeeze_even(m >> 1);  // 8 bits each
+            const uint32_t a0 = v.x & 0x01010101u, a1 = v.y & 0x01010101u, a2 = v.z & 0x01010101u, a3 = v.w & 0x01010101u;
+            const uint32_t m = a0 + a1 * 4u + a2 * 16u + a3 * 64u;            // bits 2k (+16): X of site pair k; bits 2k + 8 (+16): Y
+            const uint32_t f = m | (m >> 15);                                   // bit 2k + 1 <- bit 2k + 16 (the odd site of the pair)
+            const uint32_t xs = f & 0xffu, ys = (f >> 8) & 0xffu;
             if (L >= 8) {
                 const int s0 = 8 * i, y = s0 / L, x0 = s0 - y * L;
                 Xb[y * wpr0 * 4 + (x0 >> 3)] = (uint8_t)xs;
