@@ -156,6 +156,8 @@ struct Account {
     int Nb, npar;                        // state at the start of the next round to be replayed (all lanes of a chain)
     uint64_t Z, SNb, SNb2, Sn, Sn2;      // this lane's share of the sums
     int32_t nd;                          // dump events seen (mirrors the walker's counter)
+    int dx, dy;                          // G(r): head - tail (mod L) at the start of the next round to be replayed
+    unsigned long long *hrow;            // G(r): the chain's row of the int64 histogram (null: do not count)
 };
 
 // A step record: everything about step s that does not depend on the chain's state.
@@ -225,11 +227,11 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
         }
         rb.y = (dec ? qd : qi) << sh4;
         rb.z = dec ? (0u - (1u << sh4)) : (1u << sh4);           // occupation change (in place); negative = flipped test
-        rb.w = (dec ? 0xc0u : 0x80u) | ((LAY == LAY_NIB) ? ((15u << sh4) << 8) : 0u);   // accept-log bits | nibble mask
+        rb.w = (dec ? 0xc0u : 0x80u) | (d << 2) | ((LAY == LAY_NIB) ? ((15u << sh4) << 8) : 0u);   // accept-log bits (accepted, decrement, direction) | nibble mask
     } else {
         rb.y = ((uint64_t)a < prm.hfix) ? 0u : 1u;               // accept iff nb >= thr (occupied: always)
         rb.z = 0xffffffffu;
-        rb.w = 0x80u;
+        rb.w = 0x80u | (d << 2);
     }
 }
 
@@ -397,8 +399,13 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
 // Replay of one round's log by the producer warp: lane (q, part) owns steps [part*SP, part*SP+SP) of
 // chain slot q.  Occupation-sum / parity-count changes are prefix-summed across the parts, then
 // every lane measures its closed steps (:130-132) with the exact Nb / n of that step.
-template <int ALGO, int CH, bool SH>
-__device__ __forceinline__ void account_round(Account &k, uint32_t logbuf_abs, int q, int part, bool meas)
+// HIST: the accountants also keep G(r).  The accept-log byte carries the direction of the move (bits 2-3, from the
+// step record), so the displacement head - tail can be replayed exactly like Nb: it changes on accepted moves
+// only (a kick moves head and tail together; a worm that closes has walked its displacement back to 0 mod L).
+// Every measured iteration counts at the displacement it starts with; a lane merges the iterations of its steps
+// that share a bin and adds them with one `red` -- the walker does nothing for the histogram.
+template <int ALGO, int CH, bool SH, bool HIST>
+__device__ __forceinline__ void account_round(Account &k, uint32_t logbuf_abs, int q, int part, bool meas, int jb, int je, int L, int lgL)
 {
     using Cfg = LatCfg<CH, SH>;
     constexpr int SP = Cfg::SP, PARTS = Cfg::PARTS, ACH = Cfg::ACH;
@@ -453,6 +460,50 @@ __device__ __forceinline__ void account_round(Account &k, uint32_t logbuf_abs, i
             Nb += dNb[i]; npar += dn[i];
         }
     }
+    if constexpr (HIST) {
+        // displacement changes of this lane's steps, packed (dx in the low half, dy in the high half: sums of +-1
+        // over a round cannot reach the other half)
+        int pd[SP];
+        int spd = 0;
+#pragma unroll
+        for (int i = 0; i < SP; ++i) {
+            const uint32_t al = (aw >> (8 * i)) & 0xffu;
+            const int dir = (int)((al >> 2) & 3u);
+            const int unit = (dir & 1) ? 65536 : 1;
+            pd[i] = (al >> 7) ? ((dir & 2) ? -unit : unit) : 0;
+            spd += pd[i];
+        }
+        int ppd = spd;
+#pragma unroll
+        for (int o = ACH; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, ppd, o);
+            if (part * ACH >= o) ppd += u;
+        }
+        int off = ppd - spd;                                      // displacement change before this lane's first step
+        const int tot = __shfl_sync(0xffffffffu, ppd, last);
+        if (meas && k.hrow) {
+            const int mask = L - 1;
+            int cur = -1, cnt = 0;
+#pragma unroll
+            for (int i = 0; i < SP; ++i) {
+                const int j = part * SP + i;
+                if (j >= jb && j < je) {
+                    const int x = (k.dx + (int)(short)(off & 0xffff)) & mask;
+                    const int y = (k.dy + ((off + 0x8000) >> 16)) & mask;
+                    const int bin = (y << lgL) | x;               // hist[dy * L + dx], taken before the kick
+                    if (bin == cur) ++cnt;
+                    else {
+                        if (cnt) atomicAdd(k.hrow + cur, (unsigned long long)cnt);
+                        cur = bin; cnt = 1;
+                    }
+                }
+                off += pd[i];
+            }
+            if (cnt) atomicAdd(k.hrow + cur, (unsigned long long)cnt);
+        }
+        k.dx = (k.dx + (int)(short)(tot & 0xffff)) & (L - 1);
+        k.dy = (k.dy + ((tot + 0x8000) >> 16)) & (L - 1);
+    }
 }
 
 // The round schedule every role follows: rounds start on a Philox pair, never straddle a segment
@@ -496,13 +547,18 @@ __device__ __forceinline__ uint32_t dual_word(const uint8_t *gb, int s, int L, i
     return xy | ((uint32_t)gb[2 * left] << 16) | ((uint32_t)gb[2 * down + 1] << 24);
 }
 
-template <int ALGO, int CH, int LAY, bool HIST>
+// HMODE: G(r) histograms -- 0 none; 1 the solo walker counts in 16-bit per-chain bins in shared memory (needs
+// 2 N bytes per chain: L <= 32); 2 the accountants replay the displacement from the logged directions and add
+// runs of equal bins with `red.global` (any lattice, no walker work, but bounded by the L2's atomic rate).
+template <int ALGO, int CH, int LAY, int HMODE>
 __global__ void __launch_bounds__(512, 1)
 worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
 {
+    constexpr bool HIST = (HMODE == 2);                 // accountant histograms
     constexpr bool DUAL = (LAY == LAY_DUAL);
     constexpr bool NIB = (LAY == LAY_NIB);
-    constexpr bool SH = HIST && CH == 32;               // per-chain G(r) bins in shared memory
+    constexpr bool SH = (HMODE == 1);                   // per-chain G(r) bins in shared memory, counted by the walker
+    static_assert(!SH || CH == 32, "walker-side histograms are a solo-mode feature");
     using Cfg = LatCfg<CH, SH>;
     constexpr int R = Cfg::R, NP = Cfg::NP;
     constexpr int SC = DUAL ? 4 * CH : NIB ? CH : 2;    // bytes per unit of the scaled site index
@@ -674,6 +730,17 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             k.Z = old[0]; k.SNb = old[1]; k.SNb2 = old[2]; k.Sn = old[3]; k.Sn2 = old[4];
         }
         k.nd = (a.n_dumps && alive) ? a.n_dumps[acl] : 0;
+        k.dx = k.dy = 0;
+        k.hrow = nullptr;
+        int lgL = 0;
+        while ((1 << lgL) < g.L) ++lgL;
+        if constexpr (HIST) {
+            const int hs = a.head[acl], ts = a.tail[acl];
+            k.dx = (hs - ts) & (g.L - 1);
+            k.dy = ((hs >> lgL) - (ts >> lgL)) & (g.L - 1);
+            if (alive && a.hist && a.group_index)
+                k.hrow = reinterpret_cast<unsigned long long *>(a.hist + (int64_t)a.group_index[acl] * g.N);
+        }
         {   // occupation sum / odd-bond count of the staged configuration: the chain's parts share the sites
             int Nb = 0, npar = 0;
             if constexpr (DUAL) {
@@ -704,8 +771,8 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             k.Nb = Nb; k.npar = npar;
         }
         // replay of a finished round: dump event first (values before the round's first step), then the log
-        struct Pending { uint64_t s; int jb; bool meas, dump_first, valid; };
-        Pending pend[2] = {{0, 0, false, false, false}, {0, 0, false, false, false}};
+        struct Pending { uint64_t s; int jb, je; bool meas, dump_first, valid; };
+        Pending pend[2] = {{0, 0, 0, false, false, false}, {0, 0, 0, false, false, false}};
         uint32_t lbuf_acc = 0u;                          // log buffer of the oldest pending round
         auto account = [&](const Pending &pr) {
             const uint32_t lb = log_w + lbuf_acc;
@@ -725,7 +792,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     ++k.nd;
                 }
             }
-            account_round<ALGO, CH, SH>(k, lb, aq, ap, pr.meas);
+            account_round<ALGO, CH, SH, HIST>(k, lb, aq, ap, pr.meas, pr.jb, pr.je, g.L, lgL);
             lbuf_acc = (lbuf_acc == 2u * Cfg::LOGB) ? 0u : lbuf_acc + (uint32_t)Cfg::LOGB;
         };
 
@@ -742,7 +809,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     // the walker is now inside the previous round: the one before that is complete
                     if (pend[0].valid) account(pend[0]);
                     pend[0] = pend[1];
-                    pend[1] = Pending{sr, kk ? 0 : bt.jb, meas, dump_first && seg_first, true};
+                    pend[1] = Pending{sr, kk ? 0 : bt.jb, kk ? R : bt.je, meas, dump_first && seg_first, true};
                     seg_first = false;
                     sr = bt.s0 + (uint64_t)(kk + 1) * (uint64_t)R;
                 }
@@ -798,7 +865,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         unsigned long long hist_row = 0ull;
         unsigned long long *hist_out = nullptr;         // SH: this chain's row of the int64 histogram in HBM
         uint32_t hist_writer = 0u;
-        if constexpr (HIST) {
+        if constexpr (SH) {
             // SH: every slot, live or not, has its own bank of bins in shared memory (adds of 0 go there too):
             // bins 2i, 2i+1 of slot q are the halves of word i * 32 + q
             if constexpr (SH) hist_row = (unsigned long long)(sbase + (uint32_t)g.hist_off + (uint32_t)(q * 4));
@@ -869,7 +936,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
                 uint4 fc = make_uint4(0, 0, 0, 0);
                 if constexpr (SH) fc = lds_v4(nrec + Cfg::REC_C);
-                lat_step<ALGO, LAY, SCSH, HIST, SH, MEAS, j % 4>(g, hist_row, hist_writer, c, p0a, p0b, p0c, (int)p1b.x, p1a.z,
+                lat_step<ALGO, LAY, SCSH, SH, SH, MEAS, j % 4>(g, hist_row, hist_writer, c, p0a, p0b, p0c, (int)p1b.x, p1a.z,
                                                               lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j), pad);
                 p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
                 if constexpr (SH) { p0c = p1c; p1c = fc; }
@@ -889,7 +956,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 if constexpr (DUAL) pn = lds_u32(nrec + 8u);         // ra.z of the next step's record
                 uint4 xc = make_uint4(0, 0, 0, 0);
                 if constexpr (SH) xc = lds_v4(rec + Cfg::REC_C);
-                lat_step<ALGO, LAY, SCSH, HIST, SH, MEAS>(g, hist_row, hist_writer, c, xa, xb, xc, (int)nb_.x, pn,
+                lat_step<ALGO, LAY, SCSH, SH, SH, MEAS>(g, hist_row, hist_writer, c, xa, xb, xc, (int)nb_.x, pn,
                                                        lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j));
             }
         };
@@ -1033,17 +1100,32 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
 // ---- launch geometry: layout, warps per block and shared memory for a lattice and CH chains per walker
 struct LatPlan {
     bool ok = false;
+    int hmode = 0;
     int lay = LAY_DUAL;
     LatGeo g{};
     size_t smem = 0;
 };
 
+LatPlan lat_plan_mode(int L, int CH, int algo, bool sh, int smem_optin);
+
 LatPlan lat_plan(int L, int CH, int algo, bool hist, int smem_optin)
+{
+    // G(r): walker-side bins in shared memory when they fit next to the solo walker's bonds (fewer cycles per step
+    // than the accountants' atomics), else the accountants
+    if (hist && CH == 32) {
+        LatPlan p = lat_plan_mode(L, CH, algo, true, smem_optin);
+        if (p.ok) { p.hmode = 1; return p; }
+    }
+    LatPlan p = lat_plan_mode(L, CH, algo, false, smem_optin);
+    p.hmode = hist ? 2 : 0;
+    return p;
+}
+
+LatPlan lat_plan_mode(int L, int CH, int algo, bool sh, int smem_optin)
 {
     LatPlan p;
     if (L < 4 || (L & (L - 1)) || (CH != 32 && CH != 8 && CH != 4 && CH != 1)) return p;
     const int N = L * L;
-    const bool sh = hist && CH == 32;                    // 16-bit G(r) bins in shared memory
     const int NP = (CH == 32) ? 8 : (CH == 8) ? 2 : 1;
     const int R = 32 * NP * (sh ? 1 : 2) / CH;
     const size_t histb = sh ? (size_t)CH * N * 2 : 0;
@@ -1087,10 +1169,10 @@ LatPlan lat_plan(int L, int CH, int algo, bool hist, int smem_optin)
     return p;
 }
 
-template <int ALGO, int CH, int LAY, bool HIST>
+template <int ALGO, int CH, int LAY, int HMODE>
 cudaError_t launch_lat(const PhiloxArgs &a, const LatPlan &p, cudaStream_t st)
 {
-    auto kern = worm_lat_kernel<ALGO, CH, LAY, HIST>;
+    auto kern = worm_lat_kernel<ALGO, CH, LAY, HMODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
     const int64_t bch = (int64_t)p.g.nw * CH;
@@ -1100,17 +1182,26 @@ cudaError_t launch_lat(const PhiloxArgs &a, const LatPlan &p, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <int ALGO, bool HIST>
-cudaError_t launch_lat_ah(const PhiloxArgs &a, const LatPlan &p, int CH, cudaStream_t st)
+template <int ALGO, int CH, int LAY>
+cudaError_t launch_lat_h(const PhiloxArgs &a, const LatPlan &p, cudaStream_t st)
 {
-    if (p.lay == LAY_BYTE) return launch_lat<ALGO, 1, LAY_BYTE, HIST>(a, p, st);
+    if (p.hmode == 0) return launch_lat<ALGO, CH, LAY, 0>(a, p, st);
+    if (p.hmode == 2) return launch_lat<ALGO, CH, LAY, 2>(a, p, st);
+    if constexpr (CH == 32) return launch_lat<ALGO, CH, LAY, 1>(a, p, st);
+    return cudaErrorInvalidValue;
+}
+
+template <int ALGO>
+cudaError_t launch_lat_a(const PhiloxArgs &a, const LatPlan &p, int CH, cudaStream_t st)
+{
+    if (p.lay == LAY_BYTE) return launch_lat_h<ALGO, 1, LAY_BYTE>(a, p, st);
     if (p.lay == LAY_NIB) {
         if constexpr (ALGO == ALGO_TAYLOR) {
             switch (CH) {
-            case 32: return launch_lat<ALGO, 32, LAY_NIB, HIST>(a, p, st);
-            case 8: return launch_lat<ALGO, 8, LAY_NIB, HIST>(a, p, st);
-            case 4: return launch_lat<ALGO, 4, LAY_NIB, HIST>(a, p, st);
-            case 1: return launch_lat<ALGO, 1, LAY_NIB, HIST>(a, p, st);
+            case 32: return launch_lat_h<ALGO, 32, LAY_NIB>(a, p, st);
+            case 8: return launch_lat_h<ALGO, 8, LAY_NIB>(a, p, st);
+            case 4: return launch_lat_h<ALGO, 4, LAY_NIB>(a, p, st);
+            case 1: return launch_lat_h<ALGO, 1, LAY_NIB>(a, p, st);
             default: return cudaErrorInvalidValue;
             }
         } else {
@@ -1118,10 +1209,10 @@ cudaError_t launch_lat_ah(const PhiloxArgs &a, const LatPlan &p, int CH, cudaStr
         }
     }
     switch (CH) {
-    case 32: return launch_lat<ALGO, 32, LAY_DUAL, HIST>(a, p, st);
-    case 8: return launch_lat<ALGO, 8, LAY_DUAL, HIST>(a, p, st);
-    case 4: return launch_lat<ALGO, 4, LAY_DUAL, HIST>(a, p, st);
-    case 1: return launch_lat<ALGO, 1, LAY_DUAL, HIST>(a, p, st);
+    case 32: return launch_lat_h<ALGO, 32, LAY_DUAL>(a, p, st);
+    case 8: return launch_lat_h<ALGO, 8, LAY_DUAL>(a, p, st);
+    case 4: return launch_lat_h<ALGO, 4, LAY_DUAL>(a, p, st);
+    case 1: return launch_lat_h<ALGO, 1, LAY_DUAL>(a, p, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -1162,9 +1253,8 @@ cudaError_t launch_philox_lat(const PhiloxArgs &a, int G, bool lowt, int smem_op
     LatPlan p = lat_plan(a.L, CH, a.algo, hist, smem_optin);
     if (!p.ok) return cudaErrorInvalidValue;
     p.g.lowt = lowt ? 1 : 0;
-    if (a.algo == ALGO_TAYLOR)
-        return hist ? launch_lat_ah<ALGO_TAYLOR, true>(a, p, CH, st) : launch_lat_ah<ALGO_TAYLOR, false>(a, p, CH, st);
-    return hist ? launch_lat_ah<ALGO_BINARY, true>(a, p, CH, st) : launch_lat_ah<ALGO_BINARY, false>(a, p, CH, st);
+    if (a.algo == ALGO_TAYLOR) return launch_lat_a<ALGO_TAYLOR>(a, p, CH, st);
+    return launch_lat_a<ALGO_BINARY>(a, p, CH, st);
 }
 
 }  // namespace worm
