@@ -482,24 +482,31 @@ __device__ __forceinline__ void account_round(Account &k, uint32_t logbuf_abs, i
         int off = ppd - spd;                                      // displacement change before this lane's first step
         const int tot = __shfl_sync(0xffffffffu, ppd, last);
         if (meas && k.hrow) {
+            // Branch-free: a run starts at a valid step that is the lane's first, or follows an accepted move or an
+            // invalid step; its length is the number of valid steps up to the next accepted move.  One predicated
+            // `red` per possible run start.
             const int mask = L - 1;
-            int cur = -1, cnt = 0;
+            bool v[SP], ac[SP];
+            int len[SP + 1];
+            len[SP] = 0;
 #pragma unroll
             for (int i = 0; i < SP; ++i) {
                 const int j = part * SP + i;
-                if (j >= jb && j < je) {
+                v[i] = (j >= jb) && (j < je);
+                ac[i] = ((aw >> (8 * i + 7)) & 1u) != 0u;
+            }
+#pragma unroll
+            for (int i = SP - 1; i >= 0; --i) len[i] = v[i] ? 1 + (ac[i] ? 0 : len[i + 1]) : 0;
+#pragma unroll
+            for (int i = 0; i < SP; ++i) {
+                const bool start = v[i] && (i == 0 || ac[i - 1] || !v[i - 1]);
+                if (start) {
                     const int x = (k.dx + (int)(short)(off & 0xffff)) & mask;
                     const int y = (k.dy + ((off + 0x8000) >> 16)) & mask;
-                    const int bin = (y << lgL) | x;               // hist[dy * L + dx], taken before the kick
-                    if (bin == cur) ++cnt;
-                    else {
-                        if (cnt) atomicAdd(k.hrow + cur, (unsigned long long)cnt);
-                        cur = bin; cnt = 1;
-                    }
+                    atomicAdd(k.hrow + ((y << lgL) | x), (unsigned long long)len[i]);      // hist[dy * L + dx], before the kick
                 }
                 off += pd[i];
             }
-            if (cnt) atomicAdd(k.hrow + cur, (unsigned long long)cnt);
         }
         k.dx = (k.dx + (int)(short)(tot & 0xffff)) & (L - 1);
         k.dy = (k.dy + ((tot + 0x8000) >> 16)) & (L - 1);
@@ -1112,7 +1119,8 @@ LatPlan lat_plan(int L, int CH, int algo, bool hist, int smem_optin)
 {
     // G(r): walker-side bins in shared memory when they fit next to the solo walker's bonds (fewer cycles per step
     // than the accountants' atomics), else the accountants
-    if (hist && CH == 32) {
+    const char *hm = getenv("WORM_LAT_HMODE");          // "2": accountants even where the walker-side bins fit (experiments)
+    if (hist && CH == 32 && !(hm && hm[0] == '2')) {
         LatPlan p = lat_plan_mode(L, CH, algo, true, smem_optin);
         if (p.ok) { p.hmode = 1; return p; }
     }
