@@ -23,6 +23,8 @@ Numbers:
   roofline_packed the same issue roofline for the packed throughput kernel (worm_pack_kernel) on 125 000 L=32 chains.
   lattice_shapes  the other lattice shapes / batch sizes BASELINE.json names, with the kernel variant chosen for each.
   c5              BASELINE configs[4]: 1e6 L=32 chains with G(r) histograms over the N ranks, one all-reduce.
+  c3, c4          BASELINE configs[2] end to end (L = 64 / 128 near T_c, dump rule on, dumps through the fused kernel) and
+                  configs[3] as a quick finite-size-scaling pass against Kaufman (z-scores).
   pipeline_c3     4096 L=64 dumps -> images -> blocking levels -> counts: the fused one-launch kernel and the
                   12-launch chain on the device (configs/s) + the numpy port.
   roofline_pca    tensor roofline of the PCA Gram kernel (int8 tcgen05) + stage times + sklearn CPU baseline.
@@ -371,6 +373,8 @@ def run_b200_arm(a) -> None:
     roofline_blocking = bench_blocking(torch, engine, dev, peaks)
     roofline_pca = bench_pca(torch, engine, dev, peaks, cpu=(world == 1 and not a.no_cpu))
     pipeline_c3 = bench_pipeline(torch, engine, dev, peaks, cpu=(world == 1 and not a.no_cpu))
+    c3 = bench_c3(torch, engine, dev)
+    c4 = bench_c4(dev)
     cpu = None
     if world == 1 and not a.no_cpu:
         cores = host_cores()
@@ -397,6 +401,8 @@ def run_b200_arm(a) -> None:
         "roofline_blocking": roofline_blocking,
         "roofline_pca": roofline_pca,
         "pipeline_c3": pipeline_c3,
+        "c3": c3,
+        "c4": c4,
         "cpu_baseline": cpu,
         "check": {"multi_gpu_equal": multi_equal,
                   "multi_gpu_equal_what": "64 chains owned by rank %d, 1e5 steps: per-chain sums all-gathered to rank 0 == "
@@ -477,6 +483,48 @@ def bench_packed(torch, engine, dev, algo, issue_peak, f_max) -> dict:
             "worm_steps_per_s": rate, "one_wave": {"chains": 148 * 224, "worm_steps_per_s": rate1, "frac": rate1 * I_ALG / issue_peak,
                                                    "cycles_per_step_per_chain": f_max * 148 * 224 / rate1},
             "alg_instr_per_worm_step": I_ALG, "executed": executed, "traffic": (executed or {}).get("dram_bytes_per_launch")}
+
+
+def bench_c3(torch, engine, dev) -> list:
+    """BASELINE configs[2] end to end on the device: L = 64 and 128 at the reference's critical temperature grid with
+    the dump rule of worm_ising_2d.cpp:113-125 (every 50 steps, first 32 dumps per chain kept), then every dump through
+    the fused image -> blocking levels -> count kernel.  Simulation and post-processing timed separately."""
+    out = []
+    temps = np.array([2.21, 2.22, 2.23, 2.24, 2.26, 2.27, 2.28, 2.269])
+    for L, reps, steps in ((64, 512, 400_000), (128, 128, 800_000)):
+        n = temps.size * reps
+        t_idx = np.repeat(np.arange(temps.size), reps)
+        T = temps[t_idx]
+        seeds = (np.arange(n) % reps).astype(np.uint64)
+        md = 32
+        st = engine.PhiloxState(L, T, seeds, algo=engine.ALGO_TAYLOR, device=dev, group_index=t_idx, n_groups=temps.size, max_dumps=md)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        torch.cuda.synchronize(dev)
+        e0.record()
+        st.run(steps, therm_steps=steps // 10, dump_every=50)
+        e1.record()
+        counts = engine.pipeline(st.dumps.reshape(n * md, 2 * L * L), L)
+        e2.record()
+        torch.cuda.synchronize(dev)
+        nd = st.n_dumps.clamp(max=md)
+        kept = int(nd.sum().item())
+        valid = (torch.arange(md, device=dev)[None, :] < nd[:, None]).reshape(-1)
+        c0 = counts[valid][:, 0].double()
+        out.append({"L": L, "chains": n, "worm_steps_per_chain": steps, "dump_every": 50, "max_dumps": md,
+                    "dumps_kept": kept, "sim_ms": e0.elapsed_time(e1), "worm_steps_per_s": float(n) * steps / (e0.elapsed_time(e1) * 1e-3),
+                    "pipeline_ms": e1.elapsed_time(e2), "pipeline_configs_per_s": n * md / (e1.elapsed_time(e2) * 1e-3),
+                    "levels": int(counts.shape[1]), "mean_bond_count_level0": float(c0.mean()) if kept else None,
+                    "all_dumps_closed_loops": bool(((counts[valid] % 2) == 0).all().item()) if kept else None})
+        del st, counts
+    return out
+
+
+def bench_c4(dev) -> list:
+    """BASELINE configs[3], a quick pass: E/N and C/N at T = 2.269 for L = 8 .. 128 from 64 replicas each, beside
+    Kaufman's exact values (worm_algorithm_b200.kaufman.finite_size_scaling; the full test is in tests/test_gpu_physics.py)."""
+    from worm_algorithm_b200 import kaufman
+    rows = kaufman.finite_size_scaling(Ls=(8, 16, 32, 64, 128), T=2.269, n_replicas=64, steps_per_site=3000, device=dev)
+    return [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in r.items()} for r in rows]
 
 
 def bench_c5(torch, td, engine, dist, dev, rank, world, algo) -> dict:

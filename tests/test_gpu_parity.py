@@ -483,7 +483,7 @@ def test_philox_segment_edges_match_oracle(eng, lanes):
         assert (st.hist.cpu().numpy() == hist).all(), (lanes, chunks)
 
 
-@pytest.mark.parametrize("L,lanes", [(64, 32), (128, 32), (256, 32), (64, 0), (128, 0), (256, 0), (64, 8), (64, 4),
+@pytest.mark.parametrize("L,lanes", [(64, 32), (128, 32), (256, 32), (64, 0), (128, 0), (256, 0), (64, 8), (64, 4), (64, 2),
                                      (128, 8), (128, 4), (64, -2), (128, -2), (256, -2)])
 def test_philox_large_lattices_match_oracle(eng, L, lanes):
     """L = 64 (one chain per walker in the dual layout; three walkers of 4 chains or one of 8 for big
