@@ -10,23 +10,27 @@
 //    `int bonds[]` element per step).  Taylor chain: 4 bits per bond (occupations 0..15; an occupation
 //    that would reach 16 is reported in the chain's WORM_ACC_STATUS word, never wrapped silently), i.e.
 //    1 KiB per chain at L = 32 -> 224 chains per SM instead of 32.  Binary chain: 1 bit per bond, 256 B
-//    per chain at L = 32 (the north star's layout) -> 768 chains per SM (bounded by registers).
-//    Word w of the chain in thread t of the block lives at smem32[w * T + t]: every lane of a warp owns
-//    its own bank, so the random per-lane accesses of a step never conflict.
-//  * A step is ~55 thread-instructions, branch-free.  The head is a site index scaled to the BIT offset of
+//    per chain at L = 32 (the north star's layout) -> up to 512 chains per SM (128 registers per thread).
+//    Word w of the chain of lane l lives at region(warp) + (w * 32 + l) * 4: every lane of a warp owns
+//    its own bank, so the random per-lane accesses of a step never conflict (a ragged last warp packs its
+//    columns densely).
+//  * A step is ~63 (Taylor) / ~51 (binary) thread-instructions, branch-free.  The head is a site index scaled to the BIT offset of
 //    the site's +x bond inside the chain's packed array (x 8 Taylor, x 2 binary): a move is IADD + LOP3
 //    (x / y bit fields wrap by masking, power-of-two L), the bond's word is `offset >> 5`, its shift the low
 //    five bits.  Everything a step needs that depends only on the random word's top four bits
 //    (direction, +/- coin) -- head increment, wrap field, "bond owned by the neighbour" mask merged with
-//    the +y offset, occupation change -- comes out of a 16-entry shared-memory table with one LEA.HI +
-//    one LDS.128, instead of a chain of predicates and selects.
-//  * The Philox block of the NEXT pair of steps is drawn at the top of the loop body: it does not depend
-//    on the chain's state, so its 40 instructions fill the issue slots the dependent step chain
-//    (address -> LDS -> accept -> head) leaves empty.  Round keys live in registers.
+//    the +y offset, occupation change -- comes out of an 8-entry shared-memory table (eight conflict-free
+//    copies of each entry) with one SHF + one LOP3 + one LDS.128, instead of a chain of predicates and selects.
+//  * The Philox block and the table entries of the NEXT pair of steps are drawn one pair ahead (two pairs per
+//    loop trip, register sets alternating): they do not depend on the chain's state, so their instructions fill
+//    the issue slots the dependent step chain (address -> LDS -> accept -> head) leaves empty.  Round keys live
+//    in registers.
 //  * Observables in registers: Z, sum Nb, sum n as 32-bit partial sums folded into 64-bit totals every
 //    `fold` steps, sum Nb^2 / sum n^2 as one IMAD.WIDE each, all predicated on the closed test.
 //  * G(r): the displacement head - tail is carried along in the same scaled format (it IS the byte offset of
-//    its int64 bin) and counted with one `red.global.add.u64` per measured step.
+//    its int64 bin); iterations at an unchanged displacement are counted in a register and added with ONE
+//    `red.global.add.u64` when an accepted move changes it.  Resident blocks come from all over the batch
+//    (PackGeo::perm), so the atomics of a moment spread over all temperatures' rows.
 //  * Dumps (worm_ising_2d.cpp:113-125): the step range is cut at dump multiples by uniform loop control only;
 //    the lanes of a warp copy the configuration of every chain that dumps, unpacking as they go.
 //
@@ -95,7 +99,7 @@ struct PackChain {
 
 struct PackConst {
     uint32_t base;               // shared address of word 0 of this thread's chain
-    uint32_t pitch;              // bytes between consecutive words of a chain (4 * TPB)
+    uint32_t pitch;              // bytes between consecutive words of a chain (128 in a whole warp, 4 x its columns in a ragged one)
     uint32_t lut;                // shared address of the step table
     uint32_t lut_lane;           // byte offset of this lane's copy of a table entry
     uint32_t klo, khi;           // kfix (Taylor) / hfix (binary), 64 bits
