@@ -19,7 +19,9 @@
 //     It keeps no observables: it logs one byte per accepted step and one per closed step.
 //   * ACCOUNTANT warps replay those logs two rounds later and accumulate Z, sum Nb, sum Nb^2,
 //     sum n, sum n^2 with the exact Nb / n of every closed step; they also write the dump events
-//     (in solo mode the walker itself sweeps its shared-memory G(r) bins into the HBM histogram).
+//     and, where the walker-side G(r) bins do not fit shared memory, the histogram: the accept log carries the move's
+//     direction, so the displacement head - tail is replayed like Nb and runs of equal bins are added with red.global
+//     (in solo mode at L <= 32 the walker itself counts in 16-bit shared-memory bins and sweeps them into HBM).
 //   The group meets at one named barrier per round.
 //   CH = 32 ("solo"): one group per block -- the walker has an SM sub-partition to itself, 8 producers
 //   and 4 accountants share the other three.  CH = 8 / 4 / 1: up to four
@@ -252,15 +254,6 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
     const int kick = (int)rb.x;
     const uint32_t thr = rb.y, flip = rb.z, logbits = (LAY == LAY_NIB) ? (rb.w & 0xffu) : rb.w;
     const bool closed = c.closed != 0u;
-    if constexpr (MEAS && HIST && !SH) {
-        // G(r) bin of (head - tail) before the kick; a closed worm is bin 0
-        const int t1 = c.head - c.tail;
-        const int t2 = (c.head | g.XM | (g.SC - 1)) - (c.tail & g.YM);          // y fields, no borrow from x
-        const uint32_t f = closed ? 0u : (uint32_t)((t1 & g.XM) | (t2 & g.YM)); // site difference * SC
-        const uint32_t off8 = (SCSH >= 3) ? (f >> (SCSH - 3)) : (f << (3 - SCSH));
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.global.add.u64 [%0], 1;\n\t}"
-                     :: "l"(hist_row + off8), "r"(hist_writer) : "memory");
-    }
     const int tail = closed ? kick : c.tail;                    // kick :128-129 (head has it already)
     c.tail = tail;
     const int head = c.head;
