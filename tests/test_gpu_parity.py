@@ -240,6 +240,49 @@ def test_latency_kernel_nibble_layout_matches_oracle(eng, monkeypatch, L, tmin, 
     assert (a2[keep] == ref.acc.cpu().numpy()[keep]).all() and (st2.bonds.cpu().numpy()[keep] == ref.bonds.cpu().numpy()[keep]).all()
 
 
+def test_philox_random_batches_all_variants_agree(eng):
+    """Property test over launch geometry: random lattice, batch size, chunking, warm-up, dump period, chain and
+    histogram options; every kernel variant that can run the batch (and whatever lanes_per_chain = 0 picks) must give the
+    thread-per-chain byte kernel's result bit for bit -- that kernel is pinned to the oracle chain by chain above."""
+    rng = np.random.default_rng(2024)
+    for case in range(24):
+        L = int(rng.choice([4, 8, 16, 32, 64]))
+        algo = int(rng.integers(0, 2))
+        n = int(rng.choice([1, 3, 31, 33, 100, 257, 1000, 4100 if L <= 32 else 300]))
+        nT = int(rng.integers(1, 6))
+        gi = (np.arange(n) % nT).astype(np.int32)
+        T = rng.uniform(0.9 if case % 5 == 0 else 1.0, 3.6, nT)[gi]
+        seeds = rng.integers(0, 2 ** 63, n, dtype=np.uint64)
+        hist = bool(rng.integers(0, 2))
+        de = int(rng.choice([0, 1, 7, 50, 64]))
+        md = int(rng.integers(1, 6)) if de else 0
+        chunks = [int(x) for x in rng.integers(1, 900, int(rng.integers(1, 4)))]
+        therm = int(rng.integers(0, sum(chunks)))
+        cid0 = int(rng.integers(0, 2 ** 40))
+
+        def run(lanes):
+            st = eng.PhiloxState(L, T, seeds, algo=algo, chain_id0=cid0, group_index=gi, n_groups=nT, hist=hist, max_dumps=md)
+            for ch in chunks:
+                st.run(ch, therm_steps=therm, dump_every=de, lanes_per_chain=lanes)
+            return st
+        ref = run(1)
+        for lanes in (0, -2, 2, 4, 8, 32):
+            if lanes == 2 and n < 64:
+                continue
+            try:
+                st = run(lanes)
+            except Exception as ex:                     # a variant that cannot hold this lattice says so
+                assert "latency mode" in str(ex) or "packed mode" in str(ex), (case, lanes, ex)
+                continue
+            key = (case, L, algo, n, hist, de, md, chunks, therm, lanes)
+            assert (st.acc == ref.acc).all() and (st.bonds == ref.bonds).all(), key
+            assert (st.head == ref.head).all() and (st.tail == ref.tail).all() and (st.group_acc == ref.group_acc).all(), key
+            if hist:
+                assert (st.hist == ref.hist).all(), key
+            if de:
+                assert (st.n_dumps == ref.n_dumps).all() and (st.events == ref.events).all() and (st.dumps == ref.dumps).all(), key
+
+
 def test_philox_packed_refuses_what_it_cannot_hold(eng):
     """An occupation above 15 cannot be packed in 4 bits: the chain is left untouched and says so in
     WORM_ACC_STATUS (bit 0); the other chains of the batch run normally."""
