@@ -442,7 +442,8 @@ def bench_shapes(torch, engine, dev, algo, issue_peak) -> list:
     out = []
     T_, B_ = engine.ALGO_TAYLOR, engine.ALGO_BINARY
     cases = [(16, 4096, 400_000, False, algo), (32, 4096, 400_000, True, algo),
-             (32, 125_000, 40_000, False, T_), (32, 125_000, 40_000, False, B_), (32, 125_000, 20_000, True, T_),
+             (32, 125_000, 40_000, False, T_), (32, 125_000, 40_000, False, B_), (32, 75_776, 40_000, False, B_),
+             (32, 125_000, 20_000, True, T_),
              (64, 4096, 100_000, False, algo), (64, 8288, 100_000, False, T_), (64, 32_768, 40_000, False, B_),
              (128, 1024, 100_000, False, algo), (128, 2072, 100_000, False, T_), (128, 8192, 100_000, False, B_),
              (256, 512, 100_000, False, algo), (256, 2072, 100_000, False, B_)]

@@ -38,6 +38,13 @@
 // reference loop worm_ising_2d.cpp:111-157 on a Philox4x32-10 stream.  Power-of-two L >= 4.
 #include "worm_run.cuh"
 
+#ifndef WORM_PACK_BIG
+#define WORM_PACK_BIG 512        // threads per block of the high-occupancy instantiation (registers: 65536 / this)
+#endif
+#ifndef WORM_PACK_UNROLL2
+#define WORM_PACK_UNROLL2 1      // two pairs of steps per loop trip (register sets alternate) instead of one pair + copies
+#endif
+
 namespace worm {
 
 namespace {
@@ -495,6 +502,16 @@ worm_pack_kernel(const PhiloxArgs a, const PackGeo g)
             // next pair -- independent of the chain -- fill the issue slots and hide behind its latency.
             uint4 rA = philox4x32_10(plo, phi, c2, c3, keys);
             uint4 a0 = table(rA.y), a1 = table(rA.w);
+#if !WORM_PACK_UNROLL2
+            for (; left >= 4u; left -= 2u) {
+                ++plo;
+                const uint4 rn = philox4x32_10(plo, phi, c2, c3, keys);
+                const uint4 n0 = table(rn.y), n1 = table(rn.w);
+                pack_step<ALGO, LOWT, MEAS, HIST>(k, c, rA.x, rA.y, a0);
+                pack_step<ALGO, LOWT, MEAS, HIST>(k, c, rA.z, rA.w, a1);
+                rA = rn; a0 = n0; a1 = n1;
+            }
+#endif
             for (; left >= 4u; left -= 4u) {
                 const uint4 rB = philox4x32_10(plo + 1u, phi, c2, c3, keys);
                 const uint4 b0 = table(rB.y), b1 = table(rB.w);
@@ -624,7 +641,7 @@ PackPlan pack_plan(int L, int algo, int64_t n_chains, int smem_optin, int sm_cou
     const size_t budget = (size_t)smem_optin > LUT_BYTES ? (size_t)smem_optin - LUT_BYTES : 0;
     int cmax = (int)(budget / per_chain);
     if (cmax < 1) return p;
-    if (cmax > 512) cmax = 512;
+    if (cmax > WORM_PACK_BIG) cmax = WORM_PACK_BIG;
     // a last partial warp costs the issue slots of a whole one: not worth it for a few chains
     if (cmax >= 32 && (cmax & 31) < 16) cmax &= ~31;
     // as many waves as the largest block needs, then the smallest block that still fits the batch in them:
@@ -676,7 +693,7 @@ template <int ALGO, bool LOWT, bool HIST>
 cudaError_t launch_pack(const PhiloxArgs &a, const PackPlan &p, cudaStream_t st)
 {
     if (p.g.TPB <= 256) return launch_pack_t<ALGO, LOWT, HIST, 256>(a, p, st);
-    return launch_pack_t<ALGO, LOWT, HIST, 512>(a, p, st);
+    return launch_pack_t<ALGO, LOWT, HIST, WORM_PACK_BIG>(a, p, st);
 }
 
 template <int ALGO>
