@@ -1144,8 +1144,17 @@ LatPlan lat_plan_mode(int L, int CH, int algo, bool sh, int smem_optin)
         if (pin && ((pin[0] == 'd') != (lay == LAY_DUAL) || (pin[0] == 'b') != (lay == LAY_BYTE) || (pin[0] == 'n') != (lay == LAY_NIB))) continue;
         const size_t region = lay == LAY_DUAL ? (size_t)4 * N * CH : lay == LAY_BYTE ? (size_t)2 * N : (size_t)N * CH;
         const int sc = lay == LAY_DUAL ? 4 * CH : lay == LAY_BYTE ? 2 : CH;
+        const char *nwcap = getenv("WORM_LAT_NW");         // cap on the walker groups per block (experiments)
         for (int nw : {4, 3, 2, 1}) {
             if (CH == 32 && nw != 1) continue;
+            if (nwcap && nw > nwcap[0] - '0') continue;
+            // Groups of four chains: several one-group blocks per SM beat one block of several groups when as many
+            // chains fit that way (L = 128: three 69 KB blocks, 75 cycles per step against 89 for one block of three
+            // groups).  Not so for eight chains per group (L = 64: 102 against 224) or one (L = 256: 94 against 163).
+            if (CH == 4 && nw > 1 && lay != LAY_DUAL) {
+                const size_t need1 = ((region + recw + logw) + 15) / 16 * 16 + 16;
+                if ((size_t)(228 * 1024) / (need1 + 1024) >= (size_t)nw) continue;
+            }
             if (nw * CH <= best) continue;
             const size_t body = (nw * (region + recw + logw) + 15) / 16 * 16 + histb;
             const size_t need = body + (lay == LAY_NIB ? (size_t)((nw * CH + 15) / 16 * 16) : 0);
@@ -1234,8 +1243,14 @@ bool lat_info(int L, int G, int algo, bool hist, int smem_optin, int *chains_per
     if (G != 2 && G != 4 && G != 8 && G != 32) return false;
     const LatPlan p = lat_plan(L, chains_per_walker(G), algo, hist, smem_optin);
     if (!p.ok) return false;
-    *chains_per_block = p.g.nw * chains_per_walker(G);
-    *walkers = p.g.nw;
+    // blocks that fit an SM together (shared memory incl. the 1 KB the system keeps per block; threads)
+    const int warps = (chains_per_walker(G) == 32) ? 16 : (chains_per_walker(G) == 8 ? 4 : 3) * p.g.nw;
+    int per_sm = (int)((size_t)(228 * 1024) / (p.smem + 1024));
+    if (per_sm > 64 / warps) per_sm = 64 / warps;
+    if (per_sm < 1) per_sm = 1;
+    if (chains_per_walker(G) != 4 || p.g.nw != 1) per_sm = 1;      // only the one-group blocks of four chains are run that way
+    *chains_per_block = p.g.nw * chains_per_walker(G) * per_sm;    // chains an SM holds
+    *walkers = p.g.nw * per_sm;
     *layout = p.lay;
     return true;
 }
