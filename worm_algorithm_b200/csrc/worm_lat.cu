@@ -41,6 +41,7 @@
 //
 // Algorithm and random stream: oracle/worm_oracle.c:worm_oracle_philox_run (bit-for-bit), i.e. the
 // reference loop worm_ising_2d.cpp:111-157 on a Philox4x32-10 stream.
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 #include <utility>
@@ -522,7 +523,16 @@ __device__ __forceinline__ Batch make_batch(uint64_t s, uint64_t seg_end)
     b.s0 = s & ~1ull;
     b.jb = (int)(s - b.s0);
     const uint64_t left = seg_end - b.s0;
-    if (b.jb == 0 && left >= (uint64_t)R) {
+    const int rem = (int)(left % (uint64_t)R);
+    if (b.jb == 0 && left > (uint64_t)R && rem != 0 && (rem & 1) == 0) {
+        // The short round of a segment comes FIRST (when it is even: rounds start on a Philox pair).  With the dump
+        // rule every 50-step interval has one, and two record buffers keep the roles in lockstep: behind the short
+        // round the walker waits for a whole round to be built.  In front of the interval that wait overlaps the
+        // walker's pause at the dump multiple.
+        b.n = 1u;
+        b.je = rem;
+        b.s_next = b.s0 + (uint64_t)rem;
+    } else if (b.jb == 0 && left >= (uint64_t)R) {
         const uint64_t nf = left / (uint64_t)R;
         b.n = nf > 0x40000000ull ? 0x40000000u : (uint32_t)nf;
         b.je = R;
@@ -545,6 +555,36 @@ __device__ __forceinline__ uint32_t dual_word(const uint8_t *gb, int s, int L, i
     const int down = (s < L) ? s + N - L : s - L;
     const uint32_t xy = *reinterpret_cast<const uint16_t *>(gb + 2 * s);        // +x | +y << 8
     return xy | ((uint32_t)gb[2 * left] << 16) | ((uint32_t)gb[2 * down + 1] << 24);
+}
+
+// Dump copy (worm_ising_2d.cpp:120-124): the walker's live lanes copy, chain by chain, the bonds of the chains in `dm`
+// to their next dump slot.  Cold code, kept out of line.
+template <int CH, int LAY>
+__device__ __noinline__ void lat_copy_dumps(unsigned dm, int lane, long long cl, int nd, uint8_t *dumps, int max_dumps,
+                                            int nb2, int N, uint32_t region_abs)
+{
+    constexpr unsigned wmask = (CH == 32) ? 0xffffffffu : ((1u << CH) - 1u);
+    while (dm) {
+        const int src_lane = __ffs(dm) - 1;
+        dm &= dm - 1;
+        const long long chain = __shfl_sync(wmask, cl, src_lane);
+        const int slot = __shfl_sync(wmask, nd, src_lane);
+        uint8_t *dstb = dumps + (chain * max_dumps + slot) * nb2;
+        if constexpr (LAY == LAY_DUAL) {
+            uint16_t *dst = reinterpret_cast<uint16_t *>(dstb);
+            for (int sI = lane; sI < N; sI += CH)
+                dst[sI] = (uint16_t)lds_u32(region_abs + (uint32_t)((sI * CH + src_lane) * 4));
+        } else if constexpr (LAY == LAY_NIB) {
+            uint16_t *dst = reinterpret_cast<uint16_t *>(dstb);
+            for (int sI = lane; sI < N; sI += CH) {
+                const uint32_t v = lds_u8(region_abs + (uint32_t)(sI * CH + src_lane));
+                dst[sI] = (uint16_t)((v & 15u) | ((v >> 4) << 8));
+            }
+        } else {
+            uint4 *dst = reinterpret_cast<uint4 *>(dstb);
+            for (int i = lane; i < nb2 / 16; i += CH) dst[i] = lds_v4(region_abs + (uint32_t)(i * 16));
+        }
+    }
 }
 
 // HMODE: G(r) histograms -- 0 none; 1 the solo walker counts in 16-bit per-chain bins in shared memory (needs
@@ -677,27 +717,60 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         const PhiloxKeys keys = philox_keys((uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
         const float numf = __fmul_ru(__uint2float_ru((uint32_t)(prm.kfix - 1)), 1.0f + 1.0f / 262144.0f);
         uint32_t buf = 0u;
+        // steps of a round this lane's record(s) serve: a short round (segment edge) is built by the lanes it needs
+        const int j_lo = (Cfg::RPL == 2) ? 2 * p_of : b / CH, j_hi = (Cfg::RPL == 2) ? 2 * p_of + 1 : b / CH;
+        // the records of one Philox pair per lane into the current buffer
+        auto build = [&](uint64_t pair) {
+#if WORM_LAT_FAKE
+            uint4 r = make_uint4((uint32_t)pair * 2654435761u, (uint32_t)pair * 40503u + c2, c2 * 2246822519u + (uint32_t)pair, c3 + (uint32_t)pair * 3266489917u);
+            r.x ^= r.y >> 7; r.y ^= r.x << 9; r.z ^= r.w >> 5; r.w ^= r.z << 11;
+#else
+            const uint4 r = philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), c2, c3, keys);
+#endif
+            const uint32_t p0 = rec_q + buf;
+            if constexpr (Cfg::RPL == 2) {
+                uint4 ra0, rb0, rc0, ra1, rb1, rc1;
+                make_record<ALGO, LAY, SH>(g, prm, numf, r.x, r.y, chain_abs, ra0, rb0, rc0);
+                make_record<ALGO, LAY, SH>(g, prm, numf, r.z, r.w, chain_abs, ra1, rb1, rc1);
+                sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0);
+                sts_v4(p0 + CH * 16, ra1); sts_v4(p0 + CH * 16 + Cfg::REC_B, rb1);
+            } else {
+                uint4 ra0, rb0, rc0;
+                make_record<ALGO, LAY, SH>(g, prm, numf, half ? r.z : r.x, half ? r.w : r.y, chain_abs, ra0, rb0, rc0);
+                sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0); sts_v4(p0 + Cfg::REC_C, rc0);
+            }
+        };
+        const bool dump_even = a.dump_every != 0ull && (a.dump_every & 1ull) == 0ull;
+        const int dump_full = (int)(a.dump_every / (uint64_t)R), dump_tail = (int)(a.dump_every % (uint64_t)R);
+        Segments segs(a);
         uint64_t s = a.step_begin;
         while (s < a.step_end) {
+            if (dump_even && s == segs.next_dump && a.step_end - s >= a.dump_every) {
+                // whole dump intervals in the steady state (the schedule of make_batch: an even short round, then the
+                // full rounds) as one tight loop: the segment bookkeeping below, cold code once per 50 steps, made the
+                // walker wait ~500 cycles for the first round of every interval
+                uint64_t pair = (s >> 1) + (uint64_t)p_of;
+                do {
+                    const int nr = dump_full + (dump_tail && dump_full ? 1 : 0) + (dump_full ? 0 : 1);
+                    for (int i = 0; i < nr; ++i) {
+                        const int je = (i == 0 && (dump_tail || !dump_full)) ? (dump_tail ? dump_tail : R) : R;
+                        if (j_lo < je) build(pair);
+                        group_barrier<Cfg::GW>(bar_id);
+                        buf ^= (uint32_t)Cfg::BUF;
+                        pair += (uint64_t)(je >> 1);
+                    }
+                    s += a.dump_every;
+                    segs.next_dump += a.dump_every;
+                } while (a.step_end - s >= a.dump_every);
+                continue;
+            }
             bool meas, dump_first;
-            const uint64_t seg_end = next_segment(a, s, meas, dump_first);
+            const uint64_t seg_end = segs.next(a, s, meas, dump_first);
             while (s < seg_end) {
                 const Batch bt = make_batch<R>(s, seg_end);
                 uint64_t pair = (bt.s0 >> 1) + (uint64_t)p_of;
                 for (uint32_t kk = 0; kk < bt.n; ++kk, pair += R / 2) {
-                    const uint4 r = philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), c2, c3, keys);
-                    const uint32_t p0 = rec_q + buf;
-                    if constexpr (Cfg::RPL == 2) {
-                        uint4 ra0, rb0, rc0, ra1, rb1, rc1;
-                        make_record<ALGO, LAY, SH>(g, prm, numf, r.x, r.y, chain_abs, ra0, rb0, rc0);
-                        make_record<ALGO, LAY, SH>(g, prm, numf, r.z, r.w, chain_abs, ra1, rb1, rc1);
-                        sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0);
-                        sts_v4(p0 + CH * 16, ra1); sts_v4(p0 + CH * 16 + Cfg::REC_B, rb1);
-                    } else {
-                        uint4 ra0, rb0, rc0;
-                        make_record<ALGO, LAY, SH>(g, prm, numf, half ? r.z : r.x, half ? r.w : r.y, chain_abs, ra0, rb0, rc0);
-                        sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0); sts_v4(p0 + Cfg::REC_C, rc0);
-                    }
+                    if (j_hi >= bt.jb && j_lo < bt.je) build(pair);
                     group_barrier<Cfg::GW>(bar_id);
                     buf ^= (uint32_t)Cfg::BUF;
                 }
@@ -796,10 +869,31 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             lbuf_acc = (lbuf_acc == 2u * Cfg::LOGB) ? 0u : lbuf_acc + (uint32_t)Cfg::LOGB;
         };
 
+        const bool dump_even = a.dump_every != 0ull && (a.dump_every & 1ull) == 0ull;
+        const int dump_full = (int)(a.dump_every / (uint64_t)R), dump_tail = (int)(a.dump_every % (uint64_t)R);
+        Segments segs(a);
         uint64_t s = a.step_begin;
         while (s < a.step_end) {
+            if (dump_even && s == segs.next_dump && a.step_end - s >= a.dump_every) {
+                // whole dump intervals in the steady state, like the producers
+                do {
+                    const int nr = dump_full + (dump_tail && dump_full ? 1 : 0) + (dump_full ? 0 : 1);
+                    uint64_t sr = s;
+                    for (int i = 0; i < nr; ++i) {
+                        const int je = (i == 0 && (dump_tail || !dump_full)) ? (dump_tail ? dump_tail : R) : R;
+                        group_barrier<Cfg::GW>(bar_id);
+                        if (pend[0].valid) account(pend[0]);
+                        pend[0] = pend[1];
+                        pend[1] = Pending{sr, 0, je, true, i == 0, true};
+                        sr += (uint64_t)je;
+                    }
+                    s += a.dump_every;
+                    segs.next_dump += a.dump_every;
+                } while (a.step_end - s >= a.dump_every);
+                continue;
+            }
             bool meas, dump_first;
-            const uint64_t seg_end = next_segment(a, s, meas, dump_first);
+            const uint64_t seg_end = segs.next(a, s, meas, dump_first);
             bool seg_first = true;
             while (s < seg_end) {
                 const Batch bt = make_batch<R>(s, seg_end);
@@ -916,7 +1010,21 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         }
         int32_t nd = (a.n_dumps && live) ? a.n_dumps[cl] : 0;
 
+#if WORM_LAT_PROF
+        long long pf_seg = 0, pf_dump = 0, pf_full = 0, pf_tail = 0, pf_edge = 0, pf_n = 0, pf_t = clock64(), pf_t0 = pf_t;
+#define PF(x) { const long long t_ = clock64(); x += t_ - pf_t; pf_t = t_; }
+#else
+#define PF(x)
+#endif
         auto rec_addr = [&](uint32_t buf, int j) { return rec_q + buf + (uint32_t)(j * CH * 16); };
+        // A dump multiple (worm_ising_2d.cpp:120-124): the chains that are closed in front of this step are copied
+        // to their next dump slot (the event record {step, Z, sum Nb} is written by the accountant)
+        auto do_pause = [&]() {
+            const bool want = live && c.closed;
+            const unsigned dm = __ballot_sync(wmask, want && nd < a.max_dumps && a.dumps != nullptr);
+            if (dm) lat_copy_dumps<CH, LAY>(dm, lane, (long long)cl, nd, a.dumps, a.max_dumps, g.nb2, g.N, region_abs);
+            if (want) ++nd;
+        };
 
         // A full round (steps 0..R-1 of the buffer at `cur`), software-pipelined two steps deep: on
         // entry (p0a,p0b) / (p1a,p1b) hold the records of steps 0 / 1; step j fetches the record of
@@ -942,6 +1050,26 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 if constexpr (SH) { p0c = p1c; p1c = fc; }
             });
         };
+        // The short round that opens a dump interval (steps 0..r-1 of the buffer at `cur`, r even, 0 < r < R), software-
+        // pipelined like a full round: entered with the records of steps 0 / 1 in (p0, p1) -- the full round in front
+        // of it has fetched them -- and left with those of the next round's.  Log bytes go out one by one.
+        auto tail_round = [&](auto meas_tag, uint32_t cur, uint32_t nxt, uint32_t lg, int r) {
+            constexpr bool MEAS = decltype(meas_tag)::value;
+#pragma unroll 1
+            for (int j = 0; j < r; ++j) {                 // (rolled: one copy of the step -- this is cold code, and a
+                                                          // lone warp pays ~45 cycles for every instruction line it misses)
+                uint32_t nrec = rec_addr(cur, j + 2);
+                if (j + 2 >= r) nrec = rec_addr(nxt, j + 2 - r);
+                if (j + 2 == r) group_barrier<Cfg::GW>(bar_id);
+                const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
+                uint4 fc = make_uint4(0, 0, 0, 0);
+                if constexpr (SH) fc = lds_v4(nrec + Cfg::REC_C);
+                lat_step<ALGO, LAY, SCSH, SH, SH, MEAS>(g, hist_row, hist_writer, c, p0a, p0b, p0c, (int)p1b.x, p1a.z,
+                                                       lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j));
+                p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
+                if constexpr (SH) { p0c = p1c; p1c = fc; }
+            }
+        };
         // Any other round (segment edges): steps [jb, je), records straight from shared memory.  The
         // kick folded into the last step is the first record of the next round (slot jbn of `nxt`).
         auto edge_round = [&](auto meas_tag, uint32_t cur, uint32_t nxt, uint32_t lg, int jb, int je, int jbn) {
@@ -962,41 +1090,63 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         };
 
         uint32_t cur = 0u, lbuf = 0u;
+        const uint32_t dump_full = (uint32_t)(a.dump_every / (uint64_t)R);      // full rounds / steps of the short round
+        const int dump_tail = (int)(a.dump_every % (uint64_t)R);                // of a dump interval
+        Segments segs(a);
         uint64_t s = a.step_begin;
         bool first = true;
         bool piped = false;                  // (p0, p1) hold the first two records of the coming round
+        const bool dump_even = a.dump_every != 0ull && (a.dump_every & 1ull) == 0ull;
         while (s < a.step_end) {
-            bool meas, dump_first;
-            const uint64_t seg_end = next_segment(a, s, meas, dump_first);
-            if (dump_first) {                                        // worm_ising_2d.cpp:120-124
-                // the walker's live lanes copy the bonds of every chain that dumps now (the event
-                // record {step, Z, sum Nb} is written by the accountant)
-                const bool want = live && c.closed;
-                const bool store = want && nd < a.max_dumps;
-                unsigned dm = __ballot_sync(wmask, store && a.dumps != nullptr);
-                while (dm) {
-                    const int src_lane = __ffs(dm) - 1;
-                    dm &= dm - 1;
-                    const long long chain = __shfl_sync(wmask, (long long)cl, src_lane);
-                    const int slot = __shfl_sync(wmask, nd, src_lane);
-                    uint8_t *dstb = a.dumps + (chain * a.max_dumps + slot) * g.nb2;
-                    if constexpr (DUAL) {
-                        uint16_t *dst = reinterpret_cast<uint16_t *>(dstb);
-                        for (int sI = lane; sI < g.N; sI += CH)
-                            dst[sI] = (uint16_t)lds_u32(region_abs + (uint32_t)((sI * CH + src_lane) * 4));
-                    } else if constexpr (NIB) {
-                        uint16_t *dst = reinterpret_cast<uint16_t *>(dstb);
-                        for (int sI = lane; sI < g.N; sI += CH) {
-                            const uint32_t v = lds_u8(region_abs + (uint32_t)(sI * CH + src_lane));
-                            dst[sI] = (uint16_t)((v & 15u) | ((v >> 4) << 8));
-                        }
-                    } else {
-                        uint4 *dst = reinterpret_cast<uint4 *>(dstb);
-                        for (int i = lane; i < g.nb2 / 16; i += CH) dst[i] = lds_v4(region_abs + (uint32_t)(i * 16));
+            // A whole dump interval in the steady state: the pause, its full rounds and one short round, nothing else.
+            // Everything outside the unrolled full round is cold code for the lone in-order walker (~45 cycles per
+            // instruction line it has to fetch, ~25 per branch): the general schedule below cost as much as 20 of the
+            // interval's 50 steps.
+            if (dump_even && !first && s == segs.next_dump && a.step_end - s >= a.dump_every) {
+                segs.next_dump += a.dump_every;
+                const uint64_t seg_end = s + a.dump_every;
+                PF(pf_seg)
+                do_pause();                                          // worm_ising_2d.cpp:120-124
+                PF(pf_dump)
+                if (!piped) {
+                    p0a = lds_v4(rec_addr(cur, 0)); p0b = lds_v4(rec_addr(cur, 0) + Cfg::REC_B);
+                    p1a = lds_v4(rec_addr(cur, 1)); p1b = lds_v4(rec_addr(cur, 1) + Cfg::REC_B);
+                    if constexpr (SH) {
+                        p0c = lds_v4(rec_addr(cur, 0) + Cfg::REC_C); p1c = lds_v4(rec_addr(cur, 1) + Cfg::REC_C);
+                    }
+                    piped = true;
+                }
+                if (dump_tail) {
+                    const uint32_t nxt = cur ^ (uint32_t)Cfg::BUF;
+                    tail_round(std::true_type{}, cur, nxt, log_q + lbuf, dump_tail);
+                    cur = nxt;
+                    lbuf = (lbuf == 2u * Cfg::LOGB) ? 0u : lbuf + (uint32_t)Cfg::LOGB;
+                    if constexpr (SH) {
+                        if (++flush_ctr == Cfg::FLUSH) { flush_hist(); flush_ctr = 0; }
                     }
                 }
-                if (want) ++nd;
+                PF(pf_tail)
+                for (uint32_t kk = 0; kk < dump_full; ++kk) {
+                    const uint32_t nxt = cur ^ (uint32_t)Cfg::BUF;
+                    full_round(std::true_type{}, cur, nxt, log_q + lbuf);
+                    cur = nxt;
+                    lbuf = (lbuf == 2u * Cfg::LOGB) ? 0u : lbuf + (uint32_t)Cfg::LOGB;
+                    if constexpr (SH) {
+                        if (++flush_ctr == Cfg::FLUSH) { flush_hist(); flush_ctr = 0; }
+                    }
+                }
+                PF(pf_full)
+                s = seg_end;
+#if WORM_LAT_PROF
+                ++pf_n;
+#endif
+                continue;
             }
+            bool meas, dump_first;
+            const uint64_t seg_end = segs.next(a, s, meas, dump_first);
+            PF(pf_seg)
+            if (dump_first) do_pause();
+            PF(pf_dump)
             while (s < seg_end) {
                 const Batch bt = make_batch<R>(s, seg_end);
                 if (first) {
@@ -1028,6 +1178,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                         }
                     }
                     piped = true;
+                    PF(pf_full)
                 } else {
                     const uint32_t nxt = cur ^ (uint32_t)Cfg::BUF;
                     if (meas) edge_round(std::true_type{}, cur, nxt, log_q + lbuf, bt.jb, bt.je, (int)(bt.s_next & 1ull));
@@ -1038,10 +1189,19 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     if constexpr (SH) {
                         if (++flush_ctr == Cfg::FLUSH) { flush_hist(); flush_ctr = 0; }
                     }
+                    PF(pf_edge)
                 }
                 s = bt.s_next;
             }
+#if WORM_LAT_PROF
+            ++pf_n;
+#endif
         }
+#if WORM_LAT_PROF
+        if (blockIdx.x == 0 && lane == 0 && w == 0)
+            printf("lat prof: segments %lld total %lld cycles: seg %lld dump %lld full %lld tail %lld edge %lld (per segment %lld)\n",
+                   pf_n, clock64() - pf_t0, pf_seg, pf_dump, pf_full, pf_tail, pf_edge, (clock64() - pf_t0) / (pf_n ? pf_n : 1));
+#endif
 
         if (first) group_barrier<Cfg::GW>(bar_id);                             // empty step range: meet the producer once
         group_barrier<Cfg::GW>(bar_id);                                        // every step is logged: the accountant may finish

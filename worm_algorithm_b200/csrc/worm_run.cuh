@@ -39,20 +39,34 @@ __device__ __forceinline__ int64_t measured_iters(const PhiloxArgs &a)
 }
 
 // Segment [s, seg_end) of the step range: MEAS is constant inside it and a dump multiple can only
-// be its FIRST step.  Returns seg_end, sets meas / dump_first.
-__device__ __forceinline__ uint64_t next_segment(const PhiloxArgs &a, uint64_t s, bool &meas, bool &dump_first)
-{
-    meas = (s >= a.therm);
-    uint64_t seg_end = a.step_end;
-    if (!meas && a.therm < seg_end) seg_end = a.therm;
-    dump_first = false;
-    if (meas && a.dump_every) {
-        const uint64_t rem = s % a.dump_every;
-        dump_first = (rem == 0);
-        const uint64_t nxt = s + (a.dump_every - rem);       // next multiple after s
-        if (nxt < seg_end) seg_end = nxt;
+// be its FIRST step.  The next dump multiple is carried along (one 64-bit modulo per launch: on a lone
+// in-order warp a modulo per segment cost ~500 cycles of the 2900 a 50-step segment takes).
+struct Segments {
+    uint64_t next_dump;                  // smallest multiple of dump_every >= the current step (measured steps only)
+    __device__ __forceinline__ explicit Segments(const PhiloxArgs &a)
+    {
+        next_dump = ~0ull;
+        if (a.dump_every) {
+            const uint64_t s0 = a.step_begin > a.therm ? a.step_begin : a.therm;
+            const uint64_t rem = s0 % a.dump_every;
+            next_dump = rem ? s0 + (a.dump_every - rem) : s0;
+        }
     }
-    return seg_end;
-}
+    // returns seg_end, sets meas / dump_first.  cut_dumps = false: segments end at MEAS changes only and the
+    // caller handles the dump multiples inside its rounds (next_dump is its to advance).
+    __device__ __forceinline__ uint64_t next(const PhiloxArgs &a, uint64_t s, bool &meas, bool &dump_first, bool cut_dumps = true)
+    {
+        meas = (s >= a.therm);
+        uint64_t seg_end = a.step_end;
+        if (!meas && a.therm < seg_end) seg_end = a.therm;
+        dump_first = false;
+        if (meas && a.dump_every && cut_dumps) {
+            dump_first = (s == next_dump);
+            if (dump_first) next_dump += a.dump_every;
+            if (next_dump < seg_end) seg_end = next_dump;
+        }
+        return seg_end;
+    }
+};
 
 }  // namespace worm

@@ -198,10 +198,11 @@ worm_wide_kernel(const PhiloxArgs a, const Geo geo)
     const uint32_t k0 = (uint32_t)prm.seed, k1 = (uint32_t)(prm.seed >> 32);
     const uint32_t c2 = (uint32_t)chain_id, c3 = (uint32_t)(chain_id >> 32);
 
+    Segments segs(a);
     uint64_t s = a.step_begin;
     while (s < a.step_end) {
         bool meas, dump_first;
-        const uint64_t seg_end = next_segment(a, s, meas, dump_first);
+        const uint64_t seg_end = segs.next(a, s, meas, dump_first);
         if (dump_first && live && c.head == c.tail) {            // worm_ising_2d.cpp:113-124
             if (nd < a.max_dumps) {
                 if (a.events) {
