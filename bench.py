@@ -510,12 +510,21 @@ def bench_c3(torch, engine, dev) -> list:
         counts = engine.pipeline(st.dumps.reshape(n * md, 2 * L * L), L)
         e2.record()
         torch.cuda.synchronize(dev)
+        # the same batch with the dump rule off (what the rule costs: the step range is cut at every multiple of 50)
+        st0 = engine.PhiloxState(L, T, seeds, algo=engine.ALGO_TAYLOR, device=dev, group_index=t_idx, n_groups=temps.size)
+        st0.run(2000, therm_steps=200)
+        f0, f1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+        f0.record(); st0.run(steps // 2, therm_steps=steps // 20); f1.record()
+        torch.cuda.synchronize(dev)
+        rate_off = float(n) * (steps // 2) / (f0.elapsed_time(f1) * 1e-3)
+        del st0
         nd = st.n_dumps.clamp(max=md)
         kept = int(nd.sum().item())
         valid = (torch.arange(md, device=dev)[None, :] < nd[:, None]).reshape(-1)
         c0 = counts[valid][:, 0].double()
         out.append({"L": L, "chains": n, "worm_steps_per_chain": steps, "dump_every": 50, "max_dumps": md,
                     "dumps_kept": kept, "sim_ms": e0.elapsed_time(e1), "worm_steps_per_s": float(n) * steps / (e0.elapsed_time(e1) * 1e-3),
+                    "worm_steps_per_s_rule_off": rate_off, "dump_rule_cost": rate_off / (float(n) * steps / (e0.elapsed_time(e1) * 1e-3)),
                     "pipeline_ms": e1.elapsed_time(e2), "pipeline_configs_per_s": n * md / (e1.elapsed_time(e2) * 1e-3),
                     "levels": int(counts.shape[1]), "mean_bond_count_level0": float(c0.mean()) if kept else None,
                     "all_dumps_closed_loops": bool(((counts[valid] % 2) == 0).all().item()) if kept else None})

@@ -490,8 +490,9 @@ def test_host_entry_points(eng, ref_runs):
 # round / segment edges of the latency kernel: odd starts, runs shorter than a round, odd dump
 # periods, warm-up ending inside a round, empty ranges
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("with_hist", [True, False])
 @pytest.mark.parametrize("lanes", [2, 4, 8, 32, 1, -2])
-def test_philox_segment_edges_match_oracle(eng, lanes):
+def test_philox_segment_edges_match_oracle(eng, lanes, with_hist):
     from oracle import worm_oracle as wo
     L, n = 8, 11
     rng = np.random.default_rng(77 + lanes)
@@ -500,9 +501,13 @@ def test_philox_segment_edges_match_oracle(eng, lanes):
     cases = [  # (chunks, therm, dump_every)
         ([1, 1, 1, 2, 3], 0, 0), ([15, 17, 16, 1], 9, 7), ([33, 0, 64, 5], 40, 50), ([7, 250, 3], 123, 13),
         ([128], 128, 1), ([65], 1000, 3),
+        # whole dump intervals (the latency kernel walks them in its steady-state loops: short round first, then the full
+        # rounds): intervals shorter than / equal to / a multiple of / longer than a round, entered at and off a multiple
+        ([700, 301], 50, 50), ([640], 0, 16), ([500, 500], 100, 48), ([333, 667], 10, 10), ([1000], 0, 2),
+        ([900, 150], 64, 100), ([49, 51, 400], 0, 50), ([1200], 37, 64),
     ]
     for chunks, therm, dump_every in cases:
-        st = eng.PhiloxState(L, T, seeds, algo=0, chain_id0=5, group_index=np.arange(n) % 2, n_groups=2, hist=True,
+        st = eng.PhiloxState(L, T, seeds, algo=0, chain_id0=5, group_index=np.arange(n) % 2, n_groups=2, hist=with_hist,
                              max_dumps=300)
         for ch in chunks:
             st.run(ch, therm_steps=therm, dump_every=dump_every, lanes_per_chain=lanes)
@@ -523,7 +528,8 @@ def test_philox_segment_edges_match_oracle(eng, lanes):
             assert (ev[c, :k] == o["events"]).all(), key
             assert (dm[c, :k] == o["dumps"]).all(), key
             hist[c % 2] += o["hist"]
-        assert (st.hist.cpu().numpy() == hist).all(), (lanes, chunks)
+        if with_hist:
+            assert (st.hist.cpu().numpy() == hist).all(), (lanes, chunks)
 
 
 @pytest.mark.parametrize("L,lanes", [(64, 32), (128, 32), (256, 32), (64, 0), (128, 0), (256, 0), (64, 8), (64, 4), (64, 2),

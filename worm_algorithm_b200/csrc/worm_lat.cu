@@ -1167,16 +1167,22 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                             p0c = lds_v4(rec_addr(cur, 0) + Cfg::REC_C); p1c = lds_v4(rec_addr(cur, 1) + Cfg::REC_C);
                         }
                     }
-                    for (uint32_t kk = 0; kk < bt.n; ++kk) {
-                        const uint32_t nxt = cur ^ (uint32_t)Cfg::BUF;
-                        if (meas) full_round(std::true_type{}, cur, nxt, log_q + lbuf);
-                        else full_round(std::false_type{}, cur, nxt, log_q + lbuf);
-                        cur = nxt;
-                        lbuf = (lbuf == 2u * Cfg::LOGB) ? 0u : lbuf + (uint32_t)Cfg::LOGB;
-                        if constexpr (SH) {
-                            if (++flush_ctr == Cfg::FLUSH) { flush_hist(); flush_ctr = 0; }
-                        }
-                    }
+                    // (one loop per MEAS value, the test at the bottom: the lone walker pays ~30 cycles for every taken
+                    // branch, and `if (meas) ... else ...` inside one loop cost it three of them per round)
+                    auto rounds = [&](auto meas_tag) {
+                        uint32_t left = bt.n;
+                        do {
+                            const uint32_t nxt = cur ^ (uint32_t)Cfg::BUF;
+                            full_round(meas_tag, cur, nxt, log_q + lbuf);
+                            cur = nxt;
+                            lbuf = (lbuf == 2u * Cfg::LOGB) ? 0u : lbuf + (uint32_t)Cfg::LOGB;
+                            if constexpr (SH) {
+                                if (++flush_ctr == Cfg::FLUSH) { flush_hist(); flush_ctr = 0; }
+                            }
+                        } while (--left);
+                    };
+                    if (meas) rounds(std::true_type{});
+                    else rounds(std::false_type{});
                     piped = true;
                     PF(pf_full)
                 } else {
