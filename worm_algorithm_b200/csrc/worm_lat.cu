@@ -721,7 +721,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         const int j_lo = (Cfg::RPL == 2) ? 2 * p_of : b / CH, j_hi = (Cfg::RPL == 2) ? 2 * p_of + 1 : b / CH;
         // the records of one Philox pair per lane into the current buffer
         auto build = [&](uint64_t pair) {
-#if WORM_LAT_FAKE
+#if WORM_LAT_FAKE   // measurement aid only (wrong random numbers): how much of the walker's step waits for the producers
             uint4 r = make_uint4((uint32_t)pair * 2654435761u, (uint32_t)pair * 40503u + c2, c2 * 2246822519u + (uint32_t)pair, c3 + (uint32_t)pair * 3266489917u);
             r.x ^= r.y >> 7; r.y ^= r.x << 9; r.z ^= r.w >> 5; r.w ^= r.z << 11;
 #else
