@@ -85,8 +85,8 @@ template <int CH, bool SH = false> struct LatCfg {
     static constexpr int REC_C = 4 * BUF;             // SH: byte offset of the C records (displacement update)
     static constexpr int RECW = (SH ? 6 : 4) * BUF;   // record bytes per walker warp
     static constexpr int LSTR = R + 4;                // pitch of a chain's log row (5 words: 32 lanes hit 32 banks)
-    static constexpr int LOGH = LSTR * CH;            // bytes of one accept (or closed) log of a round
-    static constexpr int LOGB = 2 * LOGH;             // one round's log: accept bytes, then closed bytes
+    static constexpr int LOGH = LSTR * CH;            // bytes of one round's log (one byte per step and chain)
+    static constexpr int LOGB = LOGH;
     static constexpr int LOGW = 3 * LOGB;             // three rounds in flight per walker warp
     static constexpr int PARTS = 32 / ACH;            // accountant lanes per chain
     static constexpr int SP = R / PARTS;              // steps per accountant lane per round
@@ -144,7 +144,7 @@ struct LatState {
     int head, tail;      // scaled site indices (site * SC)
     uint32_t closed;     // 0 / 1.  When 1, head already holds the (folded) kick of the coming step.
     uint32_t dh;         // solo mode with histograms: head - tail in bin-address format (0 iff closed)
-    uint32_t aword, cword;   // full rounds: accept / closed log bytes of up to four steps, stored as one word each
+    uint32_t aword;          // full rounds: log bytes of up to four steps, stored as one word
     uint32_t addr, nb;   // dual layout: shared address of the coming step's bond and its occupation, loaded
                          // at the end of the previous step (right behind that step's bond stores)
 };
@@ -154,7 +154,7 @@ struct LatState {
 // producer warp of the pair replays the log two rounds later (account_round below).
 //   accept log byte: 0x80 | (decrement ? 0x40 : 0) | (old occupation & 1, in bit 0 -- bit 4 when the occupation is
 //                    the high nibble of a site byte);  0 = rejected
-//   closed log byte: non-zero iff the worm was closed at the start of the step
+//                    bit 1: the worm was closed at the start of the step (set whether or not the move is accepted)
 struct Account {
     int Nb, npar;                        // state at the start of the next round to be replayed (all lanes of a chain)
     uint64_t Z, SNb, SNb2, Sn, Sn2;      // this lane's share of the sums
@@ -240,7 +240,7 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
 
 // One worm step on a pre-decoded record.  On entry `head` already holds this step's kick when the
 // worm is closed; on exit it holds the NEXT step's kick (kick_next) when the worm is closed then.
-// alog / clog: shared addresses of this step's accept / closed log bytes.
+// alog: shared address of this step's log byte.
 // LOGK < 0: the log bytes are stored one by one.  LOGK = 0..3 (full rounds, step j = LOGK mod 4): they are
 // gathered in two registers and stored as one 32-bit word each after every fourth step -- a lone warp issues
 // a shared-memory instruction every ~4 cycles, and the ones between the accept test and the next bond load
@@ -248,7 +248,7 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
 template <int ALGO, int LAY, int SCSH, bool HIST, bool SH, bool MEAS, int LOGK = -1>
 __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long hist_row, uint32_t hist_writer,
                                          LatState &c, const uint4 ra, const uint4 rb, const uint4 rc, const int kick_next,
-                                         const uint32_t p_next, const uint32_t alog, const uint32_t clog, const uint32_t dummy = 0u)
+                                         const uint32_t p_next, const uint32_t alog, const uint32_t dummy = 0u)
 {
     constexpr bool DUAL = (LAY == LAY_DUAL);
     const int add = (int)ra.x, keep = (int)ra.y;
@@ -293,11 +293,7 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
     // closed iteration (worm_ising_2d.cpp:130-132): logged, measured by the accountant.  After the
     // load in program order: a store ahead of it would sit on the load's issue path (the compiler
     // cannot reorder shared-memory accesses that may alias).
-    if constexpr (LOGK < 0)
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u8 [%1], %2;\n\t}"
-                     :: "r"(c.closed), "r"(clog), "r"(logbits) : "memory");
-    else
-        c.cword = (LOGK == 0 ? 0u : c.cword) + (c.closed << (8 * LOGK));
+    const uint32_t closed2 = c.closed << 1;                     // bit 1 of the step's log byte
     const uint32_t pc = (nh == tail) ? 1u : 0u;                 // closed after an accepted move?
     const int A = pc ? kick_next : nh;                          // head if accepted (kick folded in)
     const int B = closed ? kick_next : head;                    // head if rejected
@@ -312,7 +308,7 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
     int head_new;
     uint32_t acc_i;
     if constexpr (DUAL && LOGK < 0) {
-        asm volatile("{\n\t.reg .pred pa, pd;\n\t"
+        asm volatile("{\n\t.reg .pred pa, pd;\n\t.reg .b32 lb;\n\t"
                      "setp.lt.u32 pa, %4, %5;\n\t"
                      "setp.lt.s32 pd, %6, 0;\n\t"
                      "xor.pred pa, pa, pd;\n\t"
@@ -322,17 +318,19 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
                      "@pa st.shared.u8 [%9], %11;\n\t"
                      "@pa st.shared.u8 [%10], %11;\n\t"
                      "ld.shared.u8 %3, [%2];\n\t"
-                     "@pa st.shared.u8 [%12], %13;\n\t}"
+                     "selp.b32 lb, %13, 0, pa;\n\t"
+                     "or.b32 lb, lb, %15;\n\t"
+                     "st.shared.u8 [%12], lb;\n\t}"
                      : "=&r"(head_new), "=&r"(acc_i), "=&r"(c.addr), "=&r"(c.nb)
                      : "r"(nb), "r"(thrx), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(addr2), "r"(nn), "r"(alog), "r"(lg),
-                       "r"(p_next)
+                       "r"(p_next), "r"(closed2)
                      : "memory");
     } else if constexpr (DUAL) {
         // Full rounds.  The two bond stores are unpredicated and take their ADDRESS by select: a guard
         // predicate is ready ~13 cycles after its ISETP, a select operand after 4, and the next bond load has
         // to follow the stores (the next step may walk straight back).  A rejected move writes the occupation
         // it would have stored to `dummy`, the padding byte of the chain's log row.
-        uint32_t lgs = (LOGK == 0) ? 0u : c.aword;
+        uint32_t lgs = ((LOGK == 0) ? 0u : c.aword) + (closed2 << (8 * LOGK));
         asm volatile("{\n\t.reg .pred pa, pd;\n\t.reg .b32 nv, nw;\n\t"
                      "setp.lt.u32 pa, %5, %6;\n\t"
                      "setp.lt.s32 pd, %7, 0;\n\t"
@@ -364,25 +362,26 @@ __device__ __forceinline__ void lat_step(const LatGeo &g, unsigned long long his
                      : "=&r"(head_new), "=&r"(acc_i), "=&r"(lgs)
                      : "r"(nb), "r"(thrx), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(nn), "r"(lg)
                      : "memory");
-        c.aword = (LOGK == 0 ? 0u : c.aword) + (lgs << (8 * LOGK));
+        c.aword = (LOGK == 0 ? 0u : c.aword) + ((lgs | closed2) << (8 * LOGK));
     } else {
-        asm volatile("{\n\t.reg .pred pa, pd;\n\t"
+        asm volatile("{\n\t.reg .pred pa, pd;\n\t.reg .b32 lb;\n\t"
                      "setp.lt.u32 pa, %2, %3;\n\t"
                      "setp.lt.s32 pd, %4, 0;\n\t"
                      "xor.pred pa, pa, pd;\n\t"
                      "selp.b32 %0, %5, %6, pa;\n\t"
                      "selp.u32 %1, 1, 0, pa;\n\t"
                      "@pa st.shared.u8 [%7], %8;\n\t"
-                     "@pa st.shared.u8 [%9], %10;\n\t}"
+                     "selp.b32 lb, %10, 0, pa;\n\t"
+                     "or.b32 lb, lb, %11;\n\t"
+                     "st.shared.u8 [%9], lb;\n\t}"
                      : "=&r"(head_new), "=&r"(acc_i)
-                     : "r"(nb), "r"(thrx), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(nn), "r"(alog), "r"(lg)
+                     : "r"(nb), "r"(thrx), "r"(flip), "r"(A), "r"(B), "r"(addr), "r"(nn), "r"(alog), "r"(lg), "r"(closed2)
                      : "memory");
     }
     c.head = head_new;
     c.closed = acc_i ? pc : c.closed;
     if constexpr (LOGK == 3) {
         asm volatile("st.shared.u32 [%0], %1;" :: "r"(alog - 3u), "r"(c.aword) : "memory");
-        asm volatile("st.shared.u32 [%0], %1;" :: "r"(clog - 3u), "r"(c.cword) : "memory");
     }
     if constexpr (HIST && SH) {
         c.dh = acc_i ? dnew : c.dh;
@@ -406,18 +405,15 @@ __device__ __forceinline__ void account_round(Account &k, uint32_t logbuf_abs, i
     static_assert(SP == 4 || SP == 2, "a lane's steps are one 32- or 16-bit word of the chain's log row");
     // this lane's SP steps are consecutive bytes of the chain's row: one load per log, one store to clear
     const uint32_t row = logbuf_abs + (uint32_t)(q * Cfg::LSTR + part * SP);
-    uint32_t aw, cw;
+    uint32_t aw;
     if constexpr (SP == 4) {
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(aw) : "r"(row) : "memory");
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(row + Cfg::LOGH) : "memory");
         asm volatile("st.shared.u32 [%0], %1;" :: "r"(row), "r"(0u) : "memory");
-        asm volatile("st.shared.u32 [%0], %1;" :: "r"(row + Cfg::LOGH), "r"(0u) : "memory");
     } else {
         asm volatile("ld.shared.u16 %0, [%1];" : "=r"(aw) : "r"(row) : "memory");
-        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(cw) : "r"(row + Cfg::LOGH) : "memory");
         asm volatile("st.shared.u16 [%0], %1;" :: "r"(row), "r"(0u) : "memory");
-        asm volatile("st.shared.u16 [%0], %1;" :: "r"(row + Cfg::LOGH), "r"(0u) : "memory");
     }
+    const uint32_t cw = aw & 0x02020202u;                          // closed-at-start flags of the lane's steps
     int dNb[SP], dn[SP];
     int sNb = 0, sn = 0;
 #pragma unroll
@@ -850,7 +846,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         auto account = [&](const Pending &pr) {
             const uint32_t lb = log_w + lbuf_acc;
             if (pr.dump_first) {                                     // worm_ising_2d.cpp:113-119
-                const uint32_t was_closed = lds_u8(lb + Cfg::LOGH + (uint32_t)(aq * Cfg::LSTR + pr.jb));
+                const uint32_t was_closed = lds_u8(lb + (uint32_t)(aq * Cfg::LSTR + pr.jb)) & 2u;
                 uint64_t Z = k.Z, SNb = k.SNb;
 #pragma unroll
                 for (int o = ACH; o < 32; o <<= 1) {
@@ -1000,7 +996,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         c.closed = (c.head == c.tail) ? 1u : 0u;
         c.dh = 0u;
         c.addr = sbase; c.nb = 0u;
-        c.aword = c.cword = 0u;
+        c.aword = 0u;
         if constexpr (SH) {
             const int hs = a.head[cl], ts = a.tail[cl];
             const int dx = (hs - ts) & (g.L - 1);
@@ -1045,7 +1041,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 uint4 fc = make_uint4(0, 0, 0, 0);
                 if constexpr (SH) fc = lds_v4(nrec + Cfg::REC_C);
                 lat_step<ALGO, LAY, SCSH, SH, SH, MEAS, j % 4>(g, hist_row, hist_writer, c, p0a, p0b, p0c, (int)p1b.x, p1a.z,
-                                                              lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j), pad);
+                                                              lg + (uint32_t)j, pad);
                 p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
                 if constexpr (SH) { p0c = p1c; p1c = fc; }
             });
@@ -1065,7 +1061,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 uint4 fc = make_uint4(0, 0, 0, 0);
                 if constexpr (SH) fc = lds_v4(nrec + Cfg::REC_C);
                 lat_step<ALGO, LAY, SCSH, SH, SH, MEAS>(g, hist_row, hist_writer, c, p0a, p0b, p0c, (int)p1b.x, p1a.z,
-                                                       lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j));
+                                                       lg + (uint32_t)j);
                 p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
                 if constexpr (SH) { p0c = p1c; p1c = fc; }
             }
@@ -1085,7 +1081,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 uint4 xc = make_uint4(0, 0, 0, 0);
                 if constexpr (SH) xc = lds_v4(rec + Cfg::REC_C);
                 lat_step<ALGO, LAY, SCSH, SH, SH, MEAS>(g, hist_row, hist_writer, c, xa, xb, xc, (int)nb_.x, pn,
-                                                       lg + (uint32_t)j, lg + (uint32_t)(Cfg::LOGH + j));
+                                                       lg + (uint32_t)j);
             }
         };
 
@@ -1297,7 +1293,7 @@ LatPlan lat_plan_mode(int L, int CH, int algo, bool sh, int smem_optin)
     const int R = 32 * NP * (sh ? 1 : 2) / CH;
     const size_t histb = sh ? (size_t)CH * N * 2 : 0;
     const size_t recw = (size_t)(sh ? 6 : 4) * R * CH * 16;
-    const size_t logw = (size_t)3 * 2 * (R + 4) * CH;
+    const size_t logw = (size_t)3 * (R + 4) * CH;                 // LatCfg::LOGW: three rounds of one byte per step
     // Throughput = (chains in flight) / (cycles per step): of the (layout, walkers per block) pairs that
     // fit, take the one with the most chains per block; ties go to the layout with the fewest instructions in
     // front of the bond load (dual, then byte per bond, then the nibble layout, which masks its occupation).
