@@ -63,34 +63,31 @@ struct LatGeo {
     int rec_off;         // byte offset of the record rings inside dynamic shared memory
     int log_off;         // byte offset of the step logs
     int hist_off;        // byte offset of the 16-bit G(r) bins (solo mode with histograms)
+    int htab_off;        // ... and of the four displacement-update entries {add, keep, gap, -}, one per direction
     int HXF, HYF;        // x / y bit fields of a displacement in bin-address format (solo mode with histograms)
     int bad_off;         // nibble layout: byte offset of the per-chain "input does not fit 4 bits" flags
     int lowt;            // some chain has T < 1 (general record builder)
     int zero;            // 0 (a value the compiler cannot see through)
 };
 
-// SH: per-chain G(r) bins in shared memory (solo mode with histograms): rounds are half as long to
-// make room for them.
+// SH: per-chain G(r) bins in shared memory (solo mode with histograms), counted by the walker.
 template <int CH, bool SH = false> struct LatCfg {
     static constexpr int NP = (CH == 32) ? 8 : (CH == 8) ? 2 : 1;   // producer warps per walker
-    static constexpr int RPL = SH ? 1 : 2;            // step records a producer lane builds per round (one Philox block
-                                                      // holds two steps; SH: the two lanes of a pair both draw it and
-                                                      // build one record each -- eight steps per round need 256 records)
+    static constexpr int RPL = 2;                     // step records a producer lane builds per round (one Philox block holds two steps)
     static constexpr int ACH = (CH > 8) ? 8 : CH;     // chains per accountant warp
     static constexpr int NA = CH / ACH;               // accountant warps per walker
     static constexpr int GW = NP + NA + 1;            // warps of a group: producers, accountants, walker
     static constexpr int R = 32 * NP * RPL / CH;      // steps per chain per round
     static constexpr int BUF = R * CH * 16;           // bytes of one buffer of A (or B) records
     static constexpr int REC_B = 2 * BUF;             // byte offset of the B records (two buffers of A first)
-    static constexpr int REC_C = 4 * BUF;             // SH: byte offset of the C records (displacement update)
-    static constexpr int RECW = (SH ? 6 : 4) * BUF;   // record bytes per walker warp
+    static constexpr int RECW = 4 * BUF;              // record bytes per walker warp
     static constexpr int LSTR = R + 4;                // pitch of a chain's log row (5 words: 32 lanes hit 32 banks)
     static constexpr int LOGH = LSTR * CH;            // bytes of one round's log (one byte per step and chain)
     static constexpr int LOGB = LOGH;
     static constexpr int LOGW = 3 * LOGB;             // three rounds in flight per walker warp
     static constexpr int PARTS = 32 / ACH;            // accountant lanes per chain
     static constexpr int SP = R / PARTS;              // steps per accountant lane per round
-    static constexpr int FLUSH = 4096;                // SH: rounds between the walker's flushes of the 16-bit bins (FLUSH * R < 65536)
+    static constexpr int FLUSH = 2048;                // SH: rounds between the walker's flushes of the 16-bit bins (FLUSH * R < 65536)
 };
 
 // ---- shared memory by absolute 32-bit shared-window address.  All hot-loop accesses are volatile
@@ -170,15 +167,25 @@ struct Account {
 //        compact: p = addneg, q = address of bond byte (y bit) of site 0: the bond is owned by
 //                 own = (head & keep) | ((head + addneg) & ~keep) and lives at own + q
 //   rb = {kick, thr, delta, logbits}:  accept iff (nb < thr) xor (delta < 0);  Taylor: nb += delta (+1 / -1)
-//   rc = {addh, keeph, gaph, -} (solo mode with histograms): the same move applied to the displacement
+//   rc = {addh, keeph, gaph, -} (solo mode with histograms; a function of the direction only, so it is not a record
+//        word but one of four table entries the walker looks up by the direction bits of rb.w -- a third record
+//        word halved the round to fit beside the 64 KiB of bins): the same move applied to the displacement
 //        head - tail kept in bin-address format,  dh' = (dh & keeph) | (((dh | gaph) + addh) & ~keeph).
 //        Bin s = dy * L + dx of a chain lives at (s >> 1) * 128 + (s & 1) * 2 of the chain's bank, so
 //        the x field is bit 1 plus bits 7.. : a +x move fills the gap (bits 2..6) with ones so that the
 //        carry out of bit 1 reaches bit 7; a -x move borrows through the gap's zeros.
 // numf = float(kfix - 1) * (1 + 2^-18), rounded up (see the threshold computation below)
-template <int ALGO, int LAY, bool SH>
+// the displacement update of direction d (bits 31-30 of the step's second random word)
+__device__ __forceinline__ uint4 hist_entry(const LatGeo &g, uint32_t d)
+{
+    const bool ym = d & 1u, neg = d & 2u;
+    const int hstep = ym ? g.L * 64 : 2;
+    return make_uint4((uint32_t)(neg ? -hstep : hstep), ym ? ~(uint32_t)g.HYF : ~(uint32_t)g.HXF, (!ym && !neg) ? 0x7cu : 0u, 0u);
+}
+
+template <int ALGO, int LAY>
 __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &prm, const float numf, uint32_t a,
-                                            uint32_t b, uint32_t chain_abs, uint4 &ra, uint4 &rb, uint4 &rc)
+                                            uint32_t b, uint32_t chain_abs, uint4 &ra, uint4 &rb)
 {
     const uint32_t d = b >> 30;                                  // :137
     const bool ym = d & 1u, neg = d & 2u;
@@ -197,13 +204,6 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
     } else {
         ra.z = neg ? (uint32_t)add : 0u;
         ra.w = chain_abs;                                        // the owner site's byte
-    }
-    if constexpr (SH) {
-        const int hstep = ym ? g.L * 64 : 2;
-        rc.x = (uint32_t)(neg ? -hstep : hstep);
-        rc.y = ym ? ~(uint32_t)g.HYF : ~(uint32_t)g.HXF;
-        rc.z = (!ym && !neg) ? 0x7cu : 0u;
-        rc.w = 0u;
     }
     rb.x = (uint32_t)g.SC * __umulhi(b << 3, (uint32_t)g.N);     // kick site :128
     if constexpr (ALGO == ALGO_TAYLOR) {
@@ -687,6 +687,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         uint32_t *rr = reinterpret_cast<uint32_t *>(smem8 + g.rec_off);
         for (int i = tid; i < nw * Cfg::RECW / 4; i += nthreads) rr[i] = 0u;
         if constexpr (SH) {
+            if (tid < 4) *reinterpret_cast<uint4 *>(smem8 + g.htab_off + tid * 16) = hist_entry(g, (uint32_t)tid);
             uint32_t *hb = reinterpret_cast<uint32_t *>(smem8 + g.hist_off);
             for (int i = tid; i < CH * g.N / 2; i += nthreads) hb[i] = 0u;
         }
@@ -698,23 +699,21 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         // Philox block b = u*32 + lane of a round (u = role: the group's two producers take one
         // block each) belongs to chain slot q = b % CH, pair p = b / CH: consecutive lanes store
         // consecutive 16-byte records (conflict-free 128-bit stores).
-        // (SH: record b = u*32 + lane is step j = b / CH of the round, half j & 1 of pair j >> 1)
         const int b = u * 32 + lane;
         const int q = b % CH;
-        const int p_of = (Cfg::RPL == 2) ? b / CH : (b / CH) >> 1;
-        const int half = (b / CH) & 1;
+        const int p_of = b / CH;
         const int64_t cg = chain0 + w * CH + q;
         const int64_t cl = cg < a.n_chains ? cg : 0;
         const PhiloxChain prm = a.prm[cl];
         const uint64_t chain_id = a.chain_id0 + (uint64_t)cl;
         const uint32_t c2 = (uint32_t)chain_id, c3 = (uint32_t)(chain_id >> 32);
         const uint32_t chain_abs = region_abs + (DUAL ? (uint32_t)q * 4u : NIB ? (uint32_t)q : 0u);
-        const uint32_t rec_q = rec_w + (uint32_t)q * 16u + (uint32_t)(Cfg::RPL == 2 ? 2 * p_of : b / CH) * (CH * 16);
+        const uint32_t rec_q = rec_w + (uint32_t)q * 16u + (uint32_t)(2 * p_of) * (CH * 16);
         const PhiloxKeys keys = philox_keys((uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
         const float numf = __fmul_ru(__uint2float_ru((uint32_t)(prm.kfix - 1)), 1.0f + 1.0f / 262144.0f);
         uint32_t buf = 0u;
         // steps of a round this lane's record(s) serve: a short round (segment edge) is built by the lanes it needs
-        const int j_lo = (Cfg::RPL == 2) ? 2 * p_of : b / CH, j_hi = (Cfg::RPL == 2) ? 2 * p_of + 1 : b / CH;
+        const int j_lo = 2 * p_of, j_hi = 2 * p_of + 1;
         // the records of one Philox pair per lane into the current buffer
         auto build = [&](uint64_t pair) {
 #if WORM_LAT_FAKE   // measurement aid only (wrong random numbers): how much of the walker's step waits for the producers
@@ -724,17 +723,11 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             const uint4 r = philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), c2, c3, keys);
 #endif
             const uint32_t p0 = rec_q + buf;
-            if constexpr (Cfg::RPL == 2) {
-                uint4 ra0, rb0, rc0, ra1, rb1, rc1;
-                make_record<ALGO, LAY, SH>(g, prm, numf, r.x, r.y, chain_abs, ra0, rb0, rc0);
-                make_record<ALGO, LAY, SH>(g, prm, numf, r.z, r.w, chain_abs, ra1, rb1, rc1);
-                sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0);
-                sts_v4(p0 + CH * 16, ra1); sts_v4(p0 + CH * 16 + Cfg::REC_B, rb1);
-            } else {
-                uint4 ra0, rb0, rc0;
-                make_record<ALGO, LAY, SH>(g, prm, numf, half ? r.z : r.x, half ? r.w : r.y, chain_abs, ra0, rb0, rc0);
-                sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0); sts_v4(p0 + Cfg::REC_C, rc0);
-            }
+            uint4 ra0, rb0, ra1, rb1;
+            make_record<ALGO, LAY>(g, prm, numf, r.x, r.y, chain_abs, ra0, rb0);
+            make_record<ALGO, LAY>(g, prm, numf, r.z, r.w, chain_abs, ra1, rb1);
+            sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0);
+            sts_v4(p0 + CH * 16, ra1); sts_v4(p0 + CH * 16 + Cfg::REC_B, rb1);
         };
         const bool dump_even = a.dump_every != 0ull && (a.dump_every & 1ull) == 0ull;
         const int dump_full = (int)(a.dump_every / (uint64_t)R), dump_tail = (int)(a.dump_every % (uint64_t)R);
@@ -1027,7 +1020,10 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         // step j+2, which for the last two steps lives in the other buffer (complete once the pair
         // barrier has been passed).  On exit they hold the records of steps 0 / 1 of the next round.
         uint4 p0a, p0b, p1a, p1b;
-        uint4 p0c = make_uint4(0, 0, 0, 0), p1c = make_uint4(0, 0, 0, 0);      // SH only
+        uint4 p0c = make_uint4(0, 0, 0, 0);          // SH only: displacement update of the record in (p0a, p0b)
+        const uint32_t htab = sbase + (uint32_t)g.htab_off;
+        // (looked up one step ahead, from the direction bits of the next step's record -- already in registers)
+        auto hist_lookup = [&](uint32_t rbw) { return lds_v4(htab + ((rbw & 0xcu) << 2)); };
         auto full_round = [&](auto meas_tag, uint32_t cur, uint32_t nxt, uint32_t lg) {
             constexpr bool MEAS = decltype(meas_tag)::value;
             static_assert(R % 4 == 0, "log words hold four steps");
@@ -1039,11 +1035,11 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 const uint32_t nrec = (j < R - 2) ? rec_addr(cur, j + 2) : rec_addr(nxt, j + 2 - R);
                 const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
                 uint4 fc = make_uint4(0, 0, 0, 0);
-                if constexpr (SH) fc = lds_v4(nrec + Cfg::REC_C);
+                if constexpr (SH) fc = hist_lookup(p1b.w);
                 lat_step<ALGO, LAY, SCSH, SH, SH, MEAS, j % 4>(g, hist_row, hist_writer, c, p0a, p0b, p0c, (int)p1b.x, p1a.z,
                                                               lg + (uint32_t)j, pad);
                 p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
-                if constexpr (SH) { p0c = p1c; p1c = fc; }
+                if constexpr (SH) p0c = fc;
             });
         };
         // The short round that opens a dump interval (steps 0..r-1 of the buffer at `cur`, r even, 0 < r < R), software-
@@ -1059,11 +1055,11 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 if (j + 2 == r) group_barrier<Cfg::GW>(bar_id);
                 const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
                 uint4 fc = make_uint4(0, 0, 0, 0);
-                if constexpr (SH) fc = lds_v4(nrec + Cfg::REC_C);
+                if constexpr (SH) fc = hist_lookup(p1b.w);
                 lat_step<ALGO, LAY, SCSH, SH, SH, MEAS>(g, hist_row, hist_writer, c, p0a, p0b, p0c, (int)p1b.x, p1a.z,
                                                        lg + (uint32_t)j);
                 p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
-                if constexpr (SH) { p0c = p1c; p1c = fc; }
+                if constexpr (SH) p0c = fc;
             }
         };
         // Any other round (segment edges): steps [jb, je), records straight from shared memory.  The
@@ -1079,7 +1075,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 uint32_t pn = 0u;
                 if constexpr (DUAL) pn = lds_u32(nrec + 8u);         // ra.z of the next step's record
                 uint4 xc = make_uint4(0, 0, 0, 0);
-                if constexpr (SH) xc = lds_v4(rec + Cfg::REC_C);
+                if constexpr (SH) xc = hist_lookup(xb.w);
                 lat_step<ALGO, LAY, SCSH, SH, SH, MEAS>(g, hist_row, hist_writer, c, xa, xb, xc, (int)nb_.x, pn,
                                                        lg + (uint32_t)j);
             }
@@ -1108,7 +1104,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                     p0a = lds_v4(rec_addr(cur, 0)); p0b = lds_v4(rec_addr(cur, 0) + Cfg::REC_B);
                     p1a = lds_v4(rec_addr(cur, 1)); p1b = lds_v4(rec_addr(cur, 1) + Cfg::REC_B);
                     if constexpr (SH) {
-                        p0c = lds_v4(rec_addr(cur, 0) + Cfg::REC_C); p1c = lds_v4(rec_addr(cur, 1) + Cfg::REC_C);
+                        p0c = hist_lookup(p0b.w);
                     }
                     piped = true;
                 }
@@ -1160,7 +1156,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                         p0a = lds_v4(rec_addr(cur, 0)); p0b = lds_v4(rec_addr(cur, 0) + Cfg::REC_B);
                         p1a = lds_v4(rec_addr(cur, 1)); p1b = lds_v4(rec_addr(cur, 1) + Cfg::REC_B);
                         if constexpr (SH) {
-                            p0c = lds_v4(rec_addr(cur, 0) + Cfg::REC_C); p1c = lds_v4(rec_addr(cur, 1) + Cfg::REC_C);
+                            p0c = hist_lookup(p0b.w);
                         }
                     }
                     // (one loop per MEAS value, the test at the bottom: the lone walker pays ~30 cycles for every taken
@@ -1290,9 +1286,9 @@ LatPlan lat_plan_mode(int L, int CH, int algo, bool sh, int smem_optin)
     if (L < 4 || (L & (L - 1)) || (CH != 32 && CH != 8 && CH != 4 && CH != 1)) return p;
     const int N = L * L;
     const int NP = (CH == 32) ? 8 : (CH == 8) ? 2 : 1;
-    const int R = 32 * NP * (sh ? 1 : 2) / CH;
-    const size_t histb = sh ? (size_t)CH * N * 2 : 0;
-    const size_t recw = (size_t)(sh ? 6 : 4) * R * CH * 16;
+    const int R = 32 * NP * 2 / CH;
+    const size_t histb = sh ? (size_t)CH * N * 2 + 64 : 0;        // 16-bit bins + the four displacement-update entries
+    const size_t recw = (size_t)4 * R * CH * 16;                  // LatCfg::RECW
     const size_t logw = (size_t)3 * (R + 4) * CH;                 // LatCfg::LOGW: three rounds of one byte per step
     // Throughput = (chains in flight) / (cycles per step): of the (layout, walkers per block) pairs that
     // fit, take the one with the most chains per block; ties go to the layout with the fewest instructions in
@@ -1331,6 +1327,7 @@ LatPlan lat_plan_mode(int L, int CH, int algo, bool sh, int smem_optin)
             p.g.rec_off = (int)(nw * region);
             p.g.log_off = (int)(nw * (region + recw));
             p.g.hist_off = (int)((nw * (region + recw + logw) + 15) / 16 * 16);
+            p.g.htab_off = p.g.hist_off + (int)((size_t)CH * N * 2);
             p.g.bad_off = (int)body;
             p.g.HXF = 2 | ((L / 2 - 1) << 7);
             p.g.HYF = (L - 1) * L * 64;
