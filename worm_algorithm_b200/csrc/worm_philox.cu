@@ -22,9 +22,9 @@ int choose_philox_variant(int L, int algo, int64_t n_chains, bool hist, int smem
             if (!lat_info(L, g, algo, hist, smem_optin, &cb, &nw, &lay)) continue;
             if (g == 2 && n_chains < 64) continue;
             double cyc;
-            // G(r): the solo walker counts in shared-memory bins where they fit (L <= 32, +36 cycles), else the
+            // G(r): the solo walker counts in shared-memory bins where they fit (L <= 32, +14 cycles), else the
             // accountants replay the displacement (+34 next to a solo walker, a few cycles next to the groups)
-            if (g == 2) cyc = (lay == 0 ? 58.0 : 76.0) + (hist ? (L <= 32 ? 36.0 : 34.0) : 0.0);
+            if (g == 2) cyc = (lay == 0 ? 57.0 : 74.0) + (hist ? (L <= 32 ? 14.0 : 34.0) : 0.0);
             else {
                 const double base = (g == 4) ? 75.0 : (g == 8) ? 70.0 : 56.0;          // one group per block
                 cyc = base + 9.0 * (nw - 1) + (lay == 2 ? 4.0 : 0.0) + (hist ? 8.0 : 0.0);
