@@ -17,6 +17,12 @@ ncu --set full --clock-control none --import-source on -k regex:worm_lat -s 3 -c
 C3="python tools/pack_case.py 64 4096 50000 0 0 0"
 $C3 > gpurun_out/plain_nib.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:worm_lat -s 1 -c 1 -f -o gpurun_out/prof_nib $C3 > gpurun_out/ncu_nib.log 2>&1
+# latency kernel with G(r) in shared-memory bins (L = 32) -- summary only (the report would not fit the 64 MiB return limit)
+C6="python tools/pack_case.py 32 4096 50000 0 0 1"
+$C6 > gpurun_out/plain_sh.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:worm_lat -s 1 -c 1 -f -o /tmp/prof_sh $C6 > gpurun_out/ncu_sh.log 2>&1
+python tools/ncu_summary.py /tmp/prof_sh.ncu-rep gpurun_out/r02_sh_ncu_full.txt "round 2, tools/gpu_round2b.sh" > /dev/null 2>&1
+python tools/ncu_roles.py /tmp/prof_sh.ncu-rep > gpurun_out/r02_sh_roles.txt 2>&1
 python tools/dump_time.py > gpurun_out/dump_time.log 2>&1
 ls -la gpurun_out | head -40
 du -sh gpurun_out

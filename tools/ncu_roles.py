@@ -18,15 +18,18 @@ stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "N
 def iv(x):
     try: return int(x)
     except ValueError: return 0
-# the walker's unrolled round: find the LDS.U8 (bond load) instructions and take the contiguous address range around them
-lds = [k for k, r in enumerate(data) if "LDS.U8" in r[src] and iv(r[ex]) > 0]
-cnt = collections.Counter(iv(data[k][ex]) for k in lds)
-per_slot = max(cnt)                      # the steady-state loop has the largest count
-idx = [k for k in lds if iv(data[k][ex]) == per_slot]
-lo, hi2 = min(idx), max(idx)
-# widen to the loop: instructions executed exactly per_slot times around
-while lo > 0 and iv(data[lo - 1][ex]) == per_slot: lo -= 1
-while hi2 + 1 < len(data) and iv(data[hi2 + 1][ex]) == per_slot: hi2 += 1
+# the walker's unrolled round: a long contiguous run of instructions with one execution count that holds bond loads
+# (LDS.U8); staging / accountant loops also load bytes, but their runs are short
+best = (0, 0, 0)
+k = 0
+while k < len(data):
+    e = iv(data[k][ex]); j = k
+    while j + 1 < len(data) and iv(data[j + 1][ex]) == e: j += 1
+    if j - k + 1 >= 200 and e > best[0] and any("LDS.U8" in data[m][src] for m in range(k, j + 1)):
+        best = (e, k, j)                 # (among the long runs the steady-state loop is the one executed most often)
+    k = j + 1
+_, lo, hi2 = best
+per_slot = iv(data[lo][ex])
 sel = data[lo:hi2 + 1]
 tot = sum(iv(r[si]) for r in sel)
 print("walker hot loop: %d instructions (%.1f KB), executed %d times each, %d samples" % (len(sel), len(sel) * 16 / 1024, per_slot, tot))
