@@ -59,6 +59,7 @@ struct LatGeo {
     int nw;              // groups (walkers) per block
     int SC;              // bytes per unit of the scaled site index (dual: 4 * CH, compact: 2)
     int XM, YM;          // x / y bit fields of a scaled site index
+    int XP, XN;          // what a +x / -x move adds to a scaled site index (nibble layout: +x also fills the gap of the x field)
     int region;          // bytes of bond storage per walker warp
     int rec_off;         // byte offset of the record rings inside dynamic shared memory
     int log_off;         // byte offset of the step logs
@@ -175,6 +176,17 @@ struct Account {
 //        the x field is bit 1 plus bits 7.. : a +x move fills the gap (bits 2..6) with ones so that the
 //        carry out of bit 1 reaches bit 7; a -x move borrows through the gap's zeros.
 // numf = float(kfix - 1) * (1 + 2^-18), rounded up (see the threshold computation below)
+// Nibble layout: a chain's site bytes are kept in 4-byte columns, chain slot q of a walker in column q, so that lane q
+// only ever touches bank q (bytes interleaved chain by chain cost the solo walker 22 % of its cycles in bank
+// conflicts).  Site s of slot q lives at region + nib_fmt(s) + 4 q with nib_fmt(s) = (s >> 2) * 4 CH + (s & 3): the
+// scaled site index the walker carries.  Its x field is bits 0-1 plus the bits above the column index; a +x move adds
+// 1 + (the gap filled with ones), so that the carry out of bit 1 crosses the gap, a -x move borrows through the gap's zeros,
+// and the masked merge nh = (head & keep) | ((head + add) & ~keep) drops whatever the gap holds afterwards.
+template <int CH>
+__device__ __forceinline__ int nib_fmt(int s) { return (s >> 2) * (4 * CH) + (s & 3); }
+template <int CH>
+__device__ __forceinline__ int nib_site(int h) { return (h / (4 * CH)) * 4 + (h & 3); }
+
 // the displacement update of direction d (bits 31-30 of the step's second random word)
 __device__ __forceinline__ uint4 hist_entry(const LatGeo &g, uint32_t d)
 {
@@ -183,14 +195,14 @@ __device__ __forceinline__ uint4 hist_entry(const LatGeo &g, uint32_t d)
     return make_uint4((uint32_t)(neg ? -hstep : hstep), ym ? ~(uint32_t)g.HYF : ~(uint32_t)g.HXF, (!ym && !neg) ? 0x7cu : 0u, 0u);
 }
 
-template <int ALGO, int LAY>
+template <int ALGO, int LAY, int CH>
 __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &prm, const float numf, uint32_t a,
                                             uint32_t b, uint32_t chain_abs, uint4 &ra, uint4 &rb)
 {
     const uint32_t d = b >> 30;                                  // :137
     const bool ym = d & 1u, neg = d & 2u;
-    const int stepsz = ym ? g.L * g.SC : g.SC;
-    const int add = neg ? -stepsz : stepsz;
+    const int ystep = g.L * g.SC;
+    const int add = ym ? (neg ? -ystep : ystep) : (neg ? g.XN : g.XP);
     ra.x = (uint32_t)add;
     ra.y = ym ? ~(uint32_t)g.YM : ~(uint32_t)g.XM;
     constexpr bool DUAL = (LAY == LAY_DUAL);
@@ -205,7 +217,8 @@ __device__ __forceinline__ void make_record(const LatGeo &g, const PhiloxChain &
         ra.z = neg ? (uint32_t)add : 0u;
         ra.w = chain_abs;                                        // the owner site's byte
     }
-    rb.x = (uint32_t)g.SC * __umulhi(b << 3, (uint32_t)g.N);     // kick site :128
+    const uint32_t ksite = __umulhi(b << 3, (uint32_t)g.N);      // kick site :128
+    rb.x = (LAY == LAY_NIB) ? (uint32_t)nib_fmt<CH>((int)ksite) : (uint32_t)g.SC * ksite;
     if constexpr (ALGO == ALGO_TAYLOR) {
         const bool dec = (b >> 29) & 1u;                         // :141
         uint32_t qi, qd;
@@ -571,10 +584,11 @@ __device__ __noinline__ void lat_copy_dumps(unsigned dm, int lane, long long cl,
             for (int sI = lane; sI < N; sI += CH)
                 dst[sI] = (uint16_t)lds_u32(region_abs + (uint32_t)((sI * CH + src_lane) * 4));
         } else if constexpr (LAY == LAY_NIB) {
-            uint16_t *dst = reinterpret_cast<uint16_t *>(dstb);
-            for (int sI = lane; sI < N; sI += CH) {
-                const uint32_t v = lds_u8(region_abs + (uint32_t)(sI * CH + src_lane));
-                dst[sI] = (uint16_t)((v & 15u) | ((v >> 4) << 8));
+            uint2 *dst = reinterpret_cast<uint2 *>(dstb);       // four sites = one word of the chain's column = 8 bond bytes
+            for (int wI = lane; wI < N / 4; wI += CH) {
+                const uint32_t v = lds_u32(region_abs + (uint32_t)(wI * 4 * CH + src_lane * 4));
+                const uint32_t lo = v & 0x0f0f0f0fu, hi = (v >> 4) & 0x0f0f0f0fu;      // +x / +y occupations of the four sites
+                dst[wI] = make_uint2(__byte_perm(lo, hi, 0x5140), __byte_perm(lo, hi, 0x7362));
             }
         } else {
             uint4 *dst = reinterpret_cast<uint4 *>(dstb);
@@ -651,7 +665,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             dst[i] = (cg < a.n_chains) ? dual_word<CH>(a.bonds + cg * (int64_t)g.nb2, s, g.L, g.N) : 0u;
         }
     } else if constexpr (NIB) {
-        // byte (walker * N + s) * CH + q = occupations of site s of chain slot q: +x | +y << 4
+        // byte walker * region + nib_fmt(s) + 4 q = occupations of site s of chain slot q: +x | +y << 4
         uint8_t *bad = smem8 + g.bad_off;
         for (int i = tid; i < bch; i += nthreads) bad[i] = 0;
         __syncthreads();
@@ -664,7 +678,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             uint32_t xy = 0u;
             if (cg < a.n_chains) xy = *reinterpret_cast<const uint16_t *>(a.bonds + cg * (int64_t)g.nb2 + 2 * s);
             if (xy & 0xf0f0u) bad[wk * CH + q] = 1;              // an occupation above 15 does not fit
-            smem8[i] = (uint8_t)((xy & 15u) | ((xy >> 4) & 0xf0u));
+            smem8[wk * g.region + nib_fmt<CH>(s) + 4 * q] = (uint8_t)((xy & 15u) | ((xy >> 4) & 0xf0u));
         }
     } else {
         const int vec_per_chain = g.nb2 / 16;
@@ -707,7 +721,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         const PhiloxChain prm = a.prm[cl];
         const uint64_t chain_id = a.chain_id0 + (uint64_t)cl;
         const uint32_t c2 = (uint32_t)chain_id, c3 = (uint32_t)(chain_id >> 32);
-        const uint32_t chain_abs = region_abs + (DUAL ? (uint32_t)q * 4u : NIB ? (uint32_t)q : 0u);
+        const uint32_t chain_abs = region_abs + ((DUAL || NIB) ? (uint32_t)q * 4u : 0u);
         const uint32_t rec_q = rec_w + (uint32_t)q * 16u + (uint32_t)(2 * p_of) * (CH * 16);
         const PhiloxKeys keys = philox_keys((uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
         const float numf = __fmul_ru(__uint2float_ru((uint32_t)(prm.kfix - 1)), 1.0f + 1.0f / 262144.0f);
@@ -724,8 +738,8 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
 #endif
             const uint32_t p0 = rec_q + buf;
             uint4 ra0, rb0, ra1, rb1;
-            make_record<ALGO, LAY>(g, prm, numf, r.x, r.y, chain_abs, ra0, rb0);
-            make_record<ALGO, LAY>(g, prm, numf, r.z, r.w, chain_abs, ra1, rb1);
+            make_record<ALGO, LAY, CH>(g, prm, numf, r.x, r.y, chain_abs, ra0, rb0);
+            make_record<ALGO, LAY, CH>(g, prm, numf, r.z, r.w, chain_abs, ra1, rb1);
             sts_v4(p0, ra0); sts_v4(p0 + Cfg::REC_B, rb0);
             sts_v4(p0 + CH * 16, ra1); sts_v4(p0 + CH * 16 + Cfg::REC_B, rb1);
         };
@@ -813,7 +827,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 }
             } else if constexpr (NIB) {
                 for (int s = ap; s < g.N; s += Cfg::PARTS) {
-                    const uint32_t v = lds_u8(region_abs + (uint32_t)(s * CH + aq));
+                    const uint32_t v = lds_u8(region_abs + (uint32_t)(nib_fmt<CH>(s) + 4 * aq));
                     Nb += (int)((v & 15u) + (v >> 4));
                     npar += (int)((v & 1u) + ((v >> 4) & 1u));
                 }
@@ -908,7 +922,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             // against the replayed sum of occupations
             int sum = 0;
             for (int s = ap; s < g.N; s += Cfg::PARTS) {
-                const uint32_t v = lds_u8(region_abs + (uint32_t)(s * CH + aq));
+                const uint32_t v = lds_u8(region_abs + (uint32_t)(nib_fmt<CH>(s) + 4 * aq));
                 sum += (int)((v & 15u) + (v >> 4));
             }
 #pragma unroll
@@ -984,8 +998,8 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         int flush_ctr = 0;
 
         LatState c;
-        c.head = SC * a.head[cl];
-        c.tail = SC * a.tail[cl];
+        c.head = NIB ? nib_fmt<CH>(a.head[cl]) : SC * a.head[cl];
+        c.tail = NIB ? nib_fmt<CH>(a.tail[cl]) : SC * a.tail[cl];
         c.closed = (c.head == c.tail) ? 1u : 0u;
         c.dh = 0u;
         c.addr = sbase; c.nb = 0u;
@@ -1206,8 +1220,9 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
         flush_hist();
         if (live) {
             // a closed worm sits on its tail (head holds the folded kick of the step after the last)
-            a.head[cl] = (c.closed ? c.tail : c.head) / SC;
-            a.tail[cl] = c.tail / SC;
+            const int hf = c.closed ? c.tail : c.head;
+            a.head[cl] = NIB ? nib_site<CH>(hf) : hf / SC;
+            a.tail[cl] = NIB ? nib_site<CH>(c.tail) : c.tail / SC;
             if (a.n_dumps) a.n_dumps[cl] = nd;
         }
     }
@@ -1237,7 +1252,7 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
                 const int ws = i / CH;
                 const int wk = ws / g.N, s = ws - wk * g.N;
                 const int64_t cg = chain0 + wk * CH + q;
-                const uint32_t v = smem8[i];
+                const uint32_t v = smem8[wk * g.region + nib_fmt<CH>(s) + 4 * q];
                 if (cg < a.n_chains && !bad[wk * CH + q])
                     reinterpret_cast<uint16_t *>(a.bonds + cg * (int64_t)g.nb2)[s] = (uint16_t)((v & 15u) | ((v >> 4) << 8));
             }
@@ -1323,6 +1338,12 @@ LatPlan lat_plan_mode(int L, int CH, int algo, bool sh, int smem_optin)
             p.g.SC = sc;
             p.g.XM = (L - 1) * p.g.SC;
             p.g.YM = (L - 1) * L * p.g.SC;
+            p.g.XP = p.g.SC; p.g.XN = -p.g.SC;
+            if (lay == LAY_NIB) {            // column format (nib_fmt): x = bits 0-1 and the bits above the column index
+                p.g.XM = ((L / 4 - 1) * 4 * CH) | 3;
+                p.g.XP = 1 + 4 * (CH - 1);
+                p.g.XN = -1;
+            }
             p.g.region = (int)region;
             p.g.rec_off = (int)(nw * region);
             p.g.log_off = (int)(nw * (region + recw));
