@@ -16,13 +16,19 @@
 //   * the WALKER warp owns CH chains, one per lane (lanes beyond CH retire at once).  Records are
 //     fetched two steps ahead; the kick that follows a closing move is folded into the accept
 //     select; everything independent of the loaded occupation is forced into the load's shadow.
-//     It keeps no observables: it logs one byte per accepted step and one per closed step.
+//     It keeps no observables: it logs one byte per step (accepted / decrement / old parity / direction, and whether
+//     the worm was closed at the start of the step), four steps to a word.
 //   * ACCOUNTANT warps replay those logs two rounds later and accumulate Z, sum Nb, sum Nb^2,
 //     sum n, sum n^2 with the exact Nb / n of every closed step; they also write the dump events
 //     and, where the walker-side G(r) bins do not fit shared memory, the histogram: the accept log carries the move's
 //     direction, so the displacement head - tail is replayed like Nb and runs of equal bins are added with red.global
 //     (in solo mode at L <= 32 the walker itself counts in 16-bit shared-memory bins and sweeps them into HBM).
-//   The group meets at one named barrier per round.
+//   The group meets at one named barrier per round (16 steps per chain; 64 with one chain per walker).
+//   The walker is a LONE in-order warp: everything outside its unrolled round is cold code for it (~45 cycles for every
+//   instruction line it has to fetch, ~30 for every taken branch).  Hence one loop per MEAS value with the test at the
+//   bottom, and for the dump rule (worm_ising_2d.cpp:113-125, the step range is cut at every multiple of write_steps)
+//   tight steady-state loops over whole dump intervals in all three roles: pause, the interval's short round (first,
+//   built by the producer lanes it needs, walked by a pipelined rolled loop), its full rounds.
 //   CH = 32 ("solo"): one group per block -- the walker has an SM sub-partition to itself, 8 producers
 //   and 4 accountants share the other three.  CH = 8 / 4 / 1: up to four
 //   groups per block, the warps of a group on the same sub-partition (walker = highest warp id,
@@ -34,8 +40,8 @@
 // a warp), and an accepted move stores twice off the critical path.  Lattices whose dual layout
 // does not fit use the compact one-byte-per-bond layout (one chain per walker) or, for the Taylor chain, the
 // nibble layout: ONE BYTE PER SITE (+x occupation in the low nibble, +y in the high one; occupations 0..15, an
-// occupation that reaches 16 is reported in WORM_ACC_STATUS like in worm_pack.cu), bytes interleaved across the
-// 1 / 4 / 8 chains of a walker.  A quarter of the dual layout's bytes: 32 chains per SM at L = 64 instead of 12,
+// occupation that reaches 16 is reported in WORM_ACC_STATUS like in worm_pack.cu), the bytes of a chain in 4-byte
+// columns, one column (one bank) per chain of the walker (nib_fmt below).  A quarter of the dual layout's bytes: 32 chains per SM at L = 64 instead of 12,
 // 12 at L = 128 instead of 4, 3 at L = 256 instead of 1 -- chains in flight are what bounds a large lattice.
 // Power-of-two L only: the head is a scaled site index whose x and y bit fields wrap by masking.
 //
