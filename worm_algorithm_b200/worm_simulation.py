@@ -191,7 +191,7 @@ class WormSimulation(object):
         """The executable dumps at every closed multiple of write_steps (worm_ising_2d.cpp:113-125); here the
         first `max_dumps` per chain are kept.  Once every chain of the shard has them, the dump rule is switched
         off for the rest of the run: the trajectory does not depend on it (chunked runs are bit-identical), and
-        a segment boundary every write_steps steps costs ~45 % of the step rate (tools/dump_time.py)."""
+        a segment boundary every write_steps steps costs about a third of the step rate (tools/dump_time.py)."""
         dump_every = self._write_steps if max_dumps else 0
         left = int(self._num_steps)
         if not dump_every:
