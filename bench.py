@@ -446,7 +446,7 @@ def bench_shapes(torch, engine, dev, algo, issue_peak) -> list:
              (32, 125_000, 20_000, True, T_),
              (64, 4096, 100_000, False, algo), (64, 8288, 100_000, False, T_), (64, 32_768, 40_000, False, B_),
              (128, 1024, 100_000, False, algo), (128, 2072, 100_000, False, T_), (128, 8192, 100_000, False, B_),
-             (256, 512, 100_000, False, algo), (256, 2072, 100_000, False, B_)]
+             (256, 444, 100_000, False, algo), (256, 512, 100_000, False, algo), (256, 2072, 100_000, False, B_)]
     for L, n, steps, hist, al in cases:
         rate, variant, status = _time_run(torch, engine, dev, L, n, steps, al, hist)
         out.append({"L": L, "chains": n, "algo": "taylor" if al == T_ else "binary", "worm_steps_per_chain": steps,

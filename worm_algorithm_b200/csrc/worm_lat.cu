@@ -1049,18 +1049,32 @@ worm_lat_kernel(const PhiloxArgs a, const LatGeo g)
             static_assert(R % 4 == 0, "log words hold four steps");
             uint32_t pad = lg + (uint32_t)R;         // padding byte of the chain's log row: where a rejected move's stores go
             asm volatile("" : "+r"(pad));            // (a register, not base + immediate: one address for all steps)
-            unroll_steps(std::make_integer_sequence<int, R>{}, [&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                if (j == R - 2) group_barrier<Cfg::GW>(bar_id);
-                const uint32_t nrec = (j < R - 2) ? rec_addr(cur, j + 2) : rec_addr(nxt, j + 2 - R);
-                const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
-                uint4 fc = make_uint4(0, 0, 0, 0);
-                if constexpr (SH) fc = hist_lookup(p1b.w);
-                lat_step<ALGO, LAY, SCSH, SH, SH, MEAS, j % 4>(g, hist_row, hist_writer, c, p0a, p0b, p0c, (int)p1b.x, p1a.z,
-                                                              lg + (uint32_t)j, pad);
-                p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
-                if constexpr (SH) p0c = fc;
-            });
+            // U steps are unrolled; a round longer than that (one chain per walker: 64 steps) loops over chunks of U --
+            // 64 unrolled steps are 30 KB of code, which a lone warp streams from L2 on every round (~30 of its 100
+            // cycles per step); 16 stay in the 32 KB L1.5.  For R == U the chunk loop and its tests fold away.
+            constexpr int U = 16, NCH = R / U;
+            static_assert(R % U == 0, "rounds are whole chunks");
+#pragma unroll 1
+            for (int h = 0; h < NCH; ++h) {
+                const bool last = (NCH == 1) || (h == NCH - 1);
+                const uint32_t rb0 = cur + (uint32_t)(h * U * CH * 16);          // this chunk's records
+                const uint32_t rb1 = last ? nxt : rb0 + (uint32_t)(U * CH * 16);  // ... and the next chunk's
+                const uint32_t lgh = lg + (uint32_t)(h * U);
+                unroll_steps(std::make_integer_sequence<int, U>{}, [&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    if (j == U - 2) {
+                        if (last) group_barrier<Cfg::GW>(bar_id);
+                    }
+                    const uint32_t nrec = (j < U - 2) ? rec_addr(rb0, j + 2) : rec_addr(rb1, j + 2 - U);
+                    const uint4 fa = lds_v4(nrec), fb = lds_v4(nrec + Cfg::REC_B);
+                    uint4 fc = make_uint4(0, 0, 0, 0);
+                    if constexpr (SH) fc = hist_lookup(p1b.w);
+                    lat_step<ALGO, LAY, SCSH, SH, SH, MEAS, j % 4>(g, hist_row, hist_writer, c, p0a, p0b, p0c, (int)p1b.x, p1a.z,
+                                                                  lgh + (uint32_t)j, pad);
+                    p0a = p1a; p0b = p1b; p1a = fa; p1b = fb;
+                    if constexpr (SH) p0c = fc;
+                });
+            }
         };
         // The short round that opens a dump interval (steps 0..r-1 of the buffer at `cur`, r even, 0 < r < R), software-
         // pipelined like a full round: entered with the records of steps 0 / 1 in (p0, p1) -- the full round in front
