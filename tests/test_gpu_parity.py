@@ -240,11 +240,12 @@ def test_latency_kernel_nibble_layout_matches_oracle(eng, monkeypatch, L, tmin, 
     assert (a2[keep] == ref.acc.cpu().numpy()[keep]).all() and (st2.bonds.cpu().numpy()[keep] == ref.bonds.cpu().numpy()[keep]).all()
 
 
-def test_philox_random_batches_all_variants_agree(eng):
+@pytest.mark.parametrize("seed", [2024, 31337])
+def test_philox_random_batches_all_variants_agree(eng, seed):
     """Property test over launch geometry: random lattice, batch size, chunking, warm-up, dump period, chain and
     histogram options; every kernel variant that can run the batch (and whatever lanes_per_chain = 0 picks) must give the
     thread-per-chain byte kernel's result bit for bit -- that kernel is pinned to the oracle chain by chain above."""
-    rng = np.random.default_rng(2024)
+    rng = np.random.default_rng(seed)
     for case in range(24):
         L = int(rng.choice([4, 8, 16, 32, 64]))
         algo = int(rng.integers(0, 2))
@@ -254,7 +255,7 @@ def test_philox_random_batches_all_variants_agree(eng):
         T = rng.uniform(0.9 if case % 5 == 0 else 1.0, 3.6, nT)[gi]
         seeds = rng.integers(0, 2 ** 63, n, dtype=np.uint64)
         hist = bool(rng.integers(0, 2))
-        de = int(rng.choice([0, 1, 7, 50, 64]))
+        de = int(rng.choice([0, 1, 7, 50, 64] if seed == 2024 else [0, 2, 10, 48, 50, 100]))
         md = int(rng.integers(1, 6)) if de else 0
         chunks = [int(x) for x in rng.integers(1, 900, int(rng.integers(1, 4)))]
         therm = int(rng.integers(0, sum(chunks)))
