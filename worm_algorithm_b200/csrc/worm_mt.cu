@@ -146,6 +146,9 @@ worm_mt_kernel(int L, int64_t n_chains, const MtChain *__restrict__ prm,
     int64_t Nb_tot = 0;
     uint64_t step = 0, Z = 0;
     int32_t ne = 0, nt = 0;
+    // first multiple of 50 above therm: the event rule `step > therm && step % 50 == 0` (:113-114) without a 64-bit
+    // modulo on every closed iteration (a lone warp pays dearly for it)
+    uint64_t next50 = (therm / 50 + 1) * 50;
 
     for (;;) {
         // the (up to) four draws of this iteration, loaded together when they do not straddle a refill
@@ -164,7 +167,8 @@ worm_mt_kernel(int L, int64_t n_chains, const MtChain *__restrict__ prm,
         }
         uint32_t u_dir = r0, u_coin = r1, u_acc = r2;
         if (closed) {
-            if (step > therm && step % 50 == 0) {                             // :113-114
+            while (next50 < step) next50 += 50;                               // (open iterations pass multiples unseen)
+            if (step == next50) {                                             // :113-114  step > therm && step % 50 == 0
                 if (ne < max_events) {
                     if (events && lane == 0) {
                         int64_t *e = events + ((int64_t)c * max_events + ne) * 3;
@@ -217,16 +221,15 @@ worm_mt_kernel(int L, int64_t n_chains, const MtChain *__restrict__ prm,
         unsigned long long thr;
         if (nb < THR_N) thr = inc ? thr_inc[nb] : thr_dec[nb];
         else thr = inc ? thr_of(p.K / ((double)nb + 1.0)) : thr_of((double)nb * p.inv_K);
-        if ((unsigned long long)u_acc < thr) {                                // genrand() < P  :151
-            if (nb + delta > 255) { status = 1; }
-            else {
-                __syncwarp();
-                bonds[ib] = (uint8_t)(nb + delta);
-                __syncwarp();
-                Nb += delta;
-                head = nh;
-            }
-        }
+        // genrand() < P  :151.  Every lane walks the chain redundantly and stores the same byte itself, so a lane only ever
+        // reads what it has written: no warp synchronisation, and the update stays predicated (no branch).
+        const bool ok = (unsigned long long)u_acc < thr;
+        const bool over = ok && (nb + delta > 255);
+        const bool acc = ok && !over;
+        status = over ? 1 : status;
+        if (acc) bonds[ib] = (uint8_t)(nb + delta);
+        Nb += acc ? delta : 0;
+        head = acc ? nh : head;
         ++step;                                                               // :156
     }
     __syncwarp();
