@@ -1,4 +1,7 @@
 #!/bin/bash
-cp /tmp/x 2>/dev/null
-python tools/mt_time.py
-timeout 1500 python -m pytest tests -x -q -m gpu -k "mt or deterministic or reference or golden or tree or compat" 2>&1 | tail -3
+for v in "" _r2; do echo "variant [$v]"; if [ -n "$v" ]; then export WORM_B200_SO=$PWD/worm_algorithm_b200/libworm_b200$v.so; fi
+python tools/pack_case.py 32 4096 800000 0 0 0 | tail -1
+python tools/pack_case.py 32 4096 800000 0 0 0 | tail -1
+python tools/pack_case.py 64 4096 400000 0 0 0 | tail -1
+python tools/pack_case.py 32 4096 400000 0 0 1 | tail -1
+done
