@@ -417,13 +417,9 @@ def run_b200_arm(a) -> None:
 
 def _time_run(torch, engine, dev, L, n, steps, algo, hist, lanes=0):
     from worm_algorithm_b200 import _lib
-    t_idx = np.repeat(np.arange(N_T), -(-n // N_T))[:n]          # temperature-major: a block's chains share a temperature
-    seeds = (np.arange(n) % max(-(-n // N_T), 1)).astype(np.uint64)
-    if hist and n >= 16000:                                      # ... in super-blocks of 64 x 125 chains (bench_c5): the
-        cg = np.arange(n)                                        # histogram atomics of a moment spread over all rows
-        t_idx = (cg % 8000) // 125
-        seeds = ((cg // 8000) * 125 + cg % 125).astype(np.uint64)
+    t_idx = np.arange(n) % N_T                                   # chain c = seed * 64 + temperature (WormSimulation's numbering)
     T = sweep_temperatures()[t_idx]
+    seeds = (np.arange(n) // N_T).astype(np.uint64)
     st = engine.PhiloxState(L, T, seeds, algo=algo, device=dev, group_index=t_idx, n_groups=N_T, hist=hist)
     st.run(max(steps // 10, 1), lanes_per_chain=lanes)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -550,14 +546,13 @@ def bench_c5(torch, td, engine, dist, dev, rank, world, algo) -> dict:
     histograms.  Timed on the device, max over ranks; every rank checks G(0) = Z and sum of bins = iterations."""
     n_all, steps = 1_000_000, 20_000
     c0, c1 = dist.shard_range(n_all, rank, world)
-    # Global chain numbering (independent of the number of ranks): super-blocks of 64 temperatures x 125 seeds, temperature-
-    # major inside.  The chains of a warp share a temperature (7-13 % faster than one temperature per lane), and every
-    # rank's contiguous shard holds all 64 temperatures, so the histogram atomics of a moment spread over 64 rows (plain
-    # temperature-major numbering leaves 8 rows to each of 8 ranks: 1.5e11 instead of 1.9e11 steps/s per GPU).
+    # chain c = seed * 64 + temperature (WormSimulation's numbering, independent of the number of ranks): every rank's
+    # contiguous shard holds all 64 temperatures, so the histogram atomics of a moment spread over 64 rows (temperature-
+    # major numbering leaves 8 rows to each of 8 ranks: 1.5e11 instead of 1.9e11 steps/s per GPU)
     cg = np.arange(c0, c1)
-    t_idx = ((cg % 8000) // 125).astype(np.int32)
+    t_idx = (cg % N_T).astype(np.int32)
     T = sweep_temperatures()[t_idx]
-    seeds = ((cg // 8000) * 125 + cg % 125).astype(np.uint64)
+    seeds = (cg // N_T).astype(np.uint64)
     st = engine.PhiloxState(L_BENCH, T, seeds, algo=algo, chain_id0=c0, device=dev, group_index=t_idx, n_groups=N_T, hist=True)
     st.run(2_000)                                                             # warm-up launch (also thermalises)
     st.group_acc.zero_(); st.hist.zero_(); st.acc.zero_()

@@ -240,6 +240,23 @@ def test_latency_kernel_nibble_layout_matches_oracle(eng, monkeypatch, L, tmin, 
     assert (a2[keep] == ref.acc.cpu().numpy()[keep]).all() and (st2.bonds.cpu().numpy()[keep] == ref.bonds.cpu().numpy()[keep]).all()
 
 
+def test_philox_many_distinct_temperatures_match_oracle(eng):
+    """The per-chain fixed-point thresholds come from a small host-side table keyed by the bits of T (c_api.cu): more
+    distinct temperatures than it holds, interleaved so that equal temperatures are far apart, and a few repeats --
+    chains from the start, the middle (colliding keys) and beyond the table's capacity against the oracle."""
+    from oracle import worm_oracle as wo
+    L, n, steps = 4, 2100, 300
+    rng = np.random.default_rng(5)
+    T = rng.uniform(0.9, 3.6, n)
+    T[1::7] = T[0]                                  # one temperature repeated all over the batch
+    seeds = rng.integers(0, 2 ** 63, n, dtype=np.uint64)
+    st = eng.PhiloxState(L, T, seeds, algo=0).run(steps, therm_steps=30, lanes_per_chain=1)
+    acc, bonds = st.acc.cpu().numpy(), st.bonds.cpu().numpy()
+    for c in list(range(0, 40)) + list(range(760, 800)) + list(range(n - 40, n)):
+        o = wo.run_philox(L, 0, c, int(seeds[c]), float(T[c]), 0, steps, 30)
+        assert (acc[c, :6] == o["acc"][:6]).all() and (bonds[c] == o["bonds"]).all(), c
+
+
 @pytest.mark.parametrize("seed", [2024, 31337])
 def test_philox_random_batches_all_variants_agree(eng, seed):
     """Property test over launch geometry: random lattice, batch size, chunking, warm-up, dump period, chain and

@@ -239,23 +239,33 @@ int worm_philox_run(int L, int algo, int64_t n_chains, uint64_t chain_id0,
     if (int rc = current_device_info(dev)) return rc;
     std::vector<worm::PhiloxChain> prm((size_t)n_chains);
     // a sweep has few distinct temperatures, in any order: the fixed-point constants (ceil / ldexp / tanh)
-    // are computed once per temperature, looked up by the bits of T in a small direct-mapped table
+    // are computed once per temperature, looked up by the bits of T in a small open-addressed table (linear
+    // probing: a direct-mapped one let two temperatures of an interleaved sweep evict each other chain after
+    // chain -- 64 temperatures collide somewhere in 1024 slots more often than not -- which cost 30 ms of host
+    // time per launch on a 10^6-chain batch); when it fills up, the rest is computed directly
     struct Slot { uint64_t bits; uint64_t k, t, h; bool used; };
-    std::vector<Slot> slots(1024, Slot{0, 0, 0, 0, false});
+    constexpr size_t NSLOT = 1024, MAXFILL = 768;
+    std::vector<Slot> slots(NSLOT, Slot{0, 0, 0, 0, false});
+    size_t filled = 0;
     bool lowt = false;            // some chain outside the T >= 1 fast path of the kernels
     for (int64_t c = 0; c < n_chains; ++c) {
         const double T = h_T[c];
         uint64_t bits;
         memcpy(&bits, &T, sizeof bits);
-        Slot &sl = slots[(size_t)((bits * 0x9E3779B97F4A7C15ull) >> 54)];
-        if (!sl.used || sl.bits != bits) {
+        size_t i = (size_t)((bits * 0x9E3779B97F4A7C15ull) >> 54);
+        while (slots[i].used && slots[i].bits != bits) i = (i + 1) & (NSLOT - 1);
+        Slot tmp{bits, 0, 0, 0, true};
+        Slot *sl = &slots[i];
+        if (!sl->used) {
             if (bad_T(T)) return fail(WORM_E_ARG, "temperature[%lld] = %g out of range", (long long)c, T);
-            thresholds(T, sl.k, sl.t, sl.h);
-            sl.bits = bits;
-            sl.used = true;
-            if (sl.k > 0x100000000ull || sl.t < 0x100000000ull) lowt = true;
+            if (filled >= MAXFILL) sl = &tmp;                    // table full: do not insert
+            else ++filled;
+            thresholds(T, sl->k, sl->t, sl->h);
+            sl->bits = bits;
+            sl->used = true;
+            if (sl->k > 0x100000000ull || sl->t < 0x100000000ull) lowt = true;
         }
-        prm[(size_t)c] = worm::PhiloxChain{sl.k, sl.t, sl.h, h_seed[c]};
+        prm[(size_t)c] = worm::PhiloxChain{sl->k, sl->t, sl->h, h_seed[c]};
     }
     cudaStream_t st = (cudaStream_t)stream;
     worm::PhiloxChain *d_prm = (worm::PhiloxChain *)d_workspace;
